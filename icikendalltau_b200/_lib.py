@@ -1,0 +1,272 @@
+"""ctypes binding of libicikt_b200.so (the C ABI in include/icikt_b200.h).
+
+The library is the product's only compute path.  If it is missing, or no CUDA device is
+usable, every call raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicikt_b200.so")
+
+OK = 0
+ERR_NO_DEVICE, ERR_BAD_ARG, ERR_TOO_LONG, ERR_CUDA, ERR_ALLOC = -1, -2, -3, -4, -5
+NCOUNTS = 7
+KERNEL_TILED, KERNEL_NAIVE = 0, 1
+PERSPECTIVE = {"global": 0, "local": 1}
+ALTERNATIVE = {"two.sided": 0, "less": 1, "greater": 2}
+
+# every symbol include/icikt_b200.h declares (checked by tests/test_abi_cpu.py)
+EXPORTS = [
+    "icikt_default_opts", "icikt_abi_version", "icikt_device_count", "icikt_max_n",
+    "icikt_last_error", "icikt_all_pairs", "icikt_pair_list", "icikt_plan_create",
+    "icikt_plan_num_pairs", "icikt_plan_upload", "icikt_plan_set_device_matrix",
+    "icikt_plan_columns", "icikt_plan_pairs", "icikt_plan_sync", "icikt_plan_download",
+    "icikt_plan_column_info", "icikt_plan_stream", "icikt_plan_timings", "icikt_plan_destroy",
+    "icikt_pnorm_device",
+]
+
+
+class IciktError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libicikt_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Opts(ctypes.Structure):
+    _fields_ = [("perspective", ctypes.c_int32), ("alternative", ctypes.c_int32),
+                ("continuity", ctypes.c_int32), ("include_diag", ctypes.c_int32),
+                ("na_inf", ctypes.c_int32), ("device", ctypes.c_int32),
+                ("kernel", ctypes.c_int32), ("want_counts", ctypes.c_int32),
+                ("pair_lo", ctypes.c_int64), ("pair_hi", ctypes.c_int64)]
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [("h2d_ms", ctypes.c_float), ("columns_ms", ctypes.c_float),
+                ("pairs_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
+                ("total_ms", ctypes.c_float), ("n_launches", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_lp = ctypes.POINTER(ctypes.c_int64)
+
+
+def load():
+    """Load the shared library; raises if it has not been built (python -m icikendalltau_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IciktError(ERR_NO_DEVICE, f"{LIB_PATH} is missing: build it with "
+                         "`python -m icikendalltau_b200.build` (nvcc, sm_100a); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    L.icikt_default_opts.argtypes = [ctypes.POINTER(Opts)]
+    L.icikt_default_opts.restype = None
+    L.icikt_abi_version.restype = ctypes.c_int
+    L.icikt_device_count.restype = ctypes.c_int
+    L.icikt_max_n.restype = ctypes.c_int64
+    L.icikt_last_error.restype = ctypes.c_char_p
+    common_out = [_dp, _dp, _dp, _dp, _ip, _lp, _dp, ctypes.POINTER(Timings)]
+    L.icikt_all_pairs.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
+                                  ctypes.c_int32, ctypes.POINTER(Opts)] + common_out
+    L.icikt_all_pairs.restype = ctypes.c_int
+    L.icikt_pair_list.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
+                                  ctypes.c_int32, _ip, _ip, ctypes.c_int64,
+                                  ctypes.POINTER(Opts)] + common_out
+    L.icikt_pair_list.restype = ctypes.c_int
+    L.icikt_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int64, ctypes.c_int64, _ip, _ip,
+                                    ctypes.c_int64, ctypes.POINTER(Opts)]
+    L.icikt_plan_create.restype = ctypes.c_int
+    L.icikt_plan_num_pairs.argtypes = [vp]
+    L.icikt_plan_num_pairs.restype = ctypes.c_int64
+    L.icikt_plan_upload.argtypes = [vp, _dp, ctypes.c_int64]
+    L.icikt_plan_upload.restype = ctypes.c_int
+    L.icikt_plan_set_device_matrix.argtypes = [vp, vp, ctypes.c_int64]
+    L.icikt_plan_set_device_matrix.restype = ctypes.c_int
+    L.icikt_plan_columns.argtypes = [vp, _dp, ctypes.c_int32]
+    L.icikt_plan_columns.restype = ctypes.c_int
+    L.icikt_plan_pairs.argtypes = [vp]
+    L.icikt_plan_pairs.restype = ctypes.c_int
+    L.icikt_plan_sync.argtypes = [vp]
+    L.icikt_plan_sync.restype = ctypes.c_int
+    L.icikt_plan_download.argtypes = [vp, _dp, _dp, _dp, _dp, _ip, _lp, _dp]
+    L.icikt_plan_download.restype = ctypes.c_int
+    L.icikt_plan_column_info.argtypes = [vp, _ip]
+    L.icikt_plan_column_info.restype = ctypes.c_int
+    L.icikt_plan_stream.argtypes = [vp]
+    L.icikt_plan_stream.restype = vp
+    L.icikt_plan_timings.argtypes = [vp, ctypes.POINTER(Timings)]
+    L.icikt_plan_timings.restype = ctypes.c_int
+    L.icikt_plan_destroy.argtypes = [vp]
+    L.icikt_plan_destroy.restype = None
+    L.icikt_pnorm_device.argtypes = [_dp, ctypes.c_int64, ctypes.c_int32, _dp, ctypes.c_int32]
+    L.icikt_pnorm_device.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise IciktError(rc, load().icikt_last_error().decode(errors="replace"))
+
+
+def make_opts(perspective="global", alternative="two.sided", continuity=False, include_diag=False,
+              na_inf=False, device=0, kernel=KERNEL_TILED, want_counts=False, pair_lo=0, pair_hi=0):
+    o = Opts()
+    load().icikt_default_opts(ctypes.byref(o))
+    o.perspective = PERSPECTIVE.get(perspective, 0)   # any other string behaves as global
+    o.alternative = ALTERNATIVE.get(alternative, 3)   # unknown alternative: p-value stays 0
+    o.continuity = int(bool(continuity))
+    o.include_diag = int(bool(include_diag))
+    o.na_inf = int(bool(na_inf))
+    o.device = int(device)
+    o.kernel = int(kernel)
+    o.want_counts = int(bool(want_counts))
+    o.pair_lo, o.pair_hi = int(pair_lo), int(pair_hi)
+    return o
+
+
+def _global_na_array(global_na):
+    g = np.ascontiguousarray(np.asarray(list(global_na), dtype=np.float64))
+    return g, (g.ctypes.data_as(_dp) if g.size else None), int(g.size)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, **opt_kw):
+    """One-shot call through icikt_all_pairs / icikt_pair_list with host buffers.
+
+    data: (n, C) array (copied to Fortran order if needed).  Returns a dict of NumPy arrays in
+    pair order: raw, pvalue, taumax, completeness, status, [counts], max_taumax, timings.
+    """
+    L = load()
+    data = np.asfortranarray(data, dtype=np.float64)
+    if data.ndim != 2:
+        raise ValueError("data must be a 2-D array (features x samples)")
+    n, C = data.shape
+    o = make_opts(want_counts=want_counts, **opt_kw)
+    if pi is None:
+        ptot = C * (C - 1) // 2 + (C if o.include_diag else 0)
+        lo, hi = o.pair_lo, o.pair_hi
+        P = ptot if (lo == 0 and hi == 0) else hi - lo
+    else:
+        pi = np.ascontiguousarray(pi, dtype=np.int32)
+        pj = np.ascontiguousarray(pj, dtype=np.int32)
+        P = int(pi.size)
+    raw, pv, tm, comp = (np.empty(max(P, 0), dtype=np.float64) for _ in range(4))
+    status = np.empty(max(P, 0), dtype=np.int32)
+    counts = np.empty((max(P, 0), NCOUNTS), dtype=np.int64) if want_counts else None
+    mx = ctypes.c_double(float("nan"))
+    t = Timings()
+    g, gp, ng = _global_na_array(global_na)
+    if pi is None:
+        rc = L.icikt_all_pairs(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), _ptr(raw, _dp),
+                               _ptr(pv, _dp), _ptr(tm, _dp), _ptr(comp, _dp), _ptr(status, _ip),
+                               _ptr(counts, _lp), ctypes.byref(mx), ctypes.byref(t))
+    else:
+        rc = L.icikt_pair_list(_ptr(data, _dp), n, C, n, gp, ng, _ptr(pi, _ip), _ptr(pj, _ip), P,
+                               ctypes.byref(o), _ptr(raw, _dp), _ptr(pv, _dp), _ptr(tm, _dp),
+                               _ptr(comp, _dp), _ptr(status, _ip), _ptr(counts, _lp),
+                               ctypes.byref(mx), ctypes.byref(t))
+    check(rc)
+    out = dict(raw=raw, pvalue=pv, taumax=tm, completeness=comp, status=status,
+               max_taumax=mx.value, timings=t.as_dict())
+    if want_counts:
+        out["counts"] = counts
+    return out
+
+
+class Plan:
+    """Thin RAII wrapper of the plan API (device-resident matrix, tables and results)."""
+
+    def __init__(self, n, C, pi=None, pj=None, **opt_kw):
+        self._L = load()
+        self._h = ctypes.c_void_p()
+        self.opts = make_opts(**opt_kw)
+        if pi is not None:
+            self._pi = np.ascontiguousarray(pi, dtype=np.int32)
+            self._pj = np.ascontiguousarray(pj, dtype=np.int32)
+            check(self._L.icikt_plan_create(ctypes.byref(self._h), n, C, _ptr(self._pi, _ip),
+                                            _ptr(self._pj, _ip), self._pi.size, ctypes.byref(self.opts)))
+        else:
+            check(self._L.icikt_plan_create(ctypes.byref(self._h), n, C, None, None, 0,
+                                            ctypes.byref(self.opts)))
+        self.n, self.C = n, C
+        self.P = int(self._L.icikt_plan_num_pairs(self._h))
+
+    def upload(self, data):
+        data = np.asfortranarray(data, dtype=np.float64)
+        assert data.shape == (self.n, self.C)
+        check(self._L.icikt_plan_upload(self._h, _ptr(data, _dp), self.n))
+        self.sync()  # the host array may go away
+
+    def set_device_matrix(self, data_ptr, ld):
+        check(self._L.icikt_plan_set_device_matrix(self._h, ctypes.c_void_p(int(data_ptr)), int(ld)))
+
+    def columns(self, global_na=()):
+        g, gp, ng = _global_na_array(global_na)
+        check(self._L.icikt_plan_columns(self._h, gp, ng))
+
+    def pairs(self):
+        check(self._L.icikt_plan_pairs(self._h))
+
+    def sync(self):
+        check(self._L.icikt_plan_sync(self._h))
+
+    def stream(self):
+        return int(self._L.icikt_plan_stream(self._h) or 0)
+
+    def download(self, want_counts=False):
+        P = self.P
+        raw, pv, tm, comp = (np.empty(P, dtype=np.float64) for _ in range(4))
+        status = np.empty(P, dtype=np.int32)
+        counts = np.empty((P, NCOUNTS), dtype=np.int64) if want_counts else None
+        mx = ctypes.c_double(float("nan"))
+        check(self._L.icikt_plan_download(self._h, _ptr(raw, _dp), _ptr(pv, _dp), _ptr(tm, _dp),
+                                          _ptr(comp, _dp), _ptr(status, _ip), _ptr(counts, _lp),
+                                          ctypes.byref(mx)))
+        out = dict(raw=raw, pvalue=pv, taumax=tm, completeness=comp, status=status, max_taumax=mx.value)
+        if want_counts:
+            out["counts"] = counts
+        return out
+
+    def column_n_na(self):
+        a = np.empty(self.C, dtype=np.int32)
+        check(self._L.icikt_plan_column_info(self._h, _ptr(a, _ip)))
+        return a
+
+    def timings(self):
+        t = Timings()
+        check(self._L.icikt_plan_timings(self._h, ctypes.byref(t)))
+        return t.as_dict()
+
+    def close(self):
+        if self._h:
+            self._L.icikt_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pnorm_device(z, lower_tail=True, device=0):
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    out = np.empty_like(z)
+    check(load().icikt_pnorm_device(_ptr(z, _dp), z.size, int(bool(lower_tail)), _ptr(out, _dp), device))
+    return out

@@ -1,0 +1,545 @@
+// icikt_capi.cu -- host side of libicikt_b200.so: the C ABI declared in include/icikt_b200.h.
+// Owns device memory, the stream, the pair-unit table and the CUDA-event timings; all
+// arithmetic lives in icikt_columns.cu / icikt_pairs.cu.  There is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/icikt_b200.h"
+#include "icikt_internal.h"
+
+using namespace icikt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return ICIKT_ERR_CUDA;
+}
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+int64_t tri_pairs(int64_t C) { return C * (C - 1) / 2; }
+int64_t row_start(int64_t i, int64_t C) { return i * (2 * C - i - 1) / 2; }
+
+}  // namespace
+
+struct icikt_plan {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  int64_t n = 0, C = 0, P = 0;
+  icikt_opts opts{};
+  bool want_counts = false;
+
+  double* d_data_own = nullptr;
+  const double* d_data = nullptr;
+  int64_t ld = 0;
+  double* d_global_na = nullptr;
+
+  ColumnTables tab;
+  ColumnWork wk;
+  bool columns_done = false;
+
+  std::vector<PairUnit> units;
+  PairUnit* d_units = nullptr;
+  int32_t* d_pj = nullptr;
+  PairRaw* d_raw = nullptr;
+  double *d_tau = nullptr, *d_p = nullptr, *d_tm = nullptr, *d_comp = nullptr;
+  int32_t* d_status = nullptr;
+  int64_t* d_counts = nullptr;
+  unsigned long long* d_scalars = nullptr;  // [0] unit counter, [1] max taumax bits
+  uint32_t* d_naive = nullptr;
+  int64_t naive_threads = 0;
+
+  cudaEvent_t ev[8]{};
+  icikt_timings tm{};
+};
+
+namespace {
+
+void free_plan(icikt_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_data_own);
+  cudaFree(p->d_global_na);
+  cudaFree(p->tab.perm);
+  cudaFree(p->tab.rank);
+  cudaFree(p->tab.trow);
+  cudaFree(p->tab.trun);
+  cudaFree(p->tab.nabits);
+  cudaFree(p->tab.firstbits);
+  cudaFree(p->tab.grpstart);
+  cudaFree(p->tab.stats);
+  cudaFree(p->wk.keys_in);
+  cudaFree(p->wk.keys_out);
+  cudaFree(p->wk.vals_in);
+  cudaFree(p->wk.gpos);
+  cudaFree(p->wk.seg_begin);
+  cudaFree(p->wk.seg_end);
+  cudaFree(p->wk.cub_temp);
+  cudaFree(p->d_units);
+  cudaFree(p->d_pj);
+  cudaFree(p->d_raw);
+  cudaFree(p->d_tau);
+  cudaFree(p->d_p);
+  cudaFree(p->d_tm);
+  cudaFree(p->d_comp);
+  cudaFree(p->d_status);
+  cudaFree(p->d_counts);
+  cudaFree(p->d_scalars);
+  cudaFree(p->d_naive);
+  for (auto& e : p->ev)
+    if (e) cudaEventDestroy(e);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+// Split the pair order into units: consecutive pairs that share their first column.
+int build_units(icikt_plan* p, const int32_t* pi, const int32_t* pj, int64_t P_list) {
+  const int64_t C = p->C;
+  std::vector<PairUnit>& U = p->units;
+  U.clear();
+  const int64_t slots = (int64_t)p->n_sm * 2;
+  if (!pi) {
+    const int64_t ptri = tri_pairs(C);
+    const int64_t ptot = ptri + (p->opts.include_diag ? C : 0);
+    int64_t lo = p->opts.pair_lo, hi = p->opts.pair_hi;
+    if (lo == 0 && hi == 0) hi = ptot;
+    if (lo < 0 || hi > ptot || lo > hi) return fail(ICIKT_ERR_BAD_ARG, "pair_lo/pair_hi out of range");
+    p->P = hi - lo;
+    int64_t ulen = p->P / (16 * slots);
+    ulen = std::max<int64_t>(1, std::min<int64_t>(16, ulen));
+    for (int64_t i = 0; i + 1 < C; ++i) {
+      const int64_t rs = row_start(i, C), re = rs + (C - 1 - i);
+      const int64_t a = std::max(rs, lo), b = std::min(re, hi);
+      for (int64_t s = a; s < b; s += ulen) {
+        PairUnit u;
+        u.slot0 = s - lo;
+        u.col = (int32_t)i;
+        u.j0 = (int32_t)(i + 1 + (s - rs));
+        u.count = (int32_t)std::min<int64_t>(ulen, b - s);
+        u.j_explicit = 0;
+        U.push_back(u);
+      }
+      if (re >= hi) break;
+    }
+    if (p->opts.include_diag) {
+      for (int64_t i = 0; i < C; ++i) {
+        const int64_t s = ptri + i;
+        if (s < lo || s >= hi) continue;
+        PairUnit u;
+        u.slot0 = s - lo;
+        u.col = (int32_t)i;
+        u.j0 = (int32_t)i;
+        u.count = 1;
+        u.j_explicit = 0;
+        U.push_back(u);
+      }
+    }
+  } else {
+    p->P = P_list;
+    for (int64_t k = 0; k < P_list; ++k)
+      if (pi[k] < 0 || pi[k] >= C || pj[k] < 0 || pj[k] >= C)
+        return fail(ICIKT_ERR_BAD_ARG, "pair index out of range");
+    int64_t ulen = P_list / (16 * slots);
+    ulen = std::max<int64_t>(1, std::min<int64_t>(16, ulen));
+    int64_t k = 0;
+    while (k < P_list) {
+      int64_t e = k + 1;
+      while (e < P_list && e - k < ulen && pi[e] == pi[k]) ++e;
+      PairUnit u;
+      u.slot0 = k;
+      u.col = pi[k];
+      u.j0 = pj[k];
+      u.count = (int32_t)(e - k);
+      u.j_explicit = 1;
+      U.push_back(u);
+      k = e;
+    }
+  }
+  return ICIKT_OK;
+}
+
+int select_device(int device) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt < 1) {
+    cudaGetLastError();
+    return fail(ICIKT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= cnt) return fail(ICIKT_ERR_BAD_ARG, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  return ICIKT_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+void icikt_default_opts(icikt_opts* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->perspective = ICIKT_PERSPECTIVE_GLOBAL;
+  o->alternative = ICIKT_ALT_TWO_SIDED;
+  o->kernel = ICIKT_KERNEL_TILED;
+}
+
+int icikt_abi_version(void) { return ICIKT_ABI_VERSION; }
+
+int icikt_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return cnt;
+}
+
+int64_t icikt_max_n(void) { return tiled_max_n(); }
+
+const char* icikt_last_error(void) { return g_err.c_str(); }
+
+int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi, const int32_t* pj,
+                      int64_t P, const icikt_opts* opts_in) {
+  if (!out) return fail(ICIKT_ERR_BAD_ARG, "plan pointer is NULL");
+  *out = nullptr;
+  if (n < 1 || C < 1) return fail(ICIKT_ERR_BAD_ARG, "n and C must be >= 1");
+  if ((pi == nullptr) != (pj == nullptr)) return fail(ICIKT_ERR_BAD_ARG, "pi and pj must both be given");
+  if (pi && P < 1) return fail(ICIKT_ERR_BAD_ARG, "empty pair list");
+  if (n > tiled_max_n()) return fail(ICIKT_ERR_TOO_LONG, "n exceeds icikt_max_n()");
+  if (C > 2147483647LL) return fail(ICIKT_ERR_BAD_ARG, "too many columns");
+  icikt_opts o;
+  if (opts_in) o = *opts_in; else icikt_default_opts(&o);
+  int rc = select_device(o.device);
+  if (rc != ICIKT_OK) return rc;
+
+  icikt_plan* p = new (std::nothrow) icikt_plan();
+  if (!p) return fail(ICIKT_ERR_ALLOC, "out of host memory");
+  p->device = o.device;
+  p->opts = o;
+  p->want_counts = o.want_counts != 0;
+  p->n = n;
+  p->C = C;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess) { free_plan(p); return fail(ICIKT_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+  p->n_sm = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    free_plan(p);
+    return fail(ICIKT_ERR_NO_DEVICE, "device is not sm_100-class; this library is built for sm_100a only");
+  }
+  rc = build_units(p, pi, pj, P);
+  if (rc != ICIKT_OK) { free_plan(p); return rc; }
+
+#define PCK(call)                                                \
+  do {                                                           \
+    cudaError_t e_ = (call);                                     \
+    if (e_ != cudaSuccess) {                                     \
+      const int c_ = (e_ == cudaErrorMemoryAllocation) ? fail(ICIKT_ERR_ALLOC, "device allocation failed: " #call) \
+                                                       : cuda_fail(e_, #call);                     \
+      free_plan(p);                                              \
+      return c_;                                                 \
+    }                                                            \
+  } while (0)
+
+  PCK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  for (auto& e : p->ev) PCK(cudaEventCreate(&e));
+  ColumnTables& t = p->tab;
+  t.n = n;
+  t.C = C;
+  t.nstride = (n + 63) & ~63LL;
+  const int64_t nwords = ((n + 31) & ~31LL) / 32;
+  t.wstride = (nwords + 3) & ~3LL;
+  const size_t ne = (size_t)t.nstride * C, nw = (size_t)t.wstride * C;
+  PCK(dmalloc(&t.perm, ne));
+  PCK(dmalloc(&t.rank, ne));
+  PCK(dmalloc(&t.trow, ne));
+  PCK(dmalloc(&t.trun, ne));
+  PCK(dmalloc(&t.nabits, nw));
+  PCK(dmalloc(&t.firstbits, nw));
+  PCK(dmalloc(&t.grpstart, nw));
+  PCK(dmalloc(&t.stats, (size_t)C));
+  PCK(dmalloc(&p->wk.keys_in, ne));
+  PCK(dmalloc(&p->wk.keys_out, ne));
+  PCK(dmalloc(&p->wk.vals_in, ne));
+  PCK(dmalloc(&p->wk.gpos, (size_t)(t.nstride + 64) * C));
+  PCK(dmalloc(&p->wk.seg_begin, (size_t)C));
+  PCK(dmalloc(&p->wk.seg_end, (size_t)C));
+  p->wk.cub_bytes = columns_cub_bytes(n, C, t.nstride);
+  PCK(cudaMalloc(&p->wk.cub_temp, std::max<size_t>(p->wk.cub_bytes, 16)));
+  PCK(dmalloc(&p->d_global_na, 64));
+
+  const size_t np = (size_t)std::max<int64_t>(p->P, 1);
+  PCK(dmalloc(&p->d_units, p->units.size()));
+  PCK(cudaMemcpyAsync(p->d_units, p->units.data(), sizeof(PairUnit) * p->units.size(),
+                      cudaMemcpyHostToDevice, p->stream));
+  if (pi) {
+    PCK(dmalloc(&p->d_pj, np));
+    PCK(cudaMemcpyAsync(p->d_pj, pj, sizeof(int32_t) * np, cudaMemcpyHostToDevice, p->stream));
+  }
+  PCK(dmalloc(&p->d_raw, np));
+  PCK(dmalloc(&p->d_tau, np));
+  PCK(dmalloc(&p->d_p, np));
+  PCK(dmalloc(&p->d_tm, np));
+  PCK(dmalloc(&p->d_comp, np));
+  PCK(dmalloc(&p->d_status, np));
+  if (p->want_counts) PCK(dmalloc(&p->d_counts, np * ICIKT_NCOUNTS));
+  PCK(dmalloc(&p->d_scalars, 2));
+  if (o.kernel == ICIKT_KERNEL_NAIVE) {
+    p->naive_threads = std::min<int64_t>((int64_t)p->units.size(), (int64_t)p->n_sm * 256);
+    p->naive_threads = std::max<int64_t>(p->naive_threads, 1);
+    PCK(cudaMalloc(reinterpret_cast<void**>(&p->d_naive), naive_scratch_bytes(n, p->naive_threads)));
+  }
+  PCK(cudaStreamSynchronize(p->stream));  // pj / units are read from caller memory
+#undef PCK
+  *out = p;
+  return ICIKT_OK;
+}
+
+int64_t icikt_plan_num_pairs(const icikt_plan* p) { return p ? p->P : 0; }
+
+int icikt_plan_upload(icikt_plan* p, const double* data, int64_t ld) {
+  if (!p || !data || ld < p->n) return fail(ICIKT_ERR_BAD_ARG, "bad upload arguments");
+  CK(cudaSetDevice(p->device));
+  if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaMemcpy2DAsync(p->d_data_own, sizeof(double) * p->n, data, sizeof(double) * ld,
+                       sizeof(double) * p->n, (size_t)p->C, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  p->d_data = p->d_data_own;
+  p->ld = p->n;
+  p->columns_done = false;
+  return ICIKT_OK;
+}
+
+int icikt_plan_set_device_matrix(icikt_plan* p, const double* d_data, int64_t ld) {
+  if (!p || !d_data || ld < p->n) return fail(ICIKT_ERR_BAD_ARG, "bad device matrix arguments");
+  p->d_data = d_data;
+  p->ld = ld;
+  p->columns_done = false;
+  CK(cudaSetDevice(p->device));
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaEventRecord(p->ev[1], p->stream));
+  return ICIKT_OK;
+}
+
+int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_na) {
+  if (!p || !p->d_data) return fail(ICIKT_ERR_BAD_ARG, "no matrix set on the plan");
+  if (n_global_na < 0 || (n_global_na > 0 && !global_na)) return fail(ICIKT_ERR_BAD_ARG, "bad global_na");
+  CK(cudaSetDevice(p->device));
+  // R/utils.R:6-15: NA and Inf entries of global_na select classes, the rest are literals
+  double lit[64];
+  int nlit = 0, na_inf = p->opts.na_inf;
+  for (int i = 0; i < n_global_na; ++i) {
+    const double v = global_na[i];
+    if (std::isnan(v)) continue;
+    if (std::isinf(v)) { na_inf = 1; continue; }
+    if (nlit == 64) return fail(ICIKT_ERR_BAD_ARG, "more than 64 global_na literals");
+    lit[nlit++] = v;
+  }
+  if (nlit) CK(cudaMemcpyAsync(p->d_global_na, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, p->stream));
+  CK(cudaEventRecord(p->ev[2], p->stream));
+  const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->stream);
+  if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
+  CK(cudaEventRecord(p->ev[3], p->stream));
+  if (nlit) CK(cudaStreamSynchronize(p->stream));  // lit[] lives on this stack frame
+  p->tm.n_launches = l;
+  p->columns_done = true;
+  return ICIKT_OK;
+}
+
+int icikt_plan_pairs(icikt_plan* p) {
+  if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
+  CK(cudaSetDevice(p->device));
+  CK(cudaEventRecord(p->ev[4], p->stream));
+  CK(cudaMemsetAsync(p->d_scalars, 0, 2 * sizeof(unsigned long long), p->stream));
+  PairLaunch pl;
+  pl.tab = &p->tab;
+  pl.units = p->d_units;
+  pl.n_units = (int64_t)p->units.size();
+  pl.pj_list = p->d_pj;
+  pl.raw = p->d_raw;
+  pl.unit_counter = p->d_scalars;
+  int launches = 0;
+  if (p->P > 0) {
+    int l;
+    if (p->opts.kernel == ICIKT_KERNEL_NAIVE)
+      l = launch_pairs_naive(pl, p->P, p->d_naive, p->naive_threads, p->stream);
+    else
+      l = launch_pairs_tiled(pl, p->n_sm, p->stream);
+    if (l < 0) return cuda_fail(cudaGetLastError(), "pair kernel");
+    launches += l;
+    EpilogueLaunch el;
+    el.tab = &p->tab;
+    el.units = p->d_units;
+    el.n_units = pl.n_units;
+    el.pj_list = p->d_pj;
+    el.raw = p->d_raw;
+    el.perspective = p->opts.perspective;
+    el.alternative = p->opts.alternative;
+    el.continuity = p->opts.continuity;
+    el.tau = p->d_tau;
+    el.pvalue = p->d_p;
+    el.taumax = p->d_tm;
+    el.completeness = p->d_comp;
+    el.status = p->d_status;
+    el.counts = p->d_counts;
+    el.max_taumax_bits = p->d_scalars + 1;
+    l = launch_epilogue(el, p->stream);
+    if (l < 0) return cuda_fail(cudaGetLastError(), "epilogue kernel");
+    launches += l;
+  }
+  CK(cudaEventRecord(p->ev[5], p->stream));
+  p->tm.n_launches = (p->tm.n_launches & 0xffff) | (launches << 16);
+  return ICIKT_OK;
+}
+
+int icikt_plan_sync(icikt_plan* p) {
+  if (!p) return fail(ICIKT_ERR_BAD_ARG, "plan is NULL");
+  CK(cudaSetDevice(p->device));
+  CK(cudaStreamSynchronize(p->stream));
+  return ICIKT_OK;
+}
+
+int icikt_plan_download(icikt_plan* p, double* raw, double* pvalue, double* taumax, double* completeness,
+                        int32_t* status, int64_t* counts, double* max_taumax) {
+  if (!p) return fail(ICIKT_ERR_BAD_ARG, "plan is NULL");
+  if (counts && !p->d_counts) return fail(ICIKT_ERR_BAD_ARG, "plan was created without want_counts");
+  CK(cudaSetDevice(p->device));
+  const size_t np = (size_t)p->P;
+  CK(cudaEventRecord(p->ev[6], p->stream));
+  if (np) {
+    if (raw) CK(cudaMemcpyAsync(raw, p->d_tau, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+    if (pvalue) CK(cudaMemcpyAsync(pvalue, p->d_p, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+    if (taumax) CK(cudaMemcpyAsync(taumax, p->d_tm, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+    if (completeness) CK(cudaMemcpyAsync(completeness, p->d_comp, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+    if (status) CK(cudaMemcpyAsync(status, p->d_status, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, p->stream));
+    if (counts) CK(cudaMemcpyAsync(counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS, cudaMemcpyDeviceToHost, p->stream));
+  }
+  unsigned long long bits = 0;
+  CK(cudaMemcpyAsync(&bits, p->d_scalars + 1, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaEventRecord(p->ev[7], p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (max_taumax) {
+    double v;
+    std::memcpy(&v, &bits, sizeof(v));
+    *max_taumax = bits ? v : std::nan("");
+  }
+  return ICIKT_OK;
+}
+
+int icikt_plan_column_info(icikt_plan* p, int32_t* n_na) {
+  if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
+  CK(cudaSetDevice(p->device));
+  std::vector<ColStats> s((size_t)p->C);
+  CK(cudaMemcpyAsync(s.data(), p->tab.stats, sizeof(ColStats) * s.size(), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (n_na)
+    for (int64_t c = 0; c < p->C; ++c) n_na[c] = s[(size_t)c].n_na;
+  return ICIKT_OK;
+}
+
+void* icikt_plan_stream(icikt_plan* p) { return p ? (void*)p->stream : nullptr; }
+
+int icikt_plan_timings(icikt_plan* p, icikt_timings* t) {
+  if (!p || !t) return fail(ICIKT_ERR_BAD_ARG, "NULL argument");
+  CK(cudaSetDevice(p->device));
+  CK(cudaStreamSynchronize(p->stream));
+  const int launches = (p->tm.n_launches & 0xffff) + (p->tm.n_launches >> 16);
+  std::memset(t, 0, sizeof(*t));
+  t->n_launches = launches;
+  if (cudaEventQuery(p->ev[1]) == cudaSuccess) t->h2d_ms = ev_ms(p->ev[0], p->ev[1]);
+  if (cudaEventQuery(p->ev[3]) == cudaSuccess) t->columns_ms = ev_ms(p->ev[2], p->ev[3]);
+  if (cudaEventQuery(p->ev[5]) == cudaSuccess) t->pairs_ms = ev_ms(p->ev[4], p->ev[5]);
+  if (cudaEventQuery(p->ev[7]) == cudaSuccess) t->d2h_ms = ev_ms(p->ev[6], p->ev[7]);
+  if (cudaEventQuery(p->ev[0]) == cudaSuccess && cudaEventQuery(p->ev[7]) == cudaSuccess)
+    t->total_ms = ev_ms(p->ev[0], p->ev[7]);
+  cudaGetLastError();
+  return ICIKT_OK;
+}
+
+void icikt_plan_destroy(icikt_plan* p) { free_plan(p); }
+
+static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                    int32_t n_global_na, const int32_t* pi, const int32_t* pj, int64_t P,
+                    const icikt_opts* opts, double* raw, double* pvalue, double* taumax,
+                    double* completeness, int32_t* status, int64_t* counts, double* max_taumax,
+                    icikt_timings* timings) {
+  if (!data || !raw) return fail(ICIKT_ERR_BAD_ARG, "data and raw must not be NULL");
+  icikt_opts o;
+  if (opts) o = *opts; else icikt_default_opts(&o);
+  o.want_counts = counts ? 1 : 0;
+  icikt_plan* p = nullptr;
+  int rc = icikt_plan_create(&p, n, C, pi, pj, P, &o);
+  if (rc != ICIKT_OK) return rc;
+  rc = icikt_plan_upload(p, data, ld);
+  if (rc == ICIKT_OK) rc = icikt_plan_columns(p, global_na, n_global_na);
+  if (rc == ICIKT_OK) rc = icikt_plan_pairs(p);
+  if (rc == ICIKT_OK) rc = icikt_plan_download(p, raw, pvalue, taumax, completeness, status, counts, max_taumax);
+  if (rc == ICIKT_OK && timings) rc = icikt_plan_timings(p, timings);
+  const std::string keep = g_err;
+  icikt_plan_destroy(p);
+  if (rc != ICIKT_OK) g_err = keep;
+  return rc;
+}
+
+int icikt_all_pairs(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                    int32_t n_global_na, const icikt_opts* opts, double* raw, double* pvalue,
+                    double* taumax, double* completeness, int32_t* status, int64_t* counts,
+                    double* max_taumax, icikt_timings* timings) {
+  return one_shot(data, n, C, ld, global_na, n_global_na, nullptr, nullptr, 0, opts, raw, pvalue, taumax,
+                  completeness, status, counts, max_taumax, timings);
+}
+
+int icikt_pair_list(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                    int32_t n_global_na, const int32_t* pi, const int32_t* pj, int64_t P,
+                    const icikt_opts* opts, double* raw, double* pvalue, double* taumax,
+                    double* completeness, int32_t* status, int64_t* counts, double* max_taumax,
+                    icikt_timings* timings) {
+  if (!pi || !pj) return fail(ICIKT_ERR_BAD_ARG, "pi and pj must not be NULL");
+  return one_shot(data, n, C, ld, global_na, n_global_na, pi, pj, P, opts, raw, pvalue, taumax,
+                  completeness, status, counts, max_taumax, timings);
+}
+
+int icikt_pnorm_device(const double* z, int64_t n, int32_t lower_tail, double* out, int32_t device) {
+  if (!z || !out || n < 0) return fail(ICIKT_ERR_BAD_ARG, "bad pnorm arguments");
+  int rc = select_device(device);
+  if (rc != ICIKT_OK) return rc;
+  if (n == 0) return ICIKT_OK;
+  double *dz = nullptr, *dout = nullptr;
+  CK(dmalloc(&dz, (size_t)n));
+  cudaError_t e = dmalloc(&dout, (size_t)n);
+  if (e != cudaSuccess) { cudaFree(dz); return cuda_fail(e, "cudaMalloc"); }
+  e = cudaMemcpy(dz, z, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = (launch_pnorm(dz, n, lower_tail, dout, 0) < 0) ? cudaGetLastError() : cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dz);
+  cudaFree(dout);
+  if (e != cudaSuccess) return cuda_fail(e, "pnorm");
+  return ICIKT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+// icikt_columns.cu -- K1: per-column preprocessing, done once per column instead of twice per
+// pair as in the reference.
+//
+//   build_keys_kernel   setup_missing_matrix (R/utils.R:1-23) + the NA -> "below the minimum"
+//                       substitution of src/kendallc.cpp:214-219, expressed as a sort key:
+//                       missing rows get key 0, every other value an order-preserving 64-bit
+//                       image of the double (-0.0 == +0.0, as compare_self :15-31 sees them).
+//   segmented sort      sortedIndex (src/kendallc.cpp:6-12), one segment per column
+//                       (cub::DeviceSegmentedSort; stability is irrelevant because rows of a
+//                       tie group are interchangeable for every downstream count).
+//   column_rank_kernel  compare_self + cumsum (:15-31, :250-251) -> dense ranks; tie-group
+//                       sizes -> count_rank_tie sums (:103-118) in exact int64; the bit masks
+//                       and the tied-row list the pair kernel needs.
+#include <cub/device/device_segmented_sort.cuh>
+
+#include "icikt_internal.h"
+
+namespace icikt {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int RANK_THREADS = 512;
+
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  if (v == 0.0) v = 0.0;  // -0.0 -> +0.0
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(256)
+    build_keys_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
+                      const double* __restrict__ global_na, int n_global_na, int na_inf,
+                      unsigned long long* __restrict__ keys, uint16_t* __restrict__ vals,
+                      uint32_t* __restrict__ nabits) {
+  const int col = blockIdx.y;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  bool miss = false;
+  if (r < n) {
+    const double v = data[(size_t)col * ld + r];
+    miss = (v != v) || (na_inf && isinf(v));
+    for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
+    keys[(size_t)col * nstride + r] = miss ? 0ull : order_key(v);
+    vals[(size_t)col * nstride + r] = (uint16_t)r;
+  }
+  const uint32_t m = __ballot_sync(FULL, miss);
+  if ((threadIdx.x & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, sets total
+__device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  int ws = (lane < (RANK_THREADS / 32)) ? warp_sums[lane] : 0;
+  int wincl = ws;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, wincl, d);
+    if (lane >= d) wincl += t;
+  }
+  total = __shfl_sync(FULL, wincl, 31);
+  const int wexcl = __shfl_sync(FULL, wincl - ws, warp);
+  __syncthreads();
+  return wexcl + incl - v;
+}
+
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  if (lane == 0) buf[warp] = v;
+  __syncthreads();
+  long long t = 0;
+  for (int w = 0; w < RANK_THREADS / 32; ++w) t += buf[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(RANK_THREADS)
+    column_rank_kernel(const unsigned long long* __restrict__ skeys, int n, int nstride, int wstride,
+                       uint16_t* __restrict__ perm, uint16_t* __restrict__ rank,
+                       uint16_t* __restrict__ trow, uint16_t* __restrict__ trun,
+                       uint32_t* __restrict__ firstbits, uint32_t* __restrict__ grpstart,
+                       uint32_t* __restrict__ gpos_all, ColStats* __restrict__ stats) {
+  __shared__ int warp_sums[32];
+  __shared__ long long llbuf[32];
+  __shared__ uint32_t bits[2048];
+  const int col = blockIdx.x;
+  const int tid = threadIdx.x;
+  const unsigned long long* sk = skeys + (size_t)col * nstride;
+  uint16_t* pm = perm + (size_t)col * nstride;
+  uint16_t* rk = rank + (size_t)col * nstride;
+  uint16_t* tr = trow + (size_t)col * nstride;
+  uint16_t* tg = trun + (size_t)col * nstride;
+  uint32_t* gpos = gpos_all + (size_t)col * (nstride + 64);
+  const int n32 = (n + 31) & ~31;
+  const int nwords = n32 >> 5;
+
+  // missing rows sort first (key 0)
+  long long a_ll = 0;
+  for (int t = tid; t < n; t += RANK_THREADS) a_ll += (sk[t] == 0ull);
+  const int a = (int)block_sum_ll(a_ll, llbuf);
+  // NA substitute = min - 0.1 (src/kendallc.cpp:214-219); if that does not move the minimum in
+  // fp64 (|min| huge or -Inf) the missing rows tie with it
+  bool absorb = false;
+  if (a > 0 && a < n) {
+    const double mn = key_value(sk[a]);
+    absorb = (__dsub_rn(mn, 0.1) == mn);
+  }
+
+  // dense ranks in sorted order
+  int carry = 0;
+  for (int t0 = 0; t0 < n32; t0 += RANK_THREADS) {
+    const int t = t0 + tid;
+    int flag = 0;
+    if (t < n) flag = (t == 0) || ((sk[t] != sk[t - 1]) && !(t == a && absorb));
+    int total;
+    const int excl = block_scan_excl(flag, warp_sums, total);
+    if (t < n) {
+      const int r = carry + excl + flag - 1;
+      rk[pm[t]] = (uint16_t)r;
+      if (flag) gpos[r] = (uint32_t)t;
+    }
+    const uint32_t m = __ballot_sync(FULL, flag != 0);
+    if ((tid & 31) == 0 && t < n32) grpstart[(size_t)col * wstride + (t >> 5)] = m;
+    carry += total;
+  }
+  const int K = carry;
+  if (tid == 0) gpos[K] = (uint32_t)n;
+  __syncthreads();
+
+  // tie sums over group sizes (count_rank_tie, src/kendallc.cpp:103-118), exact int64
+  long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
+  for (int g = tid; g < K; g += RANK_THREADS) {
+    const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
+    if (g == 0 && a > 0) continue;  // the NA group is kept apart for the local perspective
+    s2 += t * (t - 1);
+    s3 += t * (t - 1) * (t - 2);
+    s5 += t * (t - 1) * (2 * t + 5);
+    if (g > 0 && t > 1) ntied += t;
+  }
+  s2 = block_sum_ll(s2, llbuf);
+  s3 = block_sum_ll(s3, llbuf);
+  s5 = block_sum_ll(s5, llbuf);
+  ntied = block_sum_ll(ntied, llbuf);
+  const int g0size = (K > 0) ? (int)gpos[1] : 0;
+  const int first_run = g0size > 1 ? g0size : 0;
+
+  // membership mask of the first group
+  for (int w = tid; w < nwords; w += RANK_THREADS) bits[w] = 0;
+  __syncthreads();
+  for (int t = tid; t < first_run; t += RANK_THREADS) {
+    const uint32_t row = pm[t];
+    atomicOr(&bits[row >> 5], 1u << (row & 31));
+  }
+  __syncthreads();
+  for (int w = tid; w < nwords; w += RANK_THREADS) firstbits[(size_t)col * wstride + w] = bits[w];
+
+  // rows of the other tied groups, in sorted order, with their group id
+  carry = 0;
+  for (int t0 = 0; t0 < n32; t0 += RANK_THREADS) {
+    const int t = t0 + tid;
+    int flag = 0, r = 0;
+    uint16_t row = 0;
+    if (t < n && t >= g0size) {
+      row = pm[t];
+      r = rk[row];
+      flag = (gpos[r + 1] - gpos[r]) > 1;
+    }
+    int total;
+    const int excl = block_scan_excl(flag, warp_sums, total);
+    if (flag) {
+      tr[carry + excl] = row;
+      tg[carry + excl] = (uint16_t)r;
+    }
+    carry += total;
+  }
+
+  if (tid == 0) {
+    ColStats s;
+    s.n_na = a;
+    s.first_run = first_run;
+    s.n_tied = (int)ntied;
+    s.n_groups = K;
+    int L = 1;
+    while ((1 << L) < K) ++L;
+    s.levels = L;
+    s.g0extra = (a > 0) ? g0size - a : 0;
+    s.flags = absorb ? 1 : 0;
+    s.pad_ = 0;
+    s.s2o = s2;
+    s.s3o = s3;
+    s.s5o = s5;
+    s.cconst = 0;
+    stats[col] = s;
+  }
+}
+
+__global__ void seg_offsets_kernel(long long* begin, long long* end, int C, long long nstride, long long n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    begin[c] = c * nstride;
+    end[c] = c * nstride + n;
+  }
+}
+
+}  // namespace
+
+size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride) {
+  size_t bytes = 0;
+  cub::DeviceSegmentedSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr,
+                                      (unsigned long long*)nullptr, (const uint16_t*)nullptr,
+                                      (uint16_t*)nullptr, (long long)(nstride * C), (long long)C,
+                                      (const long long*)nullptr, (const long long*)nullptr);
+  (void)n;
+  return bytes;
+}
+
+int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
+                   int na_inf, ColumnTables& tab, ColumnWork& wk, cudaStream_t stream) {
+  const int n = (int)tab.n, C = (int)tab.C;
+  const int nstride = (int)tab.nstride, wstride = (int)tab.wstride;
+  int launches = 0;
+  if (cudaMemsetAsync(tab.nabits, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(tab.grpstart, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(tab.firstbits, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
+  {
+    seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, C, nstride, n);
+    ++launches;
+    const int n32 = (n + 31) & ~31;
+    dim3 grid((n32 + 255) / 256, C);
+    build_keys_kernel<<<grid, 256, 0, stream>>>(d_data, ld, n, nstride, wstride, d_global_na, n_global_na,
+                                                na_inf, wk.keys_in, wk.vals_in, tab.nabits);
+    ++launches;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+  }
+  size_t bytes = wk.cub_bytes;
+  if (cub::DeviceSegmentedSort::SortPairs(wk.cub_temp, bytes, (const unsigned long long*)wk.keys_in,
+                                          wk.keys_out, (const uint16_t*)wk.vals_in, tab.perm,
+                                          (long long)nstride * C, (long long)C,
+                                          (const long long*)wk.seg_begin, (const long long*)wk.seg_end,
+                                          stream) != cudaSuccess)
+    return -1;
+  launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
+  column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
+                                                     tab.trow, tab.trun, tab.firstbits, tab.grpstart,
+                                                     wk.gpos, tab.stats);
+  ++launches;
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  const int cl = launch_column_consts(tab, stream);
+  if (cl < 0) return -1;
+  return launches + cl;
+}
+
+}  // namespace icikt

@@ -1,0 +1,194 @@
+// icikt_common.cuh -- shared types and the fp64 epilogue of the ICI-Kendall-tau path.
+//
+// The epilogue restates src/kendallc.cpp:190-244 (guards) and :280-335 (tau, tau_max,
+// variance, z, p-value) of the reference in terms of per-column tie statistics and the
+// three per-pair integers (dis, ntie, b); SURVEY.md 7.1 derives why one set of global
+// counts serves both perspectives.  It is __host__ __device__ so the same code is unit
+// tested on the CPU (tests/test_epilogue_cpu.py) and run by the K3 kernel.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ICIKT_HD __host__ __device__ __forceinline__
+#else
+#define ICIKT_HD inline
+#endif
+
+namespace icikt {
+
+// Per-column by-products of the preprocessing kernels (K1).  Groups are the tie groups of
+// the column after missing-value substitution, in ascending order; if the column has
+// missing values group 0 is the "NA group" (missing rows rank below every value,
+// src/kendallc.cpp:214-219), which may also hold `g0extra` non-missing rows when
+// min - 0.1 == min in fp64.
+struct ColStats {
+  int32_t n_na;       // a: missing rows
+  int32_t first_run;  // size of the first group if > 1, else 0
+  int32_t n_tied;     // rows in tie groups of size > 1 other than the first group
+  int32_t n_groups;   // K: number of groups (distinct values, NA group included)
+  int32_t levels;     // L = max(1, ceil(log2 K)): bits of a dense rank
+  int32_t g0extra;    // non-missing rows merged into the NA group
+  int32_t flags;
+  int32_t pad_;
+  int64_t s2o;        // sum t(t-1)        over groups other than the NA group
+  int64_t s3o;        // sum t(t-1)(t-2)
+  int64_t s5o;        // sum t(t-1)(2t+5)
+  uint64_t cconst;    // pass-A correction constant (see icikt_pairs.cu)
+};
+
+struct PairOut {
+  double tau, pvalue, taumax, completeness;
+  int64_t xtie, ytie, tot, n_entry;
+  int32_t status;
+};
+
+// ---- R nmath pnorm_both (Cody 1969), as reached from src/kendallc.cpp:324-330 ----------
+// i_tail 0 = lower only, 1 = upper only.
+ICIKT_HD void pnorm_both(double x, double* cum, double* ccum, int i_tail) {
+  const double a[5] = {2.2352520354606839287, 161.02823106855587881, 1067.6894854603709582,
+                       18154.981253343561249, 0.065682337918207449113};
+  const double b[4] = {47.20258190468824187, 976.09855173777669322, 10260.932208618978205,
+                       45507.789335026729956};
+  const double c[9] = {0.39894151208813466764, 8.8831497943883759412, 93.506656132177855979,
+                       597.27027639480026226,  2494.5375852903726711, 6848.1904505362823326,
+                       11602.651437647350124,  9842.7148383839780218, 1.0765576773720192317e-8};
+  const double d[8] = {22.266688044328115691, 235.38790178262499861, 1519.377599407554805,
+                       6485.558298266760755,  18615.571640885098091, 34900.952721145977266,
+                       38912.003286093271411, 19685.429676859990727};
+  const double p[6] = {0.21589853405795699,   0.1274011611602473639,   0.022235277870649807,
+                       0.001421619193227893466, 2.9112874951168792e-5, 0.02307344176494017303};
+  const double q[5] = {1.28426009614491121,   0.468238212480865118, 0.0659881378689285515,
+                       0.00378239633202758244, 7.29751555083966205e-5};
+  const bool lower = i_tail != 1, upper = i_tail != 0;
+  double xden, xnum, temp, del, xsq;
+  *cum = 0.0;
+  *ccum = 0.0;
+  if (x != x) { *cum = *ccum = x; return; }
+  const double eps = 2.220446049250313e-16 * 0.5;
+  const double y = fabs(x);
+  if (y <= 0.67448975) {
+    if (y > eps) {
+      xsq = x * x;
+      xnum = a[4] * xsq;
+      xden = xsq;
+      for (int i = 0; i < 3; ++i) { xnum = (xnum + a[i]) * xsq; xden = (xden + b[i]) * xsq; }
+    } else {
+      xnum = xden = 0.0;
+    }
+    temp = x * (xnum + a[3]) / (xden + b[3]);
+    if (lower) *cum = 0.5 + temp;
+    if (upper) *ccum = 0.5 - temp;
+  } else if (y <= 5.656854249492380195206754896838) {
+    xnum = c[8] * y;
+    xden = y;
+    for (int i = 0; i < 7; ++i) { xnum = (xnum + c[i]) * y; xden = (xden + d[i]) * y; }
+    temp = (xnum + c[7]) / (xden + d[7]);
+    xsq = trunc(y * 16) / 16;
+    del = (y - xsq) * (y + xsq);
+    *cum = exp(-xsq * xsq * 0.5) * exp(-del * 0.5) * temp;
+    *ccum = 1.0 - *cum;
+    if (x > 0.) { temp = *cum; if (lower) *cum = *ccum; *ccum = temp; }
+  } else if ((lower && -37.5193 < x && x < 8.2924) || (upper && -8.2924 < x && x < 37.5193)) {
+    xsq = 1.0 / (x * x);
+    xnum = p[5] * xsq;
+    xden = xsq;
+    for (int i = 0; i < 4; ++i) { xnum = (xnum + p[i]) * xsq; xden = (xden + q[i]) * xsq; }
+    temp = xsq * (xnum + p[4]) / (xden + q[4]);
+    temp = (0.398942280401432677939946059934 - temp) / y;
+    xsq = trunc(x * 16) / 16;
+    del = (x - xsq) * (x + xsq);
+    *cum = exp(-xsq * xsq * 0.5) * exp(-del * 0.5) * temp;
+    *ccum = 1.0 - *cum;
+    if (x > 0.) { temp = *cum; if (lower) *cum = *ccum; *ccum = temp; }
+  } else {
+    if (x > 0) { *cum = 1.; *ccum = 0.; } else { *cum = 0.; *ccum = 1.; }
+  }
+}
+
+ICIKT_HD double pnorm_std(double x, bool lower_tail) {
+  if (x != x) return x;
+  if (fabs(x) > 1.7976931348623157e308) return ((x < 0) == lower_tail) ? 0.0 : 1.0;  // +-Inf
+  double p, cp;
+  pnorm_both(x, &p, &cp, lower_tail ? 0 : 1);
+  return lower_tail ? p : cp;
+}
+
+ICIKT_HD double qnan() { return nan(""); }
+
+// One pair's results from the integer counts.
+//   n        : vector length (features)
+//   X, Y     : per-column statistics of the two columns
+//   dis      : #{(p,q): x_p < x_q and y_p > y_q}            (kendall_discordant, :70-100)
+//   ntie_g   : sum over joint (x,y) tie groups g(g-1)/2 on all n rows (:261-267)
+//   b        : rows missing in both columns
+ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int64_t dis,
+                            int64_t ntie_g, int64_t b, int perspective, int alternative,
+                            int continuity, PairOut& o) {
+  const double NA = qnan();
+  o.tau = o.pvalue = o.taumax = o.completeness = NA;
+  o.xtie = o.ytie = o.tot = 0;
+  o.status = 0;
+  const int64_t bb = (perspective == 1) ? b : 0;  // local drops the joint-missing rows (:180-185)
+  const int64_t np = n - bb;
+  o.n_entry = np;
+  const int64_t a = X.n_na, c = Y.n_na;
+  if (a == n || c == n) { o.status = 1; return; }  // :190-199 (a-bb == n-bb  <=>  a == n)
+  if (np < 2) { o.status = 2; return; }            // :224-231
+  // group 0 after removing the joint-missing rows
+  const int64_t t0x = (a > 0) ? (a - bb) + X.g0extra : 0;
+  const int64_t t0y = (c > 0) ? (c - bb) + Y.g0extra : 0;
+  const int64_t kx = (int64_t)X.n_groups - (a > 0 ? 1 : 0) + (t0x > 0 ? 1 : 0);
+  const int64_t ky = (int64_t)Y.n_groups - (c > 0 ? 1 : 0) + (t0y > 0 ? 1 : 0);
+  if (kx == 1 || ky == 1) { o.status = 3; return; }  // :234-244
+  // count_rank_tie, :103-118 (sums are exact int64 here; the reference's are int32)
+  const int64_t xtie = (X.s2o + t0x * (t0x - 1)) / 2;
+  const int64_t ytie = (Y.s2o + t0y * (t0y - 1)) / 2;
+  const double x0 = (double)((X.s3o + t0x * (t0x - 1) * (t0x - 2)) / 2);
+  const double y0 = (double)((Y.s3o + t0y * (t0y - 1) * (t0y - 2)) / 2);
+  const double x1 = (double)(X.s5o + t0x * (t0x - 1) * (2 * t0x + 5));
+  const double y1 = (double)(Y.s5o + t0y * (t0y - 1) * (2 * t0y + 5));
+  const int64_t ntie = ntie_g - bb * (bb - 1) / 2;
+  const int64_t tot = np * (np - 1) / 2;  // :280
+  o.xtie = xtie;
+  o.ytie = ytie;
+  o.tot = tot;
+  if (xtie == tot || ytie == tot) { o.status = 4; return; }  // :291-298
+  // :300-308
+  const double dxt = (double)xtie, dyt = (double)ytie;
+  const double den = sqrt(((double)tot - dxt) * ((double)tot - dyt));
+  const double con_minus_dis = (double)(tot - xtie - ytie + ntie - 2 * dis);
+  const double con_plus_dis = (double)(tot - xtie - ytie + ntie);
+  double tau = con_minus_dis / den;
+  const double tau_max = con_plus_dis / den;
+  if (tau > 1) tau = 1; else if (tau < -1) tau = -1;
+  // :310-321
+  const int64_t m = np * (np - 1);
+  const double var = ((double)(m * (2 * np + 5)) - x1 - y1) / 18 + (2 * dxt * dyt) / (double)m +
+                     x0 * y0 / (double)(9 * m * (np - 2));
+  double s_adj = tau * sqrt(((double)(m / 2) - dxt) * ((double)(m / 2) - dyt));
+  if (continuity) {
+    const double sg = s_adj > 0 ? 1.0 : (s_adj == 0 ? 0.0 : -1.0);
+    s_adj = sg * (fabs(s_adj) - 1);
+  }
+  const double z = s_adj / sqrt(var);
+  // :323-332
+  double pv = 0.0;
+  if (alternative == 1) pv = pnorm_std(z, true);
+  else if (alternative == 2) pv = pnorm_std(z, false);
+  else if (alternative == 0) {
+    const double p0 = pnorm_std(z, true), p1 = pnorm_std(z, false);
+    double mn = p0;  // Rcpp sugar min(): first NaN wins
+    if (mn == mn) { if (p1 != p1) mn = p1; else if (p1 < mn) mn = p1; }
+    pv = 2 * mn;
+  }
+  o.tau = tau;
+  o.pvalue = pv;
+  o.taumax = tau_max;
+  // :205-212  completeness = 1 - card(NA_x or NA_y) / length, evaluated as one correctly
+  // rounded quotient (the reference uses x87 long double and rounds once at the end)
+  const int64_t miss = a + c - b - bb;
+  o.completeness = (double)(np - miss) / (double)np;
+}
+
+}  // namespace icikt

@@ -1,0 +1,99 @@
+// icikt_internal.h -- host-side declarations shared by the translation units of
+// libicikt_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "icikt_common.cuh"
+
+namespace icikt {
+
+// Device-resident per-column tables produced by K1 (layout: DESIGN.md "Data layout in HBM").
+struct ColumnTables {
+  int64_t n = 0;        // rows (features)
+  int64_t C = 0;        // columns (samples)
+  int64_t nstride = 0;  // elements per column in the u16 arrays (n rounded up to 64)
+  int64_t wstride = 0;  // 32-bit words per column in the bit arrays (n32/32 rounded up to 4)
+  uint16_t* perm = nullptr;       // [C][nstride] row ids in ascending value order, missing first
+  uint16_t* rank = nullptr;       // [C][nstride] dense rank of every row
+  uint16_t* trow = nullptr;       // [C][nstride] rows of tied (non-first-group) elements, sorted order
+  uint16_t* trun = nullptr;       // [C][nstride] their group ids (= rank)
+  uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
+  uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
+  uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group
+  ColStats* stats = nullptr;      // [C]
+};
+
+// A unit of pair work: column `col` is staged in shared memory and correlated with
+// `count` other columns; results go to slots [slot0, slot0+count).
+struct PairUnit {
+  int64_t slot0;
+  int32_t col;    // staged column
+  int32_t j0;     // other column of the first pair; the k-th pair uses j0 + k (j_explicit == 0)
+  int32_t count;
+  int32_t j_explicit;  // 1: other columns are pj_list[slot0 + k]
+};
+
+struct PairRaw {  // what K2 hands to K3
+  int64_t dis, ntie, b;
+};
+
+struct PairLaunch {
+  const ColumnTables* tab;
+  const PairUnit* units;  // device
+  int64_t n_units;
+  const int32_t* pj_list;  // device, may be null
+  PairRaw* raw;            // device [P]
+  unsigned long long* unit_counter;  // device, zeroed by the launcher
+};
+
+// Scratch of the column kernels (allocated by the plan).
+struct ColumnWork {
+  unsigned long long* keys_in = nullptr;   // [C][nstride] sort keys
+  unsigned long long* keys_out = nullptr;  // [C][nstride] sorted keys
+  uint16_t* vals_in = nullptr;             // [C][nstride] row ids
+  uint32_t* gpos = nullptr;                // [C][nstride+64] start position of every tie group
+  long long* seg_begin = nullptr;          // [C]
+  long long* seg_end = nullptr;            // [C]
+  void* cub_temp = nullptr;
+  size_t cub_bytes = 0;
+};
+size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride);
+
+// K1: data (device, column-major, ld) -> tables.  Returns number of kernel launches or <0.
+int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
+                   int na_inf, ColumnTables& tab, ColumnWork& wk, cudaStream_t stream);
+
+// pass-A correction constant per column (needs the pair kernel's code path)
+int launch_column_consts(ColumnTables& tab, cudaStream_t stream);
+
+// K2 (tiled) and K2-naive; both fill raw[P].
+int launch_pairs_tiled(const PairLaunch& pl, int n_sm, cudaStream_t stream);
+int launch_pairs_naive(const PairLaunch& pl, int64_t P, uint32_t* d_scratch, int64_t n_threads,
+                       cudaStream_t stream);
+size_t naive_scratch_bytes(int64_t n, int64_t n_threads);
+
+// K3: fp64 epilogue, one thread per pair.
+struct EpilogueLaunch {
+  const ColumnTables* tab;
+  const PairUnit* units;
+  int64_t n_units;
+  const int32_t* pj_list;
+  const PairRaw* raw;
+  int perspective, alternative, continuity;
+  double* tau;
+  double* pvalue;
+  double* taumax;
+  double* completeness;
+  int32_t* status;
+  int64_t* counts;  // [P][7] or null
+  unsigned long long* max_taumax_bits;  // device, initialised to 0 by the launcher's caller
+};
+int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream);
+
+int launch_pnorm(const double* d_z, int64_t n, int lower, double* d_out, cudaStream_t stream);
+
+int64_t tiled_max_n();
+
+}  // namespace icikt

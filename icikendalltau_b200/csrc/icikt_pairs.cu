@@ -1,0 +1,716 @@
+// icikt_pairs.cu -- K2 (pair kernel), K2-naive (one thread per pair) and K3 (fp64 epilogue).
+//
+// Replaces, for a whole batch of column pairs, the body of ici_kt():
+//   src/kendallc.cpp:247-258  two stable argsorts + dense ranks   -> done once per column in K1
+//   src/kendallc.cpp:261-267  joint tie runs (compare_both/which_notzero/diff)   -> ntie
+//   src/kendallc.cpp:70-100   kendall_discordant (Fenwick tree, int32)           -> dis (int64)
+//   src/kendallc.cpp:280-335  tau / tau_max / variance / p-value                  -> K3
+//
+// Counting scheme (one CTA per pair, all integer, bit-exact):
+//   x := the streamed column (its sorted order `perm` defines the positions), y := the
+//   staged column (dense ranks in shared memory).  seq[p] = rank_y[perm_x[p]].
+//   dis = #{p<q : x-group(p) != x-group(q), seq[p] > seq[q]}
+//       = INV(seq) - sum over x-groups INV(seq restricted to the group)
+//   INV is counted by an MSB-first stable bit partition of the whole sequence (a wavelet-matrix
+//   construction): at the level of bit s every element with bit 0 adds the number of
+//   1-elements that precede it inside its bucket (= elements agreeing on the higher bits).
+//   Pass A runs over all n rows.  Because every row is present, the bucket layout and the
+//   number of ones before each bucket are properties of column y alone, so the per-bucket
+//   offsets collapse into one per-column constant `cconst` (the raw count of the sorted
+//   sequence, which has no inversions): INV = sum_levels sum_{zero q} ones_before(q) - cconst.
+//   No bucket boundaries are tracked in pass A.
+//   The first x-group (the missing rows, usually the only large tie group) is written into
+//   the sequence already ordered by y (stream compaction of y's sorted order through x's
+//   membership bitmask), so it contributes no inversions and its joint ties fall out of the
+//   compaction.  The remaining tied x-groups go through pass B: the same partition on the
+//   composite key (x-group << 16 | y-rank) with explicit bucket boundaries (ballot + clz),
+//   which yields their internal inversions and their joint ties.
+//   Each level is two warp-synchronous sweeps over register-resident chunks (ballot/popc
+//   prefix sums), one cross-warp scan of W per-warp totals, and an in-place scatter in
+//   shared memory; two __syncthreads per level.
+#include <cstdio>
+
+#include "icikt_internal.h"
+
+namespace icikt {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t lanemask_le() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+  return m;
+}
+// lanes strictly below the highest set bit of `bits` (bits != 0)
+__device__ __forceinline__ uint32_t below_top(uint32_t bits) {
+  return (1u << (31 - __clz((int)bits))) - 1u;
+}
+
+// Exclusive scan of the per-warp totals (every warp computes it redundantly from shared
+// memory) and, for the bucketed variants, the count at the nearest bucket start that lies in
+// an earlier warp's segment (counts are monotone in position, so that is a running max).
+template <int W, bool BUCKETS>
+__device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t* descB, int lane,
+                                           int warp, uint32_t& G, uint32_t& total, int32_t& carry) {
+  const uint32_t v = (lane < W) ? descT[lane] : 0u;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  total = __shfl_sync(FULL, incl, 31);
+  const uint32_t excl = incl - v;
+  G = __shfl_sync(FULL, excl, warp);
+  carry = -1;
+  if (BUCKETS) {
+    const int32_t bl = (lane < W) ? descB[lane] : -1;
+    int32_t babs = (bl >= 0 && lane < warp) ? (int32_t)excl + bl : -1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) babs = max(babs, __shfl_xor_sync(FULL, babs, d));
+    carry = babs;
+  }
+}
+
+// One counting pass over S[0, nelem32) (nelem32 a multiple of 32; positions >= nreal hold
+// all-ones pad keys).  Levels L-1..0 of the low bits are partitioned in place.
+//   BUCKETS = false: acc += sum over zero-bit elements of the GLOBAL count of preceding ones.
+//   BUCKETS = true : buckets are runs of equal (key >> (s+1)); acc += ones preceding inside
+//                    the bucket; after level 0 one more sweep on the full key adds, for every
+//                    real element, its index inside its run of equal keys to `ties`.
+template <int W, int K, bool BUCKETS>
+__device__ __forceinline__ void partition_pass(uint32_t* __restrict__ S, const int nelem32,
+                                               const int nreal, const int L, uint32_t* descT,
+                                               int32_t* descB, const int lane, const int warp,
+                                               uint32_t& acc, uint32_t& ties) {
+  const int nchunks = nelem32 >> 5;
+  const int kk = (nchunks + W - 1) / W;
+  const int c0 = warp * kk;
+  int mycnt = nchunks - c0;
+  mycnt = mycnt < 0 ? 0 : (mycnt > kk ? kk : mycnt);
+  const int base = c0 << 5;
+  const uint32_t lt = lanemask_lt();
+  const uint32_t le = lanemask_le();
+
+  uint32_t e[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) e[c] = (c < mycnt) ? S[base + (c << 5) + lane] : 0u;
+  uint32_t prevlast = 0;
+  if (BUCKETS) prevlast = (base > 0 && mycnt > 0) ? S[base - 1] : 0u;
+
+  for (int s = L - 1; s >= (BUCKETS ? -1 : 0); --s) {
+    const bool tie_step = (s < 0);  // BUCKETS only: every element counts as a "one"
+    const uint32_t bitmask = tie_step ? 0u : (1u << s);
+    const int sh = s + 1;
+
+    // ---- sweep 1: ones per warp segment (+ count at the last bucket start) ----
+    uint32_t T = 0;
+    int32_t lastB = -1;
+    uint32_t carrylast = prevlast;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      if (c < mycnt) {
+        const bool one = tie_step || ((e[c] & bitmask) != 0u);
+        const uint32_t m = __ballot_sync(FULL, one);
+        if (BUCKETS) {
+          uint32_t prev = __shfl_up_sync(FULL, e[c], 1);
+          if (lane == 0) prev = carrylast;
+          const int pos = base + (c << 5) + lane;
+          const uint32_t bd = __ballot_sync(FULL, (pos == 0) || (((e[c] ^ prev) >> sh) != 0u));
+          carrylast = __shfl_sync(FULL, e[c], 31);
+          if (bd) lastB = (int32_t)(T + __popc(m & below_top(bd)));
+        }
+        T += __popc(m);
+      }
+    }
+    if (lane == 0) {
+      descT[warp] = T;
+      if (BUCKETS) descB[warp] = lastB;
+    }
+    __syncthreads();
+
+    uint32_t G, total;
+    int32_t carry;
+    cross_warp<W, BUCKETS>(descT, descB, lane, warp, G, total, carry);
+    const uint32_t Z = (uint32_t)nelem32 - total;
+
+    // ---- sweep 2: count and scatter ----
+    uint32_t P = G;
+    carrylast = prevlast;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      if (c < mycnt) {
+        const int pos = base + (c << 5) + lane;
+        const bool one = tie_step || ((e[c] & bitmask) != 0u);
+        const uint32_t m = __ballot_sync(FULL, one);
+        const uint32_t P1 = P + __popc(m & lt);
+        if (BUCKETS) {
+          uint32_t prev = __shfl_up_sync(FULL, e[c], 1);
+          if (lane == 0) prev = carrylast;
+          const uint32_t bd = __ballot_sync(FULL, (pos == 0) || (((e[c] ^ prev) >> sh) != 0u));
+          carrylast = __shfl_sync(FULL, e[c], 31);
+          const uint32_t seg = bd & le;
+          const uint32_t startP = seg ? P + __popc(m & below_top(seg)) : (uint32_t)carry;
+          const uint32_t cnt = P1 - startP;
+          if (tie_step) {
+            if (pos < nreal) ties += cnt;
+          } else if (!one) {
+            acc += cnt;
+          }
+          if (bd) carry = (int32_t)(P + __popc(m & below_top(bd)));
+        } else {
+          if (!one) acc += P1;
+        }
+        if (!tie_step) {
+          const uint32_t dest = one ? Z + P1 : (uint32_t)pos - P1;
+          S[dest] = e[c];
+        }
+        P += __popc(m);
+      }
+    }
+    if (tie_step) break;
+    __syncthreads();
+    if (BUCKETS || s > 0) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) e[c] = (c < mycnt) ? S[base + (c << 5) + lane] : 0u;
+      if (BUCKETS) prevlast = (base > 0 && mycnt > 0) ? S[base - 1] : 0u;
+    }
+  }
+}
+
+// Writes the rows of x's first tie group into S[0, f) ordered by y: sweep y's sorted order,
+// keep the rows whose bit is set in x's membership mask (ordered stream compaction).  Rows
+// of one y tie group are contiguous in that order (gsY marks group starts), so the joint
+// (x-first-group, y) ties are counted on the way: every kept row adds the number of kept
+// rows before it in its y group.
+template <int W, int K>
+__device__ __forceinline__ void emit_first_group(uint32_t* __restrict__ S, const int n,
+                                                 const int n32, const uint16_t* __restrict__ permY_g,
+                                                 const uint16_t* __restrict__ rankY,
+                                                 const uint32_t* __restrict__ gsY,
+                                                 const uint32_t* __restrict__ fbX, uint32_t* descT,
+                                                 int32_t* descB, const int lane, const int warp,
+                                                 uint32_t& ties) {
+  const int nchunks = n32 >> 5;
+  const int kk = (nchunks + W - 1) / W;
+  const int c0 = warp * kk;
+  int mycnt = nchunks - c0;
+  mycnt = mycnt < 0 ? 0 : (mycnt > kk ? kk : mycnt);
+  const int base = c0 << 5;
+  const uint32_t lt = lanemask_lt();
+  const uint32_t le = lanemask_le();
+
+  uint32_t F[K];
+  uint32_t T = 0;
+  int32_t lastB = -1;
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    F[c] = 0;
+    if (c < mycnt) {
+      const int t = base + (c << 5) + lane;
+      bool mem = false;
+      if (t < n) {
+        const uint32_t row = permY_g[t];
+        mem = (fbX[row >> 5] >> (row & 31)) & 1u;
+      }
+      F[c] = __ballot_sync(FULL, mem);
+      const uint32_t gs = gsY[c0 + c];
+      if (gs) lastB = (int32_t)(T + __popc(F[c] & below_top(gs)));
+      T += __popc(F[c]);
+    }
+  }
+  if (lane == 0) {
+    descT[warp] = T;
+    descB[warp] = lastB;
+  }
+  __syncthreads();
+  uint32_t G, total;
+  int32_t carry;
+  cross_warp<W, true>(descT, descB, lane, warp, G, total, carry);
+  uint32_t P = G;
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    if (c < mycnt) {
+      const int t = base + (c << 5) + lane;
+      const uint32_t f = F[c];
+      const uint32_t gs = gsY[c0 + c];
+      const uint32_t P1 = P + __popc(f & lt);
+      if ((f >> lane) & 1u) {
+        const uint32_t row = permY_g[t];
+        const uint32_t seg = gs & le;
+        const uint32_t startE = seg ? P + __popc(f & below_top(seg)) : (uint32_t)carry;
+        S[P1] = rankY[row];
+        ties += P1 - startE;
+      }
+      if (gs) carry = (int32_t)(P + __popc(f & below_top(gs)));
+      P += __popc(f);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+struct TiledParams {
+  const uint16_t* perm;
+  const uint16_t* rank;
+  const uint16_t* trow;
+  const uint16_t* trun;
+  const uint32_t* nabits;
+  const uint32_t* firstbits;
+  const uint32_t* grpstart;
+  const ColStats* stats;
+  const PairUnit* units;
+  const int32_t* pj_list;
+  PairRaw* raw;
+  unsigned long long* unit_counter;
+  long long n_units;
+  int n, n32, nstride, wstride;
+};
+
+template <int W>
+struct Carve {
+  uint32_t* S;
+  uint16_t* rankY;
+  uint32_t* gsY;
+  uint32_t* nabY;
+  uint32_t* fbX;
+  uint32_t* descT;
+  int32_t* descB;
+  unsigned long long* red;
+  long long* unit_slot;
+  __device__ Carve(unsigned char* p, int n32, int nstride, int wstride) {
+    red = reinterpret_cast<unsigned long long*>(p);
+    p += sizeof(unsigned long long) * (W * 4);
+    unit_slot = reinterpret_cast<long long*>(p);
+    p += 16;
+    S = reinterpret_cast<uint32_t*>(p);
+    p += 4 * (size_t)n32;
+    gsY = reinterpret_cast<uint32_t*>(p);
+    p += 4 * (size_t)wstride;
+    nabY = reinterpret_cast<uint32_t*>(p);
+    p += 4 * (size_t)wstride;
+    fbX = reinterpret_cast<uint32_t*>(p);
+    p += 4 * (size_t)wstride;
+    descT = reinterpret_cast<uint32_t*>(p);
+    p += 4 * 32;
+    descB = reinterpret_cast<int32_t*>(p);
+    p += 4 * 32;
+    rankY = reinterpret_cast<uint16_t*>(p);
+  }
+};
+
+inline size_t tiled_smem_bytes(int W, int n32, int nstride, int wstride, bool with_rank) {
+  return 8 * (size_t)(W * 4) + 16 + 4 * (size_t)n32 + 12 * (size_t)wstride + 256 +
+         (with_rank ? 2 * (size_t)nstride : 0);
+}
+
+template <int W, int K, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Carve<W> sm(smem_raw, p.n32, p.nstride, p.wstride);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int T = 32 * W;
+  const int n = p.n, n32 = p.n32;
+  const int nwords = n32 >> 5;
+
+  for (;;) {
+    if (tid == 0) *sm.unit_slot = (long long)atomicAdd(p.unit_counter, 1ull);
+    __syncthreads();
+    const long long u = *sm.unit_slot;
+    if (u >= p.n_units) break;
+    const PairUnit unit = p.units[u];
+    const int ycol = unit.col;
+    const ColStats YS = p.stats[ycol];
+    {  // stage column y: dense ranks + tie-group starts + missing mask
+      const uint4* src = reinterpret_cast<const uint4*>(p.rank + (size_t)ycol * p.nstride);
+      uint4* dst = reinterpret_cast<uint4*>(sm.rankY);
+      for (int i = tid; i < (p.nstride >> 3); i += T) dst[i] = src[i];
+      const uint32_t* g = p.grpstart + (size_t)ycol * p.wstride;
+      const uint32_t* nb = p.nabits + (size_t)ycol * p.wstride;
+      for (int i = tid; i < nwords; i += T) {
+        sm.gsY[i] = g[i];
+        sm.nabY[i] = nb[i];
+      }
+    }
+    const uint16_t* permY_g = p.perm + (size_t)ycol * p.nstride;
+    const int L = YS.levels;
+    const uint32_t padA = (1u << L) - 1u;
+    __syncthreads();
+
+    for (int k = 0; k < unit.count; ++k) {
+      const long long slot = unit.slot0 + k;
+      const int xcol = unit.j_explicit ? p.pj_list[slot] : unit.j0 + k;
+      const ColStats XS = p.stats[xcol];
+      const uint16_t* permX = p.perm + (size_t)xcol * p.nstride;
+      const uint32_t* fbXg = p.firstbits + (size_t)xcol * p.wstride;
+      const uint32_t* nbXg = p.nabits + (size_t)xcol * p.wstride;
+      uint32_t bpart = 0;
+      for (int i = tid; i < nwords; i += T) {
+        sm.fbX[i] = fbXg[i];
+        bpart += __popc(nbXg[i] & sm.nabY[i]);
+      }
+      if (YS.n_groups < 2 || XS.n_groups < 2) {
+        // a constant or all-missing column: K3 reports NA; only the joint-missing count is kept
+        const unsigned long long sb = warp_sum_u64(bpart);
+        if (lane == 0) sm.red[warp * 4 + 3] = sb;
+        __syncthreads();
+        if (tid == 0) {
+          unsigned long long bb = 0;
+          for (int w = 0; w < W; ++w) bb += sm.red[w * 4 + 3];
+          PairRaw r;
+          r.dis = 0;
+          r.ntie = 0;
+          r.b = (long long)bb;
+          p.raw[slot] = r;
+        }
+        __syncthreads();
+        continue;
+      }
+      const int f = XS.first_run;
+      for (int q = f + tid; q < n32; q += T) sm.S[q] = (q < n) ? (uint32_t)sm.rankY[permX[q]] : padA;
+      __syncthreads();
+      uint32_t ties = 0;
+      if (f > 0)
+        emit_first_group<W, K>(sm.S, n, n32, permY_g, sm.rankY, sm.gsY, sm.fbX, sm.descT, sm.descB,
+                               lane, warp, ties);
+      __syncthreads();
+      uint32_t accA = 0, accB = 0, dummy = 0;
+      partition_pass<W, K, false>(sm.S, n32, n, L, sm.descT, sm.descB, lane, warp, accA, dummy);
+      const int m = XS.n_tied;
+      if (m > 0) {
+        const int m32 = (m + 31) & ~31;
+        const uint16_t* trow = p.trow + (size_t)xcol * p.nstride;
+        const uint16_t* trun = p.trun + (size_t)xcol * p.nstride;
+        for (int t = tid; t < m32; t += T)
+          sm.S[t] = (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)sm.rankY[trow[t]]) : 0xffffffffu;
+        __syncthreads();
+        partition_pass<W, K, true>(sm.S, m32, m, L, sm.descT, sm.descB, lane, warp, accB, ties);
+      }
+      const unsigned long long sA = warp_sum_u64(accA), sB = warp_sum_u64(accB),
+                               sT = warp_sum_u64(ties), sb = warp_sum_u64(bpart);
+      if (lane == 0) {
+        sm.red[warp * 4 + 0] = sA;
+        sm.red[warp * 4 + 1] = sB;
+        sm.red[warp * 4 + 2] = sT;
+        sm.red[warp * 4 + 3] = sb;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long a = 0, b2 = 0, t2 = 0, bb = 0;
+        for (int w = 0; w < W; ++w) {
+          a += sm.red[w * 4 + 0];
+          b2 += sm.red[w * 4 + 1];
+          t2 += sm.red[w * 4 + 2];
+          bb += sm.red[w * 4 + 3];
+        }
+        PairRaw r;
+        r.dis = (long long)(a - YS.cconst - b2);
+        r.ntie = (long long)t2;
+        r.b = (long long)bb;
+        p.raw[slot] = r;
+      }
+      __syncthreads();
+    }
+    __syncthreads();  // unit_slot is rewritten at the top of the loop
+  }
+}
+
+// cconst of every column: the raw pass-A count of the column's own sorted rank sequence
+// (no inversions), evaluated by the same code path and padding as the pair kernel.
+template <int W, int K, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB)
+    column_const_kernel(const uint16_t* __restrict__ perm, const uint16_t* __restrict__ rank,
+                        ColStats* stats, int n, int n32, int nstride, int wstride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Carve<W> sm(smem_raw, n32, nstride, wstride);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int T = 32 * W;
+  const int col = blockIdx.x;
+  const ColStats CS = stats[col];
+  if (CS.n_groups < 2) {
+    if (tid == 0) stats[col].cconst = 0;
+    return;
+  }
+  const uint16_t* pm = perm + (size_t)col * nstride;
+  const uint16_t* rk = rank + (size_t)col * nstride;
+  const uint32_t padA = (1u << CS.levels) - 1u;
+  for (int q = tid; q < n32; q += T) sm.S[q] = (q < n) ? (uint32_t)rk[pm[q]] : padA;
+  __syncthreads();
+  uint32_t acc = 0, dummy = 0;
+  partition_pass<W, K, false>(sm.S, n32, n, CS.levels, sm.descT, sm.descB, lane, warp, acc, dummy);
+  const unsigned long long s = warp_sum_u64(acc);
+  if (lane == 0) sm.red[warp] = s;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long a = 0;
+    for (int w = 0; w < W; ++w) a += sm.red[w];
+    stats[col].cconst = a;
+  }
+}
+
+// ---- K2-naive: one thread per pair, the reference's Fenwick algorithm ---------------------
+// (src/kendallc.cpp:70-100) on the precomputed ranks, Fenwick array and a per-group counter
+// array in global memory.  This is the internal baseline BASELINE.json names and an
+// independent on-device cross-check of the tiled kernel.
+__global__ void pairs_naive_kernel(const TiledParams p, long long P, uint32_t* scratch,
+                                   long long n_threads) {
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid0 >= n_threads) return;
+  const int n = p.n;
+  uint32_t* bit = scratch + (size_t)tid0 * (2 * (size_t)n + 2);  // Fenwick tree, 1-based
+  uint32_t* cnt = bit + n + 1;                                    // joint-tie counters per y rank
+  // thread t takes units t, t + n_threads, ...
+  for (long long u = tid0; u < p.n_units; u += n_threads) {
+    const PairUnit unit = p.units[u];
+    for (int k = 0; k < unit.count; ++k) {
+      const long long slot = unit.slot0 + k;
+      const int ycol = unit.col;
+      const int xcol = unit.j_explicit ? p.pj_list[slot] : unit.j0 + k;
+      const ColStats XS = p.stats[xcol], YS = p.stats[ycol];
+      PairRaw r;
+      r.dis = 0;
+      r.ntie = 0;
+      r.b = 0;
+      if (XS.n_groups >= 2 && YS.n_groups >= 2) {
+        const uint16_t* permX = p.perm + (size_t)xcol * p.nstride;
+        const uint16_t* rankX = p.rank + (size_t)xcol * p.nstride;
+        const uint16_t* rankY = p.rank + (size_t)ycol * p.nstride;
+        const int sup = YS.n_groups + 1;
+        for (int i = 0; i <= sup; ++i) bit[i] = 0;
+        for (int i = 0; i < sup; ++i) cnt[i] = 0;
+        long long dis = 0, ntie = 0;
+        int i = 0, kk = 0;
+        while (i < n) {
+          const int xg = rankX[permX[i]];
+          while (kk < n && rankX[permX[kk]] == xg) {  // query the whole x group first
+            dis += i;
+            int idx = (int)rankY[permX[kk]] + 1;
+            ntie += cnt[idx - 1]++;
+            while (idx != 0) {
+              dis -= bit[idx];
+              idx &= idx - 1;
+            }
+            ++kk;
+          }
+          while (i < kk) {  // then insert it
+            int idx = (int)rankY[permX[i]] + 1;
+            cnt[idx - 1] = 0;
+            while (idx < sup) {
+              bit[idx] += 1;
+              idx += idx & (-idx);
+            }
+            ++i;
+          }
+        }
+        r.dis = dis;
+        r.ntie = ntie;
+      }
+      {
+        const uint32_t* nbX = p.nabits + (size_t)xcol * p.wstride;
+        const uint32_t* nbY = p.nabits + (size_t)ycol * p.wstride;
+        long long b = 0;
+        for (int w = 0; w < (p.n32 >> 5); ++w) b += __popc(nbX[w] & nbY[w]);
+        r.b = b;
+      }
+      p.raw[slot] = r;
+    }
+  }
+}
+
+// ---- K3: fp64 epilogue -------------------------------------------------------------------
+struct EpiParams {
+  const ColStats* stats;
+  const PairUnit* units;
+  const int32_t* pj_list;
+  const PairRaw* raw;
+  double* tau;
+  double* pvalue;
+  double* taumax;
+  double* completeness;
+  int32_t* status;
+  long long* counts;
+  unsigned long long* max_bits;
+  long long n_units;
+  long long n;
+  int perspective, alternative, continuity;
+};
+
+__global__ void __launch_bounds__(128) epilogue_kernel(const EpiParams p) {
+  // 4 units per block, one warp per unit (a unit holds at most 32 pairs)
+  const long long u = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  double mx = -1.0;
+  if (u < p.n_units) {
+    const PairUnit unit = p.units[u];
+    for (int k = lane; k < unit.count; k += 32) {
+      const long long slot = unit.slot0 + k;
+      const int xcol = unit.j_explicit ? p.pj_list[slot] : unit.j0 + k;
+      const PairRaw r = p.raw[slot];
+      PairOut o;
+      // reference naming: x = first column of the pair (unit.col), y = the second
+      pair_epilogue(p.n, p.stats[unit.col], p.stats[xcol], r.dis, r.ntie, r.b, p.perspective,
+                    p.alternative, p.continuity, o);
+      p.tau[slot] = o.tau;
+      if (p.pvalue) p.pvalue[slot] = o.pvalue;
+      if (p.taumax) p.taumax[slot] = o.taumax;
+      if (p.completeness) p.completeness[slot] = o.completeness;
+      if (p.status) p.status[slot] = o.status;
+      if (p.counts) {
+        long long* c = p.counts + 7 * slot;
+        c[0] = r.dis;
+        c[1] = (p.perspective == 1) ? r.ntie - r.b * (r.b - 1) / 2 : r.ntie;
+        c[2] = o.xtie;
+        c[3] = o.ytie;
+        c[4] = o.tot;
+        c[5] = o.n_entry;
+        c[6] = r.b;
+      }
+      if (o.status == 0 && o.taumax == o.taumax) mx = fmax(mx, o.taumax);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, d));
+  // tau_max >= 0, so the IEEE bit pattern orders like an unsigned integer
+  if (lane == 0 && mx >= 0.0) atomicMax(p.max_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+__global__ void pnorm_kernel(const double* z, long long n, int lower, double* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = pnorm_std(z[i], lower != 0);
+}
+
+TiledParams make_params(const PairLaunch& pl) {
+  const ColumnTables& t = *pl.tab;
+  TiledParams p;
+  p.perm = t.perm;
+  p.rank = t.rank;
+  p.trow = t.trow;
+  p.trun = t.trun;
+  p.nabits = t.nabits;
+  p.firstbits = t.firstbits;
+  p.grpstart = t.grpstart;
+  p.stats = t.stats;
+  p.units = pl.units;
+  p.pj_list = pl.pj_list;
+  p.raw = pl.raw;
+  p.unit_counter = pl.unit_counter;
+  p.n_units = pl.n_units;
+  p.n = (int)t.n;
+  p.n32 = (int)((t.n + 31) & ~31LL);
+  p.nstride = (int)t.nstride;
+  p.wstride = (int)t.wstride;
+  return p;
+}
+
+template <int W, int K, int MINB>
+int launch_tiled_t(const TiledParams& p, int n_sm, cudaStream_t stream) {
+  const size_t smem = tiled_smem_bytes(W, p.n32, p.nstride, p.wstride, true);
+  auto kern = pairs_tiled_kernel<W, K, MINB>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem) != cudaSuccess || per_sm < 1)
+    return -1;
+  long long grid = (long long)n_sm * per_sm;
+  if (grid > p.n_units) grid = p.n_units;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, 32 * W, smem, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+template <int W, int K, int MINB>
+int launch_const_t(ColumnTables& t, cudaStream_t stream) {
+  const int n32 = (int)((t.n + 31) & ~31LL);
+  const size_t smem = tiled_smem_bytes(W, n32, (int)t.nstride, (int)t.wstride, false);
+  auto kern = column_const_kernel<W, K, MINB>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  kern<<<(unsigned)t.C, 32 * W, smem, stream>>>(t.perm, t.rank, t.stats, (int)t.n, n32, (int)t.nstride,
+                                               (int)t.wstride);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace
+
+int64_t tiled_max_n() { return 32768; }
+
+// The (warps, chunks-per-warp) shape is chosen from n; both launchers must agree because
+// cconst depends on the padded length only, not on the shape -- they do by construction,
+// the shape only has to cover n32.
+#define ICIKT_DISPATCH(FN, ...)                                   \
+  do {                                                            \
+    if (n32 <= 2048) return FN<4, 16, 8>(__VA_ARGS__);            \
+    if (n32 <= 4096) return FN<8, 16, 4>(__VA_ARGS__);            \
+    if (n32 <= 8192) return FN<16, 16, 2>(__VA_ARGS__);           \
+    if (n32 <= 16384) return FN<32, 16, 1>(__VA_ARGS__);          \
+    if (n32 <= 24576) return FN<32, 24, 1>(__VA_ARGS__);          \
+    if (n32 <= 32768) return FN<32, 32, 1>(__VA_ARGS__);          \
+    return -1;                                                    \
+  } while (0)
+
+int launch_pairs_tiled(const PairLaunch& pl, int n_sm, cudaStream_t stream) {
+  if (cudaMemsetAsync(pl.unit_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+  const TiledParams p = make_params(pl);
+  const int n32 = p.n32;
+  ICIKT_DISPATCH(launch_tiled_t, p, n_sm, stream);
+}
+
+int launch_column_consts(ColumnTables& tab, cudaStream_t stream) {
+  const int n32 = (int)((tab.n + 31) & ~31LL);
+  ICIKT_DISPATCH(launch_const_t, tab, stream);
+}
+
+size_t naive_scratch_bytes(int64_t n, int64_t n_threads) {
+  return sizeof(uint32_t) * (size_t)n_threads * (2 * (size_t)n + 2);
+}
+
+int launch_pairs_naive(const PairLaunch& pl, int64_t P, uint32_t* d_scratch, int64_t n_threads,
+                       cudaStream_t stream) {
+  const TiledParams p = make_params(pl);
+  const int block = 128;
+  const long long grid = (n_threads + block - 1) / block;
+  pairs_naive_kernel<<<(unsigned)grid, block, 0, stream>>>(p, P, d_scratch, n_threads);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream) {
+  EpiParams p;
+  p.stats = el.tab->stats;
+  p.units = el.units;
+  p.pj_list = el.pj_list;
+  p.raw = el.raw;
+  p.tau = el.tau;
+  p.pvalue = el.pvalue;
+  p.taumax = el.taumax;
+  p.completeness = el.completeness;
+  p.status = el.status;
+  p.counts = reinterpret_cast<long long*>(el.counts);
+  p.max_bits = el.max_taumax_bits;
+  p.n_units = el.n_units;
+  p.n = el.tab->n;
+  p.perspective = el.perspective;
+  p.alternative = el.alternative;
+  p.continuity = el.continuity;
+  if (el.n_units <= 0) return 0;
+  const long long grid = (el.n_units + 3) / 4;
+  epilogue_kernel<<<(unsigned)grid, 128, 0, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_pnorm(const double* d_z, int64_t n, int lower, double* d_out, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  pnorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_z, n, lower, d_out);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace icikt

@@ -1,0 +1,171 @@
+/* include/icikt_b200.h -- C ABI of libicikt_b200.so (CUDA, sm_100a).
+ *
+ * Drop-in boundary for the ONE hot path of ICIKendallTau: the all-pairs / pair-list
+ * information-content-informed Kendall-tau-b.  It replaces, in one batched call,
+ *
+ *   - the R pair loop            R/kendalltau.R:158 + ici_split R/kendalltau.R:280-308
+ *     (and kt_split R/kendalltau.R:310-354 for kt_fast),
+ *   - the per-pair FFI call      .Call('_ICIKendallTau_ici_kt', ...)  R/RcppExports.R:62-64,
+ *                                SEXP _ICIKendallTau_ici_kt(SEXP x6)  src/RcppExports.cpp:83-96,
+ *   - the native pair kernel     ici_kt()  src/kendallc.cpp:166-366 and its helpers :5-129,
+ *   - the missing-value marking  setup_missing_matrix  R/utils.R:1-23 (fused into the
+ *                                per-column preprocessing kernel).
+ *
+ * (Paths are relative to the reference repository.)  Plain C: pointers and sizes only,
+ * no torch / Rcpp types.  There is NO CPU fallback: every entry point returns
+ * ICIKT_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Conventions
+ *   data      column-major n x C doubles, leading dimension ld >= n (R matrix layout);
+ *             n = features = vector length, C = samples = columns being correlated.
+ *   missing   a value is missing if it is NaN/NA, or (na_inf) +-Inf, or equal to one of
+ *             the finite literals in global_na[] -- exactly R/utils.R:1-23.  For the
+ *             plain ici_kt()/kt_fast() semantics pass n_global_na = 0 and na_inf = 0
+ *             (NaN only, src/kendallc.cpp:181,190-191).
+ *   pairs     0-based column indices.  icikt_all_pairs enumerates utils::combn(C, 2)
+ *             order (0,1),(0,2)...(C-2,C-1) and, if include_diag, appends (0,0)...(C-1,C-1)
+ *             exactly as setup_comparisons does when !diag_good (R/kendalltau.R:188-194).
+ *   outputs   caller-allocated arrays of length P (pair order above).  Degenerate pairs
+ *             get NaN in all four doubles and a non-zero status so the R shim can turn them
+ *             into NA_real_ and raise the reference's warnings once per class.
+ *   counts    optional int64[P][ICIKT_NCOUNTS]: dis, ntie, xtie, ytie, tot, n_entry, b
+ *             (bit-exact against the reference's integer intermediates, for tests).
+ */
+#ifndef ICIKT_B200_H
+#define ICIKT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICIKT_ABI_VERSION 1
+
+/* return codes */
+#define ICIKT_OK 0
+#define ICIKT_ERR_NO_DEVICE (-1)  /* no CUDA device / driver: there is no CPU fallback     */
+#define ICIKT_ERR_BAD_ARG (-2)    /* NULL pointer, n < 1, C < 1, bad pair index, ...       */
+#define ICIKT_ERR_TOO_LONG (-3)   /* n > icikt_max_n()                                     */
+#define ICIKT_ERR_CUDA (-4)       /* CUDA runtime failure, see icikt_last_error()          */
+#define ICIKT_ERR_ALLOC (-5)      /* host or device allocation failed                      */
+
+/* per-pair status (src/kendallc.cpp line of the matching early return) */
+#define ICIKT_STATUS_OK 0
+#define ICIKT_STATUS_ALL_NA 1        /* :190-199  silent NA                                 */
+#define ICIKT_STATUS_TOO_SHORT 2     /* :224-231  "The vectors only have a single value"     */
+#define ICIKT_STATUS_SINGLE_UNIQUE 3 /* :234-244  "... have only a single unique value"      */
+#define ICIKT_STATUS_ALL_TIED 4      /* :291-298  "Ties equal the total"                     */
+
+#define ICIKT_PERSPECTIVE_GLOBAL 0 /* any string other than "local", src/kendallc.cpp:180 */
+#define ICIKT_PERSPECTIVE_LOCAL 1
+
+#define ICIKT_ALT_TWO_SIDED 0
+#define ICIKT_ALT_LESS 1
+#define ICIKT_ALT_GREATER 2
+#define ICIKT_ALT_OTHER 3 /* unknown string: p-value stays 0, src/kendallc.cpp:323-332 */
+
+#define ICIKT_NCOUNTS 7
+#define ICIKT_COUNT_DIS 0
+#define ICIKT_COUNT_NTIE 1
+#define ICIKT_COUNT_XTIE 2
+#define ICIKT_COUNT_YTIE 3
+#define ICIKT_COUNT_TOT 4
+#define ICIKT_COUNT_N_ENTRY 5
+#define ICIKT_COUNT_B 6 /* rows missing in both columns */
+
+#define ICIKT_KERNEL_TILED 0 /* one CTA per pair, shared-memory bit-partition counting */
+#define ICIKT_KERNEL_NAIVE 1 /* one thread per pair, Fenwick tree in global memory
+                                (the internal baseline BASELINE.json names)           */
+
+typedef struct icikt_opts {
+  int32_t perspective;  /* ICIKT_PERSPECTIVE_*  (ici_kt argument `perspective`)          */
+  int32_t alternative;  /* ICIKT_ALT_*          (ici_kt argument `alternative`)          */
+  int32_t continuity;   /* 0/1                  (ici_kt argument `continuity`)           */
+  int32_t include_diag; /* all-pairs only: append the C (i,i) pairs (!diag_good)         */
+  int32_t na_inf;       /* treat +-Inf as missing (Inf present in global_na)             */
+  int32_t device;       /* CUDA device ordinal to run on                                 */
+  int32_t kernel;       /* ICIKT_KERNEL_*                                                */
+  int32_t want_counts;  /* plan API: allocate and fill the int64 counts (one-shot: set from `counts`) */
+  int64_t pair_lo;      /* compute only pairs [pair_lo, pair_hi) of the pair order; the   */
+  int64_t pair_hi;      /* output arrays are still indexed from 0 = pair_lo.  0,0 = all.  */
+} icikt_opts;
+
+typedef struct icikt_timings { /* milliseconds, CUDA events on the library's stream */
+  float h2d_ms;     /* host -> device copy of the data matrix                         */
+  float columns_ms; /* per-column preprocessing kernels (K1)                          */
+  float pairs_ms;   /* pair kernel incl. fused epilogue (K2+K3)                       */
+  float d2h_ms;     /* device -> host copy of the results                             */
+  float total_ms;   /* first to last event                                            */
+  int32_t n_launches; /* kernels launched by this call                                */
+  int32_t reserved;
+} icikt_timings;
+
+/* defaults: global, two.sided, no continuity, no diag, NaN-only missing, device 0, tiled */
+void icikt_default_opts(icikt_opts* o);
+
+int icikt_abi_version(void);
+int icikt_device_count(void);          /* 0 when no usable device                      */
+int64_t icikt_max_n(void);             /* longest supported vector (features)          */
+const char* icikt_last_error(void);    /* thread-local message of the last failure     */
+
+/* Replaces R/kendalltau.R:158 for the all-pairs case.  P = C*(C-1)/2 (+ C).
+ * pvalue/taumax/completeness/status/counts/max_taumax/timings may be NULL.
+ * max_taumax receives max(taumax, na.rm = TRUE) over the computed pairs
+ * (R/kendalltau.R:368-370), or NaN if every pair is degenerate.                      */
+int icikt_all_pairs(const double* data, int64_t n, int64_t C, int64_t ld,
+                    const double* global_na, int32_t n_global_na, const icikt_opts* opts,
+                    double* raw, double* pvalue, double* taumax, double* completeness,
+                    int32_t* status, int64_t* counts, double* max_taumax,
+                    icikt_timings* timings);
+
+/* Same for an explicit pair list (include_only, ici_kt(x, y) with C = 2 and P = 1,
+ * kt_fast incl. (i,i) pairs).  pi[k], pj[k] in [0, C).                               */
+int icikt_pair_list(const double* data, int64_t n, int64_t C, int64_t ld,
+                    const double* global_na, int32_t n_global_na, const int32_t* pi,
+                    const int32_t* pj, int64_t P, const icikt_opts* opts, double* raw,
+                    double* pvalue, double* taumax, double* completeness, int32_t* status,
+                    int64_t* counts, double* max_taumax, icikt_timings* timings);
+
+/* ---- plan API: keeps the matrix, the per-column tables and the results resident in
+ * HBM so that repeated runs (benchmarks, several perspectives on one matrix) do not
+ * pay the copies.  A plan is bound to one device and is not thread-safe.            */
+typedef struct icikt_plan icikt_plan;
+
+/* pi/pj NULL => all pairs (honours opts->include_diag, pair_lo/pair_hi).            */
+int icikt_plan_create(icikt_plan** plan, int64_t n, int64_t C, const int32_t* pi,
+                      const int32_t* pj, int64_t P, const icikt_opts* opts);
+int64_t icikt_plan_num_pairs(const icikt_plan* plan);
+/* copy the host matrix into the plan's device buffer (pinned staging inside)        */
+int icikt_plan_upload(icikt_plan* plan, const double* data, int64_t ld);
+/* or hand over a device pointer (column-major, ld), e.g. a torch tensor's data_ptr  */
+int icikt_plan_set_device_matrix(icikt_plan* plan, const double* d_data, int64_t ld);
+/* K1: missing marking, sort, dense ranks, tie sums, per-column tables               */
+int icikt_plan_columns(icikt_plan* plan, const double* global_na, int32_t n_global_na);
+/* K2+K3 over the plan's pairs; results stay on the device                           */
+int icikt_plan_pairs(icikt_plan* plan);
+/* block until the plan's stream is idle                                             */
+int icikt_plan_sync(icikt_plan* plan);
+/* copy results to host arrays (any may be NULL)                                     */
+int icikt_plan_download(icikt_plan* plan, double* raw, double* pvalue, double* taumax,
+                        double* completeness, int32_t* status, int64_t* counts,
+                        double* max_taumax);
+/* per-column by-products: n_na[C] (missing count per column, gives n_good and
+ * frac_complete of R/kendalltau.R:165-167); may be NULL                             */
+int icikt_plan_column_info(icikt_plan* plan, int32_t* n_na);
+/* the CUDA stream the plan launches on, as a cudaStream_t cast to void*             */
+void* icikt_plan_stream(icikt_plan* plan);
+/* timings of the last upload/columns/pairs/download calls                           */
+int icikt_plan_timings(icikt_plan* plan, icikt_timings* t);
+void icikt_plan_destroy(icikt_plan* plan);
+
+/* Standard normal CDF exactly as the epilogue kernel evaluates it (R nmath pnorm
+ * semantics incl. the exact-zero tails), computed ON THE DEVICE for n values.
+ * Test hook for the p-value path; lower_tail as in pnorm().                         */
+int icikt_pnorm_device(const double* z, int64_t n, int32_t lower_tail, double* out,
+                       int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICIKT_B200_H */
