@@ -27,7 +27,8 @@ EXPORTS = [
     "icikt_plan_num_pairs", "icikt_plan_upload", "icikt_plan_set_device_matrix",
     "icikt_plan_columns", "icikt_plan_pairs", "icikt_plan_sync", "icikt_plan_download",
     "icikt_plan_column_info", "icikt_plan_stream", "icikt_plan_timings", "icikt_plan_destroy",
-    "icikt_pnorm_device",
+    "icikt_pnorm_device", "icikt_release_workspace", "icikt_measure_smem_bandwidth",
+    "icikt_pair_from_index",
 ]
 
 
@@ -47,7 +48,7 @@ class Opts(ctypes.Structure):
 
 class Timings(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("columns_ms", ctypes.c_float),
-                ("pairs_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
+                ("pairs_ms", ctypes.c_float), ("epilogue_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
                 ("total_ms", ctypes.c_float), ("n_launches", ctypes.c_int32),
                 ("reserved", ctypes.c_int32)]
 
@@ -112,6 +113,12 @@ def load():
     L.icikt_plan_destroy.restype = None
     L.icikt_pnorm_device.argtypes = [_dp, ctypes.c_int64, ctypes.c_int32, _dp, ctypes.c_int32]
     L.icikt_pnorm_device.restype = ctypes.c_int
+    L.icikt_pair_from_index.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _ip, _ip]
+    L.icikt_pair_from_index.restype = ctypes.c_int
+    L.icikt_release_workspace.argtypes = []
+    L.icikt_release_workspace.restype = None
+    L.icikt_measure_smem_bandwidth.argtypes = [ctypes.c_int32, _dp, _dp]
+    L.icikt_measure_smem_bandwidth.restype = ctypes.c_int
     _lib = L
     return L
 
@@ -270,3 +277,20 @@ def pnorm_device(z, lower_tail=True, device=0):
     out = np.empty_like(z)
     check(load().icikt_pnorm_device(_ptr(z, _dp), z.size, int(bool(lower_tail)), _ptr(out, _dp), device))
     return out
+
+
+def release_workspace():
+    load().icikt_release_workspace()
+
+
+def measure_smem_bandwidth(device=0):
+    """(GB/s with 32-bit accesses, GB/s with 128-bit accesses) of a conflict-free load+store sweep."""
+    a, b = ctypes.c_double(0), ctypes.c_double(0)
+    check(load().icikt_measure_smem_bandwidth(device, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
+
+
+def pair_from_index(C, index, include_diag=False):
+    i, j = ctypes.c_int32(), ctypes.c_int32()
+    check(load().icikt_pair_from_index(C, int(bool(include_diag)), int(index), ctypes.byref(i), ctypes.byref(j)))
+    return i.value, j.value

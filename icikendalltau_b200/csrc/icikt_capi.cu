@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -70,7 +71,7 @@ struct icikt_plan {
   uint32_t* d_naive = nullptr;
   int64_t naive_threads = 0;
 
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[9]{};
   icikt_timings tm{};
 };
 
@@ -374,8 +375,9 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
 int icikt_plan_pairs(icikt_plan* p) {
   if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
   CK(cudaSetDevice(p->device));
-  CK(cudaEventRecord(p->ev[4], p->stream));
   CK(cudaMemsetAsync(p->d_scalars, 0, 2 * sizeof(unsigned long long), p->stream));
+  CK(cudaEventRecord(p->ev[4], p->stream));
+  if (p->P <= 0) CK(cudaEventRecord(p->ev[8], p->stream));
   PairLaunch pl;
   pl.tab = &p->tab;
   pl.units = p->d_units;
@@ -392,6 +394,7 @@ int icikt_plan_pairs(icikt_plan* p) {
       l = launch_pairs_tiled(pl, p->n_sm, p->stream);
     if (l < 0) return cuda_fail(cudaGetLastError(), "pair kernel");
     launches += l;
+    CK(cudaEventRecord(p->ev[8], p->stream));
     EpilogueLaunch el;
     el.tab = &p->tab;
     el.units = p->d_units;
@@ -473,7 +476,8 @@ int icikt_plan_timings(icikt_plan* p, icikt_timings* t) {
   t->n_launches = launches;
   if (cudaEventQuery(p->ev[1]) == cudaSuccess) t->h2d_ms = ev_ms(p->ev[0], p->ev[1]);
   if (cudaEventQuery(p->ev[3]) == cudaSuccess) t->columns_ms = ev_ms(p->ev[2], p->ev[3]);
-  if (cudaEventQuery(p->ev[5]) == cudaSuccess) t->pairs_ms = ev_ms(p->ev[4], p->ev[5]);
+  if (cudaEventQuery(p->ev[8]) == cudaSuccess) t->pairs_ms = ev_ms(p->ev[4], p->ev[8]);
+  if (cudaEventQuery(p->ev[5]) == cudaSuccess) t->epilogue_ms = ev_ms(p->ev[8], p->ev[5]);
   if (cudaEventQuery(p->ev[7]) == cudaSuccess) t->d2h_ms = ev_ms(p->ev[6], p->ev[7]);
   if (cudaEventQuery(p->ev[0]) == cudaSuccess && cudaEventQuery(p->ev[7]) == cudaSuccess)
     t->total_ms = ev_ms(p->ev[0], p->ev[7]);
@@ -482,6 +486,16 @@ int icikt_plan_timings(icikt_plan* p, icikt_timings* t) {
 }
 
 void icikt_plan_destroy(icikt_plan* p) { free_plan(p); }
+
+// One cached plan for the one-shot entry points (all-pairs shape only).
+static icikt_plan* g_cached = nullptr;
+static std::mutex g_cache_mu;
+
+static bool cache_matches(const icikt_plan* p, int64_t n, int64_t C, const icikt_opts& o) {
+  return p && p->n == n && p->C == C && p->opts.device == o.device && p->opts.kernel == o.kernel &&
+         p->opts.include_diag == o.include_diag && p->opts.pair_lo == o.pair_lo &&
+         p->opts.pair_hi == o.pair_hi && p->want_counts == (o.want_counts != 0);
+}
 
 static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
                     int32_t n_global_na, const int32_t* pi, const int32_t* pj, int64_t P,
@@ -492,18 +506,70 @@ static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const 
   icikt_opts o;
   if (opts) o = *opts; else icikt_default_opts(&o);
   o.want_counts = counts ? 1 : 0;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
   icikt_plan* p = nullptr;
-  int rc = icikt_plan_create(&p, n, C, pi, pj, P, &o);
-  if (rc != ICIKT_OK) return rc;
+  const bool cacheable = (pi == nullptr);
+  int rc = ICIKT_OK;
+  if (cacheable && cache_matches(g_cached, n, C, o)) {
+    p = g_cached;
+    p->opts.perspective = o.perspective;
+    p->opts.alternative = o.alternative;
+    p->opts.continuity = o.continuity;
+    p->opts.na_inf = o.na_inf;
+  } else {
+    if (cacheable && g_cached) { icikt_plan_destroy(g_cached); g_cached = nullptr; }
+    rc = icikt_plan_create(&p, n, C, pi, pj, P, &o);
+    if (rc != ICIKT_OK) return rc;
+    if (cacheable) g_cached = p;
+  }
   rc = icikt_plan_upload(p, data, ld);
   if (rc == ICIKT_OK) rc = icikt_plan_columns(p, global_na, n_global_na);
   if (rc == ICIKT_OK) rc = icikt_plan_pairs(p);
   if (rc == ICIKT_OK) rc = icikt_plan_download(p, raw, pvalue, taumax, completeness, status, counts, max_taumax);
   if (rc == ICIKT_OK && timings) rc = icikt_plan_timings(p, timings);
   const std::string keep = g_err;
-  icikt_plan_destroy(p);
+  if (!cacheable) {
+    icikt_plan_destroy(p);
+  } else if (rc != ICIKT_OK) {
+    icikt_plan_destroy(g_cached);
+    g_cached = nullptr;
+  }
   if (rc != ICIKT_OK) g_err = keep;
   return rc;
+}
+
+int icikt_pair_from_index(int64_t C, int32_t include_diag, int64_t index, int32_t* i, int32_t* j) {
+  if (C < 1 || !i || !j || index < 0) return fail(ICIKT_ERR_BAD_ARG, "bad pair index arguments");
+  const int64_t ptri = tri_pairs(C);
+  if (index >= ptri) {
+    if (!include_diag || index >= ptri + C) return fail(ICIKT_ERR_BAD_ARG, "pair index out of range");
+    *i = *j = (int32_t)(index - ptri);
+    return ICIKT_OK;
+  }
+  // row r starts at r(2C-r-1)/2: invert with a float guess, then fix up exactly
+  const double b = 2.0 * (double)C - 1.0;
+  int64_t r = (int64_t)((b - std::sqrt(b * b - 8.0 * (double)index)) / 2.0);
+  r = std::max<int64_t>(0, std::min<int64_t>(r, C - 2));
+  while (r > 0 && row_start(r, C) > index) --r;
+  while (r + 1 < C - 1 && row_start(r + 1, C) <= index) ++r;
+  *i = (int32_t)r;
+  *j = (int32_t)(r + 1 + (index - row_start(r, C)));
+  return ICIKT_OK;
+}
+
+void icikt_release_workspace(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  if (g_cached) { icikt_plan_destroy(g_cached); g_cached = nullptr; }
+}
+
+int icikt_measure_smem_bandwidth(int32_t device, double* g32, double* g128) {
+  int rc = select_device(device);
+  if (rc != ICIKT_OK) return rc;
+  double a = 0, b = 0;
+  if (measure_smem_bandwidth(&a, &b) < 0) return cuda_fail(cudaGetLastError(), "smem bandwidth kernel");
+  if (g32) *g32 = a;
+  if (g128) *g128 = b;
+  return ICIKT_OK;
 }
 
 int icikt_all_pairs(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,

@@ -96,4 +96,7 @@ int launch_pnorm(const double* d_z, int64_t n, int lower, double* d_out, cudaStr
 
 int64_t tiled_max_n();
 
+// shared-memory read+write sweep, GB/s for 32-bit and 128-bit accesses (benchmark utility)
+int measure_smem_bandwidth(double* gbps32, double* gbps128);
+
 }  // namespace icikt

@@ -28,6 +28,7 @@
 //   Each level is two warp-synchronous sweeps over register-resident chunks (ballot/popc
 //   prefix sums), one cross-warp scan of W per-warp totals, and an in-place scatter in
 //   shared memory; two __syncthreads per level.
+#include <algorithm>
 #include <cstdio>
 
 #include "icikt_internal.h"
@@ -589,6 +590,65 @@ __global__ void pnorm_kernel(const double* z, long long n, int lower, double* ou
   if (i < n) out[i] = pnorm_std(z[i], lower != 0);
 }
 
+
+// ---- shared-memory bandwidth microbenchmark (roofline denominator) -----------------------
+// Conflict-free sweep: every thread loads one word (or one uint4) and stores one per step.
+template <typename T>
+__global__ void __launch_bounds__(1024) smem_sweep_kernel(int iters, unsigned* sink) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s = reinterpret_cast<T*>(smem_raw);
+  constexpr int N = 4096;  // elements of T per CTA
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N; i += 1024) s[i] = T{};
+  __syncthreads();
+  T a0 = s[tid], a1 = s[tid + 1024], a2 = s[tid + 2048], a3 = s[tid + 3072];
+  for (int it = 0; it < iters; ++it) {
+    s[tid] = a1;
+    s[tid + 1024] = a2;
+    s[tid + 2048] = a3;
+    s[tid + 3072] = a0;
+    __syncwarp();
+    a0 = s[tid];
+    a1 = s[tid + 1024];
+    a2 = s[tid + 2048];
+    a3 = s[tid + 3072];
+    __syncwarp();
+  }
+  s[tid] = a0;
+  s[tid + 1024] = a1;
+  s[tid + 2048] = a2;
+  s[tid + 3072] = a3;
+  __syncthreads();
+  if (tid == 0) sink[blockIdx.x] = *reinterpret_cast<unsigned*>(&s[blockIdx.x & 1023]);
+}
+
+template <typename T>
+double run_smem_sweep(int n_sm, unsigned* d_sink) {
+  const int iters = 4000;
+  const size_t smem = sizeof(T) * 4096;
+  auto kern = smem_sweep_kernel<T>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  const int grid = n_sm * 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  kern<<<grid, 1024, smem>>>(iters / 10, d_sink);  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    kern<<<grid, 1024, smem>>>(iters, d_sink);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1; break; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = (double)grid * 1024.0 * iters * 4.0 * 2.0 * sizeof(T);  // 4 loads + 4 stores
+    best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
+
 TiledParams make_params(const PairLaunch& pl) {
   const ColumnTables& t = *pl.tab;
   TiledParams p;
@@ -643,6 +703,21 @@ int launch_const_t(ColumnTables& t, cudaStream_t stream) {
 }  // namespace
 
 int64_t tiled_max_n() { return 32768; }
+
+int measure_smem_bandwidth(double* gbps32, double* gbps128) {
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  unsigned* d_sink = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&d_sink), sizeof(unsigned) * n_sm * 2) != cudaSuccess) return -1;
+  const double a = run_smem_sweep<unsigned>(n_sm, d_sink);
+  const double b = run_smem_sweep<uint4>(n_sm, d_sink);
+  cudaFree(d_sink);
+  if (a < 0 || b < 0) return -1;
+  *gbps32 = a;
+  *gbps128 = b;
+  return 0;
+}
 
 // The (warps, chunks-per-warp) shape is chosen from n; both launchers must agree because
 // cconst depends on the padded length only, not on the shape -- they do by construction,

@@ -92,12 +92,13 @@ typedef struct icikt_opts {
 } icikt_opts;
 
 typedef struct icikt_timings { /* milliseconds, CUDA events on the library's stream */
-  float h2d_ms;     /* host -> device copy of the data matrix                         */
-  float columns_ms; /* per-column preprocessing kernels (K1)                          */
-  float pairs_ms;   /* pair kernel incl. fused epilogue (K2+K3)                       */
-  float d2h_ms;     /* device -> host copy of the results                             */
-  float total_ms;   /* first to last event                                            */
-  int32_t n_launches; /* kernels launched by this call                                */
+  float h2d_ms;      /* host -> device copy of the data matrix                        */
+  float columns_ms;  /* per-column preprocessing kernels (K1)                         */
+  float pairs_ms;    /* pair kernel (K2) alone                                        */
+  float epilogue_ms; /* fp64 epilogue kernel (K3)                                     */
+  float d2h_ms;      /* device -> host copy of the results                            */
+  float total_ms;    /* first to last event                                           */
+  int32_t n_launches; /* kernels launched by the last columns + pairs calls           */
   int32_t reserved;
 } icikt_timings;
 
@@ -164,6 +165,22 @@ void icikt_plan_destroy(icikt_plan* plan);
  * Test hook for the p-value path; lower_tail as in pnorm().                         */
 int icikt_pnorm_device(const double* z, int64_t n, int32_t lower_tail, double* out,
                        int32_t device);
+
+/* Host-only helper: the (i, j) columns of pair `index` in the pair order of icikt_all_pairs
+ * (utils::combn(C, 2) order, then the diagonal if include_diag).  Used by callers that shard
+ * the pair order with pair_lo/pair_hi or scatter results into C x C matrices.             */
+int icikt_pair_from_index(int64_t C, int32_t include_diag, int64_t index, int32_t* i, int32_t* j);
+
+/* The one-shot calls keep their device workspace (tables, result buffers, stream) cached
+ * between calls with the same shape so that repeated calls do not pay cudaMalloc; this
+ * frees it (the R shim calls it from .onUnload).                                      */
+void icikt_release_workspace(void);
+
+/* Measures the shared-memory bandwidth of `device` with a conflict-free read+write sweep
+ * (the traffic pattern the roofline model of the pair kernel assumes: one 32-bit load and
+ * one 32-bit store per element per level).  Returns GB/s through the pointers (either may
+ * be NULL): 32-bit accesses and 128-bit accesses.  Benchmark utility, not on the hot path. */
+int icikt_measure_smem_bandwidth(int32_t device, double* gbps_32bit, double* gbps_128bit);
 
 #ifdef __cplusplus
 }

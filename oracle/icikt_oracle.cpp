@@ -254,13 +254,14 @@ int icikt_oracle_ici_kt(const double* xin, int64_t nx, const double* yin, int64_
   const bool wrap32 = emulate_int32 != 0;
 
   std::vector<double> x(xin, xin + nx), y(yin, yin + ny);
+  // diagnostic only (not part of the reference's outputs): rows missing in both vectors
+  for (size_t i = 0; i < x.size(); i++) r->n_matching_na += (std::isnan(x[i]) && std::isnan(y[i]));
   if (perspective == 1) {  // :180-185
     std::vector<double> fx, fy;
     fx.reserve(x.size());
     fy.reserve(y.size());
     for (size_t i = 0; i < x.size(); i++) {
       if (!(std::isnan(x[i]) && std::isnan(y[i]))) { fx.push_back(x[i]); fy.push_back(y[i]); }
-      else r->n_matching_na++;
     }
     x.swap(fx);
     y.swap(fy);

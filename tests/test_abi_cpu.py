@@ -1,0 +1,109 @@
+"""CPU-only checks of the drop-in boundary: the shared library builds/loads, exports every
+symbol include/icikt_b200.h declares, refuses to compute without a GPU (no CPU fallback), and
+the host-side planning logic matches the oracle's restatement of the R code."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import icikendalltau_b200 as ik
+from icikendalltau_b200 import _lib, api
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        return _lib.load().icikt_device_count() > 0
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "icikt_b200.h")).read()
+    declared = set(re.findall(r"\b(icikt_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"icikt_max_n"} - {"icikt_max_n"}  # keep all
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) <= declared
+    assert _lib.load().icikt_abi_version() == 1
+    assert _lib.load().icikt_max_n() >= 20000
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Opts) == 8 * 4 + 2 * 8
+    assert ctypes.sizeof(_lib.Timings) == 6 * 4 + 2 * 4
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    x = np.random.default_rng(0).normal(size=(20, 3))
+    with pytest.raises(ik.IciktError) as e:
+        ik.run_pairs(x)
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(ik.IciktError):
+        ik.ici_kt(x[:, 0], x[:, 1])
+    with pytest.raises(ik.IciktError):
+        ik.Plan(20, 3)
+
+
+def test_argument_errors_before_any_device_work():
+    x = np.arange(10.0)
+    with pytest.raises(ValueError, match="not the same length"):  # src/kendallc.cpp:168-170
+        ik.ici_kt(x, x[:9])
+    m = np.random.default_rng(0).normal(size=(20, 10))
+    with pytest.raises(ValueError, match="Colnames of `data_matrix` must be be specified."):
+        ik.ici_kendalltau(m)
+    with pytest.raises(ValueError, match="Colnames of `x` must be be specified."):
+        ik.kt_fast(m)
+    with pytest.raises(TypeError, match="must be a numeric type"):
+        ik.ici_kendalltau(m.astype(str), colnames=[f"S{i}" for i in range(10)])
+    with pytest.raises(ValueError, match="is not a supported"):
+        ik.kt_fast(m, use="na.or.complete", colnames=list("abcdefghij"))
+    with pytest.raises(ValueError, match="should both be provided as vectors"):
+        ik.kt_fast(m[:, 0])
+    with pytest.raises(ValueError, match="must be vectors"):
+        ik.kt_fast(m, m)
+
+
+def test_setup_comparisons_matches_oracle():
+    names = [f"s{i + 1}" for i in range(100)]
+    for inc_names, inc_idx, diag in (
+            (None, None, True), (None, None, False),
+            ("s1", 0, True), (["s1", "s3"], [0, 2], True),
+            ((["s1"], ["s2", "s3"]), ([0], [1, 2]), True),
+            ((["s1"], ["s2", "s3"]), ([0], [1, 2]), False)):
+        pi, pj, allp = api.setup_comparisons(names, inc_names, diag)
+        opi, opj = O.setup_comparisons(100, inc_idx, diag)
+        assert np.array_equal(pi, opi) and np.array_equal(pj, opj)
+        assert allp == (inc_names is None)
+    # test-kendall-tau.R:102-136: zero counts of the C x C result follow from the pair counts
+    for inc, zeros in (("s1", 9702), (["s1", "s3"], 9506), ((["s1"], ["s2", "s3"]), 9896)):
+        pi, pj, _ = api.setup_comparisons(names, inc, True)
+        n_off = pi.size
+        assert 100 * 100 - 2 * n_off - 100 == zeros
+    pi, pj, _ = api.setup_comparisons(names, (["s1"], ["s2", "s3"]), False)
+    assert pi.size == 2 and 100 * 100 - 2 * pi.size == 9996
+    with pytest.raises(ValueError, match="list of two vectors"):
+        api.setup_comparisons(names, (["s1"], ["s2", "s3"], ["s4"]), False)
+    with pytest.raises(ValueError, match="No comparisons to do."):
+        api.setup_comparisons(names, (["s102"], ["s105"]), False)
+    # check_timing structure (test-kendall-tau.R:256-265): 40 columns -> 780 pairs
+    pi, _, _ = api.setup_comparisons([f"s{i}" for i in range(40)], None, True)
+    assert pi.size == 780
+
+
+def test_setup_missing_matrix_matches_oracle():
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(30, 5))
+    x[rng.random(x.shape) < 0.1] = 0.0
+    x[rng.random(x.shape) < 0.1] = np.nan
+    x[3, 2] = np.inf
+    x[4, 2] = -np.inf
+    x[5, 1] = -2.0
+    for g in ((np.nan, np.inf, 0), (np.nan,), (0,), (np.nan, np.inf, -2), ()):
+        assert np.array_equal(api.setup_missing_matrix(x, g), O.setup_missing_matrix(x, g))

@@ -1,0 +1,400 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the CPU oracle on the same inputs, against the committed golden fixtures, and -- at the
+BASELINE.json sizes -- through size-independent properties plus a sampled oracle check.
+
+Bars: integer counts (dis, ntie, xtie, ytie, tot, n_entry, b) and status bit-exact;
+tau / tau_max 1e-12 relative (north_star); completeness 1 ulp; p-value 1e-9 relative (it is
+ill-conditioned in z: relative error ~ z^2 * eps) with exact zeros preserved.
+"""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import icikendalltau_b200 as ik
+from icikendalltau_b200 import _lib, synth
+from oracle import oracle as O
+from oracle.r_rng import RRng
+
+pytestmark = pytest.mark.gpu
+
+COUNT_NAMES = ["dis", "ntie", "xtie", "ytie", "tot", "n_entry", "b"]
+
+
+def assert_parity(got, ref, what=""):
+    assert np.array_equal(got["status"], ref["status"]), what
+    ok = ref["status"] == 0
+    for k, nm in enumerate(COUNT_NAMES):
+        assert np.array_equal(got["counts"][ok, k], ref["counts"][ok, k]), f"{what}: {nm}"
+    for nm, tol in (("raw", 1e-12), ("taumax", 1e-12), ("completeness", 2.3e-16), ("pvalue", 1e-9)):
+        a, b = got[nm], ref[nm]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{what}: {nm} NaN pattern"
+        m = ~np.isnan(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=tol, atol=0, err_msg=f"{what}: {nm}")
+    assert np.array_equal(got["pvalue"][ok] == 0, ref["pvalue"][ok] == 0), f"{what}: exact-zero p-values"
+    if ok.any():
+        assert got["max_taumax"] == pytest.approx(np.nanmax(ref["taumax"]), rel=1e-12)
+    else:
+        assert np.isnan(got["max_taumax"])
+
+
+def oracle_pairs(x, pi=None, pj=None, include_diag=False, global_na=(), **kw):
+    ex = np.array(x, copy=True)
+    if len(global_na):
+        ex[O.setup_missing_matrix(ex, global_na)] = np.nan
+    if pi is None:
+        pi, pj = O.setup_comparisons(x.shape[1], None, not include_diag)
+    return O.pair_loop(ex, pi, pj, ncore=os.cpu_count() or 1, want_counts=True, **kw)
+
+
+def gen(n, C, kind, na, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, 1)) + rng.normal(size=(n, C)) * 0.7
+    if kind == "ties":
+        x = np.round(x * 2)
+    elif kind == "heavy":
+        x = np.floor(np.exp(x))
+    elif kind == "mixed":
+        x[:, ::2] = np.round(x[:, ::2] * 3)
+    if na > 0:
+        x = np.where(x <= np.quantile(x, na), np.nan, x)
+    return np.asfortranarray(x)
+
+
+# ---------------------------------------------------------------- golden fixtures (config 1)
+@pytest.mark.parametrize("persp", ["global", "local"])
+def test_yeast_missing_matches_golden(golden_dir, persp):
+    """BASELINE config 1: ici_kendalltau(yeast_missing), all 4560 pairs, vs committed oracle output."""
+    d = np.load(os.path.join(golden_dir, "yeast_missing.npz"))
+    o = np.load(os.path.join(golden_dir, "yeast_oracle.npz"))
+    got = ik.run_pairs(d["data"], (np.nan, np.inf, 0.0), perspective=persp, want_counts=True)
+    ref = {k: o[f"{persp}_{k}"] for k in ("raw", "pvalue", "taumax", "completeness", "status", "counts")}
+    assert_parity(got, ref, f"yeast {persp}")
+    # Snf2.01 x Snf2.02
+    if persp == "global":
+        assert list(got["counts"][0, :4]) == [650208, 19481, 51756, 79654]
+        assert got["raw"][0] == pytest.approx(0.943050719783801, rel=1e-12)
+
+
+def test_yeast_ici_kendalltau_api(golden_dir):
+    d = np.load(os.path.join(golden_dir, "yeast_missing.npz"))
+    names = [str(s) for s in d["colnames"]]
+    got = ik.ici_kendalltau(d["data"], colnames=names)
+    ref = O.ici_kendalltau(d["data"], ncore=os.cpu_count() or 1)
+    for k in ("cor", "raw", "pvalue", "taumax", "completeness"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, atol=0, err_msg=k)
+    assert np.array_equal(got["keep"], ref["keep"])
+    assert got["cor"].shape == (96, 96) and np.allclose(np.diag(got["taumax"]), 1.0)
+
+
+# ---------------------------------------------------------------- reference snapshot values
+def test_snapshot_kt_fast(golden_dir):
+    """tests/testthat/test-kendall-tau.R:153-198 with the reference's snapshot numbers."""
+    snaps = json.load(open(os.path.join(golden_dir, "reference_snapshots.json")))
+    r = RRng(1234)
+    x = r.rnorm(400).reshape(4, 100).T
+    names = ["s1", "s2", "s3", "s4"]
+    fast = ik.kt_fast(x, colnames=names)
+    import scipy.stats as ss
+    for i in range(4):
+        for j in range(4):
+            assert fast["tau"][i, j] == pytest.approx(ss.kendalltau(x[:, i], x[:, j]).statistic, abs=1e-14)
+    x_na = x.copy()
+    x_na[:, 0] = np.nan
+    assert np.isnan(ik.kt_fast(x_na, use="complete.obs", colnames=names)["tau"]).all()
+    x2 = x.copy()
+    x2[9, 0] = np.nan
+    ev = ik.kt_fast(x2[:, 0], x2[:, 1])
+    assert np.isnan(ev["tau"]).all() and np.isnan(ev["pvalue"]).all()
+    comp = ik.kt_fast(x2, use="complete.obs", colnames=names)
+    s = snaps["kt_fast_na_matrix_complete"]
+    np.testing.assert_allclose(comp["tau"], np.array(s["tau"]), rtol=6e-7)
+    np.testing.assert_allclose(comp["pvalue"], np.array(s["pvalue"]), rtol=6e-7)
+    pw = ik.kt_fast(x2, use="pairwise.complete.obs", colnames=names)
+    s = snaps["kt_fast_na_matrix_pairwise"]
+    np.testing.assert_allclose(pw["tau"], np.array(s["tau"]), rtol=6e-7)
+    np.testing.assert_allclose(pw["pvalue"], np.array(s["pvalue"]), rtol=6e-7)
+    pc = ik.kt_fast(x2[:, 0], x2[:, 1], use="complete.obs")
+    pp = ik.kt_fast(x2[:, 0], x2[:, 1], use="pairwise.complete.obs")
+    np.testing.assert_allclose(pc["tau"], pp["tau"], rtol=0, atol=0)
+    assert fast["tau"][0, 1] > pc["tau"][0, 1]
+    long = ik.kt_fast(x, return_matrix=False, colnames=names)
+    assert long["tau"]["tau"][3] == fast["tau"][1, 2]  # df_out$tau[4, "tau"] == tau["s2", "s3"]
+
+
+def test_snapshot_completeness(golden_dir):
+    """test-kendall-tau.R:138-151 + _snaps/kendall-tau.md:9-17."""
+    snaps = json.load(open(os.path.join(golden_dir, "reference_snapshots.json")))
+    r = RRng(1234)
+    x = r.rnorm(5000).reshape(50, 100)
+    idx = r.sample(5000, 40)
+    xf = x.flatten(order="F")
+    xf[idx - 1] = np.nan
+    x = xf.reshape(50, 100, order="F")
+    names = [f"s{i + 1}" for i in range(100)]
+    x_cor = ik.ici_kendalltau(x, perspective="global", return_matrix=False, colnames=names)
+    x_comp = ik.pairwise_completeness(x, return_matrix=False, colnames=names)
+    assert x_cor["cor"]["raw"].size == x_comp["completeness"].size
+    np.testing.assert_allclose(x_cor["cor"]["completeness"], x_comp["completeness"], rtol=0, atol=1e-15)
+    s = snaps["completeness_rows_4_6"]
+    assert list(x_comp["s2"][3:6]) == ["s5", "s6", "s7"]
+    assert list(x_comp["missingness"][3:6]) == s["missingness"]
+    np.testing.assert_allclose(x_comp["completeness"][3:6], s["completeness"], atol=1e-15)
+
+
+# ---------------------------------------------------------------- reference unit tests
+def test_basic_kendall_tau_matches_base_r():
+    """test-kendall-tau.R:5-32."""
+    import scipy.stats as ss
+    x = np.arange(1, 11, dtype=float)
+    y = np.arange(1, 11, dtype=float)
+    assert ik.ici_kt(x, y)[0] == pytest.approx(1.0, abs=1e-15)
+    y[1] = 15
+    assert ik.ici_kt(x, y)[0] == pytest.approx(ss.kendalltau(x, y).statistic, abs=1e-15)
+    y = np.arange(10, 0, -1, dtype=float)
+    assert ik.ici_kt(x, y)[0] == pytest.approx(-1.0, abs=1e-15)
+    y[1] = 15
+    assert ik.ici_kt(x, y)[0] == pytest.approx(ss.kendalltau(x, y).statistic, abs=1e-15)
+    for alt in ("two.sided", "less", "greater"):
+        ref = ss.kendalltau(x, y, method="asymptotic", alternative=alt.replace(".", "-")).pvalue
+        assert ik.ici_kt(x, y, alternative=alt)[1] == pytest.approx(ref, rel=1e-12)
+    y[1] = np.nan
+    assert ik.ici_kt(x, y)[3] == pytest.approx(0.9, abs=1e-15)
+    x[7] = np.nan
+    assert ik.ici_kt(x, y)[3] == pytest.approx(0.8, abs=1e-15)
+    x[1] = np.nan
+    assert ik.ici_kt(x, y)[3] == pytest.approx(1 - 1 / 9, abs=1e-15)
+    assert ik.ici_kt(x, y, perspective="global")[3] == pytest.approx(0.8, abs=1e-15)
+
+
+def test_difference_and_reference_match_short():
+    """test-kendall-tau.R:34-40: ici_kt(global) vs the O(n^2) ici_kt_pairs."""
+    rng = np.random.default_rng(21)
+    x = np.sort(rng.normal(size=100))
+    y = x + 1
+    y[:20] = np.nan
+    a = ik.ici_kt(x, y, perspective="global", continuity=True)
+    b = O.ici_kt_pairs(x, y, "global")
+    assert a["tau"] == pytest.approx(b[0], abs=1e-14)
+    assert a["pvalue"] == pytest.approx(b[1], rel=1e-8)
+
+
+def test_bad_values():
+    """test-kendall-tau.R:42-59."""
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.normal(size=100))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # the all-NA case is silent
+        r = ik.ici_kt(x, np.full(100, np.nan))
+    assert list(r.keys()) == ["tau", "pvalue", "tau_max", "completeness"] and np.isnan(r.as_array()).all()
+    with pytest.raises(ValueError, match="not the same length"):
+        ik.ici_kt(x, x[:99])
+    with pytest.warns(RuntimeWarning, match="vectors only have a single value"):
+        assert np.isnan(ik.ici_kt(x[1:2], x[1:2]).as_array()).all()
+    with pytest.warns(RuntimeWarning, match="have only a single unique value"):
+        assert np.isnan(ik.ici_kt(x, np.ones(100)).as_array()).all()
+
+
+def test_matrix_kendall_and_long_format():
+    """test-kendall-tau.R:61-70 and :223-239."""
+    rng = np.random.default_rng(11)
+    x = np.sort(rng.normal(size=100))
+    y = x + 1
+    y[:20] = np.nan
+    m = np.column_stack([x, y])
+    mc = ik.ici_kendalltau(m, global_na=(np.nan,), perspective="global", scale_max=False, colnames=["x", "y"])
+    assert ik.ici_kt(x, y, "global")[0] == mc["raw"][1, 0]
+    lc = ik.ici_kendalltau(m, global_na=(np.nan,), perspective="global", scale_max=False,
+                           return_matrix=False, colnames=["x", "y"])
+    assert lc["cor"]["raw"].size == 3
+    assert lc["cor"]["raw"][0] == mc["raw"][1, 0] and lc["cor"]["raw"][2] == mc["raw"][1, 1]
+
+
+def test_include_only():
+    """test-kendall-tau.R:102-136."""
+    r = RRng(1234)
+    x = r.rnorm(5000).reshape(100, 50).T  # matrix(rnorm(5000), nrow = 50, ncol = 100)
+    names = [f"s{i + 1}" for i in range(100)]
+    assert (ik.ici_kendalltau(x, include_only="s1", colnames=names)["cor"] == 0).sum() == 9702
+    assert (ik.ici_kendalltau(x, include_only=["s1", "s3"], colnames=names)["cor"] == 0).sum() == 9506
+    inc = {"s1": ["s1"], "s2": ["s2", "s3"]}
+    a3 = ik.ici_kendalltau(x, include_only=inc, colnames=names)
+    assert (a3["cor"] == 0).sum() == 9896
+    a4 = ik.ici_kendalltau(x, include_only=(["s1", "s1"], ["s2", "s3"]), colnames=names)
+    assert np.array_equal(a4["cor"], a3["cor"])
+    assert (ik.ici_kendalltau(x, include_only=inc, diag_good=False, colnames=names)["cor"] == 0).sum() == 9996
+    a6 = ik.ici_kendalltau(x, include_only=inc, diag_good=False, return_matrix=False, colnames=names)
+    assert a6["cor"]["raw"].size == 2
+    with pytest.raises(ValueError, match="list of two vectors"):
+        ik.ici_kendalltau(x, include_only=(["s1"], ["s2", "s3"], ["s4"]), diag_good=False, colnames=names)
+    with pytest.raises(ValueError, match="No comparisons to do."):
+        ik.ici_kendalltau(x, include_only=(["s102"], ["s105"]), diag_good=False, colnames=names)
+    # values of the included pairs equal the full run's
+    full = ik.ici_kendalltau(x, colnames=names, scale_max=False)
+    assert a3["raw"][0, 1] == full["raw"][0, 1] and a3["raw"][2, 0] == full["raw"][2, 0]
+
+
+def test_check_timing_structure():
+    """test-kendall-tau.R:256-265."""
+    x = np.random.default_rng(1234).normal(size=(100, 40))
+    chk = ik.ici_kendalltau(x, check_timing=True, colnames=[f"s{i}" for i in range(40)])
+    assert chk["value"][0] == 5 and chk["value"][1] == 780
+
+
+# ---------------------------------------------------------------- randomized parity vs oracle
+CASES = [
+    ("normal", 100, 6, 0.0), ("normal", 100, 6, 0.25), ("ties", 100, 6, 0.0), ("ties", 100, 6, 0.25),
+    ("heavy", 333, 5, 0.3), ("mixed", 1000, 8, 0.2), ("ties", 33, 4, 0.2), ("normal", 2, 3, 0.0),
+    ("ties", 3, 3, 0.0), ("normal", 31, 3, 0.5), ("ties", 32, 3, 0.1), ("normal", 2048, 4, 0.25),
+    ("normal", 2049, 6, 0.25), ("ties", 4097, 4, 0.25), ("normal", 5000, 12, 0.2),
+    ("heavy", 5000, 6, 0.2), ("mixed", 8193, 4, 0.25), ("mixed", 9000, 6, 0.25),
+    ("normal", 16385, 4, 0.25), ("normal", 20000, 6, 0.25), ("heavy", 20000, 4, 0.25),
+    ("mixed", 24577, 3, 0.2), ("mixed", 30000, 4, 0.25), ("heavy", 32768, 3, 0.3),
+]
+
+
+@pytest.mark.parametrize("kind,n,C,na", CASES)
+def test_random_parity(kind, n, C, na):
+    x = gen(n, C, kind, na, seed=n * 7 + C)
+    for persp in ("global", "local"):
+        got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+        assert_parity(got, oracle_pairs(x, perspective=persp), f"{kind} n={n} {persp}")
+
+
+def test_options_and_pair_lists():
+    x = gen(500, 7, "mixed", 0.3, 5)
+    for alt, cont in (("less", True), ("greater", False), ("two.sided", True), ("bogus", False)):
+        got = ik.run_pairs(x, (), alternative=alt, continuity=cont, want_counts=True)
+        assert_parity(got, oracle_pairs(x, alternative=alt, continuity=cont), alt)
+    got = ik.run_pairs(x, (), include_diag=True, perspective="local", want_counts=True)
+    assert_parity(got, oracle_pairs(x, include_diag=True, perspective="local"), "diag")
+    pi, pj = [0, 0, 3, 6, 2, 2, 5], [1, 5, 3, 0, 4, 2, 1]
+    got = ik.run_pairs(x, (), pi=pi, pj=pj, want_counts=True)
+    assert_parity(got, oracle_pairs(x, np.array(pi, np.int32), np.array(pj, np.int32)), "pair list")
+    got = ik.run_pairs(x, (), want_counts=True, pair_lo=5, pair_hi=17)
+    full = oracle_pairs(x)
+    assert_parity(got, {k: v[5:17] for k, v in full.items()}, "pair range")
+
+
+def test_global_na_and_degenerate_columns():
+    x = gen(500, 8, "mixed", 0.3, 9)
+    x[::5, 1] = 0.0
+    x[::9, 2] = np.inf
+    x[::11, 2] = -np.inf
+    x[:, 4] = np.nan
+    x[:, 5] = 3.0
+    x[:, 6] = np.where(np.arange(500) % 2 == 0, np.nan, 7.0)  # one value + missing
+    for g in ((np.nan, np.inf, 0.0), (np.nan,), (), (np.nan, np.inf, 0.0, 3.0)):
+        for persp in ("global", "local"):
+            got = ik.run_pairs(x, g, perspective=persp, want_counts=True)
+            assert_parity(got, oracle_pairs(x, global_na=g, perspective=persp), f"global_na={g} {persp}")
+
+
+def test_absorbed_minimum_and_signed_zero():
+    # |min| so large that min - 0.1 == min: missing rows tie with the minimum
+    rng = np.random.default_rng(4)
+    x = rng.normal(size=(200, 4))
+    x[:, 0] = np.round(x[:, 0]) * 1e17
+    x[:, 1] = np.where(rng.random(200) < 0.3, -np.inf, x[:, 1])
+    x[:, 2] = np.where(rng.random(200) < 0.5, -0.0, 0.0) + np.round(x[:, 2])
+    x[rng.random(x.shape) < 0.2] = np.nan
+    for persp in ("global", "local"):
+        got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+        assert_parity(got, oracle_pairs(x, perspective=persp), f"absorbed {persp}")
+
+
+def test_naive_kernel_matches_tiled_and_oracle():
+    x = gen(700, 9, "mixed", 0.3, 77)
+    for persp in ("global", "local"):
+        got = ik.run_pairs(x, (), perspective=persp, want_counts=True, kernel=_lib.KERNEL_NAIVE)
+        assert_parity(got, oracle_pairs(x, perspective=persp), f"naive {persp}")
+
+
+def test_pnorm_device_matches_oracle():
+    z = np.concatenate([np.linspace(-38.5, 38.5, 4001), [-37.5193, 37.5193, 0.0, 1e-20, -8.2924, 8.2924,
+                                                          np.inf, -np.inf, np.nan]])
+    for lower in (True, False):
+        dev = ik.pnorm_device(z, lower)
+        ref = np.array([O.pnorm(v, lower) for v in z])
+        assert np.array_equal(np.isnan(dev), np.isnan(ref))
+        m = ~np.isnan(ref)
+        assert np.array_equal(dev[m] == 0, ref[m] == 0)
+        np.testing.assert_allclose(dev[m], ref[m], rtol=2e-13, atol=0)
+
+
+def test_plan_api_device_resident_reuse():
+    x = gen(3000, 10, "mixed", 0.25, 8)
+    plan = ik.Plan(3000, 10, perspective="local", want_counts=True)
+    plan.upload(x)
+    for _ in range(3):  # repeated runs on the resident matrix give identical results
+        plan.columns(())
+        plan.pairs()
+        got = plan.download(want_counts=True)
+        assert_parity(got, oracle_pairs(x, perspective="local"), "plan")
+    assert np.array_equal(plan.column_n_na(), np.isnan(x).sum(axis=0))
+    t = plan.timings()
+    assert t["pairs_ms"] > 0 and t["n_launches"] >= 4
+    plan.close()
+
+
+# ---------------------------------------------------------------- BASELINE.json sizes
+def _sampled_oracle_check(x, persp, got, n_sample=48, seed=0):
+    C = x.shape[1]
+    pi, pj = O.setup_comparisons(C, None, True)
+    sel = np.random.default_rng(seed).choice(pi.size, size=min(n_sample, pi.size), replace=False)
+    ref = O.pair_loop(x, pi[sel], pj[sel], perspective=persp, ncore=os.cpu_count() or 1, want_counts=True)
+    sub = {k: (v[sel] if isinstance(v, np.ndarray) else v) for k, v in got.items()}
+    sub["max_taumax"] = np.nanmax(ref["taumax"])  # the global max is checked separately
+    assert_parity(sub, ref, "sampled")
+
+
+def test_config2_full_size():
+    """BASELINE config 2: 5000 features x 100 samples, 20% left-censored, global; all 4950 pairs."""
+    x, persp = synth.make("config2")
+    got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+    assert_parity(got, oracle_pairs(x, perspective=persp), "config2")
+
+
+def test_config3_shape_properties_and_sample():
+    """BASELINE config 3 shape (n = 20000, local + scale_max) on 160 of the 1000 samples."""
+    x, persp = synth.make("config3", C=160)
+    got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+    assert (got["status"] == 0).all()
+    _sampled_oracle_check(x, persp, got)
+    # size-independent properties: |tau| <= tau_max <= 1 + eps, symmetry under swapping the columns
+    assert (np.abs(got["raw"]) <= got["taumax"] + 1e-15).all()
+    pi, pj = O.setup_comparisons(160, None, True)
+    sel = np.arange(0, pi.size, 97)
+    sw = ik.run_pairs(x, (), pi=pj[sel], pj=pi[sel], perspective=persp, want_counts=True)
+    assert np.array_equal(sw["counts"][:, 0], got["counts"][sel, 0])
+    assert np.array_equal(sw["counts"][:, 1], got["counts"][sel, 1])
+    assert np.array_equal(sw["raw"], got["raw"][sel])
+    # tiled kernel == naive kernel (independent Fenwick algorithm) on a slice of the pair order
+    nv = ik.run_pairs(x, (), perspective=persp, want_counts=True, kernel=_lib.KERNEL_NAIVE,
+                      pair_lo=1000, pair_hi=1400)
+    assert np.array_equal(nv["counts"], got["counts"][1000:1400])
+    # scale_max: cor = raw / max(taumax)
+    names = [f"s{i}" for i in range(160)]
+    res = ik.ici_kendalltau(x, global_na=(np.nan,), perspective="local", colnames=names)
+    assert res["cor"][0, 1] == got["raw"][0] / got["max_taumax"]
+
+
+def test_config5_shape_short_vectors():
+    """BASELINE config 5 shape (n = 2000) on 700 of the 5000 samples: 244,650 pairs."""
+    x, persp = synth.make("config5", C=700)
+    got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+    assert (got["status"] == 0).all()
+    _sampled_oracle_check(x, persp, got, n_sample=400)
+    # identical columns: tau == 1, dis == 0
+    x2 = np.asfortranarray(np.column_stack([x[:, 0], x[:, 0], x[:, 1]]))
+    r = ik.run_pairs(x2, (), want_counts=True)
+    assert r["raw"][0] == 1.0 and r["counts"][0, 0] == 0
+
+
+def test_target_shape_sample():
+    """north_star target shape (n = 20000, 25% censored, global) on 120 of the 2000 samples."""
+    x, persp = synth.make("target", C=120)
+    got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+    _sampled_oracle_check(x, persp, got)
