@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=8.0, help="seconds per reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "naive"])
+    ap.add_argument("--quick", action="store_true", help="skip the e2e and CPU legs (tuning sweeps)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -251,14 +252,15 @@ def main():
 
     # ---- e2e: one-shot C-ABI call with host buffers, every step uploads and downloads ----
     e2e_kw = dict(perspective=persp, device=local_rank, kernel=kernel, pair_lo=lo, pair_hi=hi)
-    for _ in range(2):
+    e2e_steps = 1 if args.quick else args.steps
+    for _ in range(0 if args.quick else 2):
         ik.run_pairs(x_pinned, gna, **e2e_kw)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         res = ik.run_pairs(x_pinned, gna, **e2e_kw)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = max_over_ranks(time.perf_counter() - t0) * args.steps / e2e_steps
     e2e_value = P_total * args.steps / e2e_s
     h2d = n * C * 8
     d2h = P_rank * (4 * 8 + 4) + 8
@@ -305,7 +307,7 @@ def main():
                                 "peak_gbs": hbm_peak}},
         "max_taumax": res["max_taumax"],
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         cores = os.cpu_count() or 1
         rate, sample = cpu_port_rate(x, persp, args.cpu_budget, cores)
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",

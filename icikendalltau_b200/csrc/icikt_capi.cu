@@ -59,6 +59,8 @@ struct icikt_plan {
   ColumnTables tab;
   ColumnWork wk;
   bool columns_done = false;
+  TiledShape shape;            // launch shape of the tiled kernels
+  int32_t* h_max_tied = nullptr;  // pinned
 
   std::vector<PairUnit> units;
   PairUnit* d_units = nullptr;
@@ -90,6 +92,8 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->tab.firstbits);
   cudaFree(p->tab.grpstart);
   cudaFree(p->tab.stats);
+  cudaFree(p->tab.max_tied);
+  if (p->h_max_tied) cudaFreeHost(p->h_max_tied);
   cudaFree(p->wk.keys_in);
   cudaFree(p->wk.keys_out);
   cudaFree(p->wk.vals_in);
@@ -283,6 +287,9 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.firstbits, nw));
   PCK(dmalloc(&t.grpstart, nw));
   PCK(dmalloc(&t.stats, (size_t)C));
+  PCK(dmalloc(&t.max_tied, 1));
+  PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_max_tied), sizeof(int32_t)));
+  p->shape = tiled_shape(n, 0, 0);
   PCK(dmalloc(&p->wk.keys_in, ne));
   PCK(dmalloc(&p->wk.keys_out, ne));
   PCK(dmalloc(&p->wk.vals_in, ne));
@@ -363,10 +370,15 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   }
   if (nlit) CK(cudaMemcpyAsync(p->d_global_na, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, p->stream));
   CK(cudaEventRecord(p->ev[2], p->stream));
-  const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->stream);
+  p->shape = tiled_shape(p->n, 0, 0);
+  const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
+                               p->stream);
   if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
   CK(cudaEventRecord(p->ev[3], p->stream));
-  if (nlit) CK(cudaStreamSynchronize(p->stream));  // lit[] lives on this stack frame
+  // the pair kernel's shared-memory region is sized for the longest tied list
+  CK(cudaMemcpyAsync(p->h_max_tied, p->tab.max_tied, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));  // also: lit[] lives on this stack frame
+  p->shape = tiled_shape(p->n, *p->h_max_tied, 0);
   p->tm.n_launches = l;
   p->columns_done = true;
   return ICIKT_OK;
@@ -391,7 +403,10 @@ int icikt_plan_pairs(icikt_plan* p) {
     if (p->opts.kernel == ICIKT_KERNEL_NAIVE)
       l = launch_pairs_naive(pl, p->P, p->d_naive, p->naive_threads, p->stream);
     else
-      l = launch_pairs_tiled(pl, p->n_sm, p->stream);
+      l = launch_pairs_tiled(pl, p->shape, p->n_sm, p->stream);
+    if (l == -2)
+      return fail(ICIKT_ERR_TOO_LONG, "the tied-value lists of this matrix do not fit the pair kernel's "
+                                      "shared memory (long vectors with heavy ties)");
     if (l < 0) return cuda_fail(cudaGetLastError(), "pair kernel");
     launches += l;
     CK(cudaEventRecord(p->ev[8], p->stream));

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        uint16_t* __restrict__ perm, uint16_t* __restrict__ rank,
                        uint16_t* __restrict__ trow, uint16_t* __restrict__ trun,
                        uint32_t* __restrict__ firstbits, uint32_t* __restrict__ grpstart,
-                       uint32_t* __restrict__ gpos_all, ColStats* __restrict__ stats) {
+                       uint32_t* __restrict__ gpos_all, ColStats* __restrict__ stats,
+                       int32_t* __restrict__ max_tied) {
   __shared__ int warp_sums[32];
   __shared__ long long llbuf[32];
   __shared__ uint32_t bits[2048];
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
     s.s5o = s5;
     s.cconst = 0;
     stats[col] = s;
+    atomicMax(max_tied, (int)ntied);
   }
 }
 
@@ -227,13 +229,15 @@ size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride) {
 }
 
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
-                   int na_inf, ColumnTables& tab, ColumnWork& wk, cudaStream_t stream) {
+                   int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
+                   cudaStream_t stream) {
   const int n = (int)tab.n, C = (int)tab.C;
   const int nstride = (int)tab.nstride, wstride = (int)tab.wstride;
   int launches = 0;
   if (cudaMemsetAsync(tab.nabits, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
   if (cudaMemsetAsync(tab.grpstart, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
   if (cudaMemsetAsync(tab.firstbits, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(tab.max_tied, 0, sizeof(int32_t), stream) != cudaSuccess) return -1;
   {
     seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, C, nstride, n);
     ++launches;
@@ -254,10 +258,10 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
   column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                      tab.trow, tab.trun, tab.firstbits, tab.grpstart,
-                                                     wk.gpos, tab.stats);
+                                                     wk.gpos, tab.stats, tab.max_tied);
   ++launches;
   if (cudaGetLastError() != cudaSuccess) return -1;
-  const int cl = launch_column_consts(tab, stream);
+  const int cl = launch_column_consts(tab, sh, stream);
   if (cl < 0) return -1;
   return launches + cl;
 }

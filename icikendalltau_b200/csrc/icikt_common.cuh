@@ -39,7 +39,7 @@ struct ColStats {
 
 struct PairOut {
   double tau, pvalue, taumax, completeness;
-  int64_t xtie, ytie, tot, n_entry;
+  int64_t xtie, ytie, tot, n_entry, ntie;
   int32_t status;
 };
 
@@ -122,12 +122,14 @@ ICIKT_HD double qnan() { return nan(""); }
 //   dis      : #{(p,q): x_p < x_q and y_p > y_q}            (kendall_discordant, :70-100)
 //   ntie_g   : sum over joint (x,y) tie groups g(g-1)/2 on all n rows (:261-267)
 //   b        : rows missing in both columns
+//   g00      : rows in the lowest tie group of both columns (== b unless a column's missing
+//              rows tie with its minimum)
 ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int64_t dis,
-                            int64_t ntie_g, int64_t b, int perspective, int alternative,
-                            int continuity, PairOut& o) {
+                            int64_t ntie_g, int64_t b, int64_t g00, int perspective,
+                            int alternative, int continuity, PairOut& o) {
   const double NA = qnan();
   o.tau = o.pvalue = o.taumax = o.completeness = NA;
-  o.xtie = o.ytie = o.tot = 0;
+  o.xtie = o.ytie = o.tot = o.ntie = 0;
   o.status = 0;
   const int64_t bb = (perspective == 1) ? b : 0;  // local drops the joint-missing rows (:180-185)
   const int64_t np = n - bb;
@@ -148,7 +150,9 @@ ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int
   const double y0 = (double)((Y.s3o + t0y * (t0y - 1) * (t0y - 2)) / 2);
   const double x1 = (double)(X.s5o + t0x * (t0x - 1) * (2 * t0x + 5));
   const double y1 = (double)(Y.s5o + t0y * (t0y - 1) * (2 * t0y + 5));
-  const int64_t ntie = ntie_g - bb * (bb - 1) / 2;
+  // the joint group (lowest x group, lowest y group) shrinks from g00 to g00 - bb rows
+  const int64_t ntie = ntie_g - g00 * (g00 - 1) / 2 + (g00 - bb) * (g00 - bb - 1) / 2;
+  o.ntie = ntie;
   const int64_t tot = np * (np - 1) / 2;  // :280
   o.xtie = xtie;
   o.ytie = ytie;

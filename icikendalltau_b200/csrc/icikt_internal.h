@@ -23,6 +23,7 @@ struct ColumnTables {
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
   uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group
   ColStats* stats = nullptr;      // [C]
+  int32_t* max_tied = nullptr;    // [1] max over columns of ColStats::n_tied
 };
 
 // A unit of pair work: column `col` is staged in shared memory and correlated with
@@ -36,8 +37,15 @@ struct PairUnit {
 };
 
 struct PairRaw {  // what K2 hands to K3
-  int64_t dis, ntie, b;
+  int64_t dis, ntie, b, g00;
 };
+
+struct TiledShape {
+  int warps = 0;         // warps per CTA
+  int kk = 0;            // 32-element chunks per warp
+  int region_bytes = 0;  // ping-pong region
+};
+TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override);
 
 struct PairLaunch {
   const ColumnTables* tab;
@@ -63,13 +71,14 @@ size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride);
 
 // K1: data (device, column-major, ld) -> tables.  Returns number of kernel launches or <0.
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
-                   int na_inf, ColumnTables& tab, ColumnWork& wk, cudaStream_t stream);
+                   int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
+                   cudaStream_t stream);
 
 // pass-A correction constant per column (needs the pair kernel's code path)
-int launch_column_consts(ColumnTables& tab, cudaStream_t stream);
+int launch_column_consts(ColumnTables& tab, const TiledShape& sh, cudaStream_t stream);
 
 // K2 (tiled) and K2-naive; both fill raw[P].
-int launch_pairs_tiled(const PairLaunch& pl, int n_sm, cudaStream_t stream);
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream);
 int launch_pairs_naive(const PairLaunch& pl, int64_t P, uint32_t* d_scratch, int64_t n_threads,
                        cudaStream_t stream);
 size_t naive_scratch_bytes(int64_t n, int64_t n_threads);

@@ -30,6 +30,7 @@
 //   shared memory; two __syncthreads per level.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "icikt_internal.h"
 
@@ -53,13 +54,43 @@ __device__ __forceinline__ uint32_t below_top(uint32_t bits) {
   return (1u << (31 - __clz((int)bits))) - 1u;
 }
 
+// ---- explicit shared-memory accessors (32-bit shared-window addresses) --------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+template <typename E>
+struct Sh;
+template <>
+struct Sh<uint16_t> {
+  static __device__ __forceinline__ uint32_t ld(uint32_t base, uint32_t idx) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + idx * 2u) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(uint32_t base, uint32_t idx, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + idx * 2u), "h"((unsigned short)v) : "memory");
+  }
+};
+template <>
+struct Sh<uint32_t> {
+  static __device__ __forceinline__ uint32_t ld(uint32_t base, uint32_t idx) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + idx * 4u) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(uint32_t base, uint32_t idx, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + idx * 4u), "r"(v) : "memory");
+  }
+};
+
 // Exclusive scan of the per-warp totals (every warp computes it redundantly from shared
 // memory) and, for the bucketed variants, the count at the nearest bucket start that lies in
 // an earlier warp's segment (counts are monotone in position, so that is a running max).
-template <int W, bool BUCKETS>
-__device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t* descB, int lane,
-                                           int warp, uint32_t& G, uint32_t& total, int32_t& carry) {
-  const uint32_t v = (lane < W) ? descT[lane] : 0u;
+template <bool BUCKETS>
+__device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t* descB, int nwarps,
+                                           int lane, int warp, uint32_t& G, uint32_t& total,
+                                           int32_t& carry) {
+  const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
   uint32_t incl = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -71,7 +102,7 @@ __device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t*
   G = __shfl_sync(FULL, excl, warp);
   carry = -1;
   if (BUCKETS) {
-    const int32_t bl = (lane < W) ? descB[lane] : -1;
+    const int32_t bl = (lane < nwarps) ? descB[lane] : -1;
     int32_t babs = (bl >= 0 && lane < warp) ? (int32_t)excl + bl : -1;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) babs = max(babs, __shfl_xor_sync(FULL, babs, d));
@@ -79,56 +110,50 @@ __device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t*
   }
 }
 
-// One counting pass over S[0, nelem32) (nelem32 a multiple of 32; positions >= nreal hold
-// all-ones pad keys).  Levels L-1..0 of the low bits are partitioned in place.
+// One counting pass over a sequence of nwarps*kk*32 elements held in shared memory (positions
+// >= nreal hold all-ones pad keys).  Every warp owns kk consecutive 32-element chunks; kk is
+// uniform over the CTA, so the chunk loops are plain uniform loops.  Each level reads buffer
+// `a` and scatters into buffer `b` (ping-pong), then the two swap.
 //   BUCKETS = false: acc += sum over zero-bit elements of the GLOBAL count of preceding ones.
 //   BUCKETS = true : buckets are runs of equal (key >> (s+1)); acc += ones preceding inside
 //                    the bucket; after level 0 one more sweep on the full key adds, for every
 //                    real element, its index inside its run of equal keys to `ties`.
-template <int W, int K, bool BUCKETS>
-__device__ __forceinline__ void partition_pass(uint32_t* __restrict__ S, const int nelem32,
+template <typename E, bool BUCKETS>
+__device__ __forceinline__ void partition_pass(uint32_t a, uint32_t b, const int kk, const int nwarps,
                                                const int nreal, const int L, uint32_t* descT,
                                                int32_t* descB, const int lane, const int warp,
                                                uint32_t& acc, uint32_t& ties) {
-  const int nchunks = nelem32 >> 5;
-  const int kk = (nchunks + W - 1) / W;
-  const int c0 = warp * kk;
-  int mycnt = nchunks - c0;
-  mycnt = mycnt < 0 ? 0 : (mycnt > kk ? kk : mycnt);
-  const int base = c0 << 5;
+  const uint32_t base = (uint32_t)(warp * kk) << 5;
+  const uint32_t total_len = (uint32_t)(nwarps * kk) << 5;
   const uint32_t lt = lanemask_lt();
   const uint32_t le = lanemask_le();
 
-  uint32_t e[K];
-#pragma unroll
-  for (int c = 0; c < K; ++c) e[c] = (c < mycnt) ? S[base + (c << 5) + lane] : 0u;
-  uint32_t prevlast = 0;
-  if (BUCKETS) prevlast = (base > 0 && mycnt > 0) ? S[base - 1] : 0u;
-
   for (int s = L - 1; s >= (BUCKETS ? -1 : 0); --s) {
     const bool tie_step = (s < 0);  // BUCKETS only: every element counts as a "one"
-    const uint32_t bitmask = tie_step ? 0u : (1u << s);
+    uint32_t bitmask = tie_step ? 0u : (1u << s);
+    asm volatile("" : "+r"(bitmask));  // keep `e & bitmask` a single LOP3 with predicate output
     const int sh = s + 1;
 
     // ---- sweep 1: ones per warp segment (+ count at the last bucket start) ----
     uint32_t T = 0;
     int32_t lastB = -1;
-    uint32_t carrylast = prevlast;
-#pragma unroll
-    for (int c = 0; c < K; ++c) {
-      if (c < mycnt) {
-        const bool one = tie_step || ((e[c] & bitmask) != 0u);
-        const uint32_t m = __ballot_sync(FULL, one);
-        if (BUCKETS) {
-          uint32_t prev = __shfl_up_sync(FULL, e[c], 1);
-          if (lane == 0) prev = carrylast;
-          const int pos = base + (c << 5) + lane;
-          const uint32_t bd = __ballot_sync(FULL, (pos == 0) || (((e[c] ^ prev) >> sh) != 0u));
-          carrylast = __shfl_sync(FULL, e[c], 31);
-          if (bd) lastB = (int32_t)(T + __popc(m & below_top(bd)));
-        }
-        T += __popc(m);
+    uint32_t carrylast = 0;
+    if (BUCKETS && base > 0) carrylast = Sh<E>::ld(a, base - 1);
+    const uint32_t prevlast = carrylast;
+#pragma unroll 4
+    for (int c = 0; c < kk; ++c) {
+      const uint32_t pos = base + ((uint32_t)c << 5) + lane;
+      const uint32_t e = Sh<E>::ld(a, pos);
+      const bool one = tie_step || ((e & bitmask) != 0u);
+      const uint32_t m = __ballot_sync(FULL, one);
+      if (BUCKETS) {
+        uint32_t prev = __shfl_up_sync(FULL, e, 1);
+        if (lane == 0) prev = carrylast;
+        const uint32_t bd = __ballot_sync(FULL, (pos == 0u) || (((e ^ prev) >> sh) != 0u));
+        carrylast = __shfl_sync(FULL, e, 31);
+        if (bd) lastB = (int32_t)(T + __popc(m & below_top(bd)));
       }
+      T += __popc(m);
     }
     if (lane == 0) {
       descT[warp] = T;
@@ -138,93 +163,78 @@ __device__ __forceinline__ void partition_pass(uint32_t* __restrict__ S, const i
 
     uint32_t G, total;
     int32_t carry;
-    cross_warp<W, BUCKETS>(descT, descB, lane, warp, G, total, carry);
-    const uint32_t Z = (uint32_t)nelem32 - total;
+    cross_warp<BUCKETS>(descT, descB, nwarps, lane, warp, G, total, carry);
+    const uint32_t Z = total_len - total;
 
     // ---- sweep 2: count and scatter ----
     uint32_t P = G;
     carrylast = prevlast;
-#pragma unroll
-    for (int c = 0; c < K; ++c) {
-      if (c < mycnt) {
-        const int pos = base + (c << 5) + lane;
-        const bool one = tie_step || ((e[c] & bitmask) != 0u);
-        const uint32_t m = __ballot_sync(FULL, one);
-        const uint32_t P1 = P + __popc(m & lt);
-        if (BUCKETS) {
-          uint32_t prev = __shfl_up_sync(FULL, e[c], 1);
-          if (lane == 0) prev = carrylast;
-          const uint32_t bd = __ballot_sync(FULL, (pos == 0) || (((e[c] ^ prev) >> sh) != 0u));
-          carrylast = __shfl_sync(FULL, e[c], 31);
-          const uint32_t seg = bd & le;
-          const uint32_t startP = seg ? P + __popc(m & below_top(seg)) : (uint32_t)carry;
-          const uint32_t cnt = P1 - startP;
-          if (tie_step) {
-            if (pos < nreal) ties += cnt;
-          } else if (!one) {
-            acc += cnt;
-          }
-          if (bd) carry = (int32_t)(P + __popc(m & below_top(bd)));
-        } else {
-          if (!one) acc += P1;
+#pragma unroll 4
+    for (int c = 0; c < kk; ++c) {
+      const uint32_t pos = base + ((uint32_t)c << 5) + lane;
+      const uint32_t e = Sh<E>::ld(a, pos);
+      const bool one = tie_step || ((e & bitmask) != 0u);
+      const uint32_t m = __ballot_sync(FULL, one);
+      const uint32_t P1 = P + __popc(m & lt);
+      if (BUCKETS) {
+        uint32_t prev = __shfl_up_sync(FULL, e, 1);
+        if (lane == 0) prev = carrylast;
+        const uint32_t bd = __ballot_sync(FULL, (pos == 0u) || (((e ^ prev) >> sh) != 0u));
+        carrylast = __shfl_sync(FULL, e, 31);
+        const uint32_t seg = bd & le;
+        const uint32_t startP = seg ? P + __popc(m & below_top(seg)) : (uint32_t)carry;
+        const uint32_t cnt = P1 - startP;
+        if (tie_step) {
+          if (pos < (uint32_t)nreal) ties += cnt;
+        } else if (!one) {
+          acc += cnt;
         }
-        if (!tie_step) {
-          const uint32_t dest = one ? Z + P1 : (uint32_t)pos - P1;
-          S[dest] = e[c];
-        }
-        P += __popc(m);
+        if (bd) carry = (int32_t)(P + __popc(m & below_top(bd)));
+      } else {
+        if (!one) acc += P1;
       }
+      if (!tie_step) Sh<E>::st(b, one ? Z + P1 : pos - P1, e);
+      P += __popc(m);
     }
     if (tie_step) break;
-    __syncthreads();
-    if (BUCKETS || s > 0) {
-#pragma unroll
-      for (int c = 0; c < K; ++c) e[c] = (c < mycnt) ? S[base + (c << 5) + lane] : 0u;
-      if (BUCKETS) prevlast = (base > 0 && mycnt > 0) ? S[base - 1] : 0u;
-    }
+    __syncthreads();  // also protects descT/descB for the next level
+    const uint32_t t = a;
+    a = b;
+    b = t;
   }
 }
 
-// Writes the rows of x's first tie group into S[0, f) ordered by y: sweep y's sorted order,
+// Writes the rows of x's first tie group into buf[0, f) ordered by y: sweep y's sorted order,
 // keep the rows whose bit is set in x's membership mask (ordered stream compaction).  Rows
 // of one y tie group are contiguous in that order (gsY marks group starts), so the joint
 // (x-first-group, y) ties are counted on the way: every kept row adds the number of kept
 // rows before it in its y group.
-template <int W, int K>
-__device__ __forceinline__ void emit_first_group(uint32_t* __restrict__ S, const int n,
-                                                 const int n32, const uint16_t* __restrict__ permY_g,
+__device__ __forceinline__ void emit_first_group(uint32_t buf, const int n, const int kk,
+                                                 const int nwarps,
+                                                 const uint16_t* __restrict__ permY_g,
                                                  const uint16_t* __restrict__ rankY,
                                                  const uint32_t* __restrict__ gsY,
                                                  const uint32_t* __restrict__ fbX, uint32_t* descT,
                                                  int32_t* descB, const int lane, const int warp,
                                                  uint32_t& ties) {
-  const int nchunks = n32 >> 5;
-  const int kk = (nchunks + W - 1) / W;
   const int c0 = warp * kk;
-  int mycnt = nchunks - c0;
-  mycnt = mycnt < 0 ? 0 : (mycnt > kk ? kk : mycnt);
-  const int base = c0 << 5;
+  const int nwords = (n + 31) >> 5;
   const uint32_t lt = lanemask_lt();
   const uint32_t le = lanemask_le();
-
-  uint32_t F[K];
   uint32_t T = 0;
   int32_t lastB = -1;
-#pragma unroll
-  for (int c = 0; c < K; ++c) {
-    F[c] = 0;
-    if (c < mycnt) {
-      const int t = base + (c << 5) + lane;
-      bool mem = false;
-      if (t < n) {
-        const uint32_t row = permY_g[t];
-        mem = (fbX[row >> 5] >> (row & 31)) & 1u;
-      }
-      F[c] = __ballot_sync(FULL, mem);
-      const uint32_t gs = gsY[c0 + c];
-      if (gs) lastB = (int32_t)(T + __popc(F[c] & below_top(gs)));
-      T += __popc(F[c]);
+#pragma unroll 2
+  for (int c = 0; c < kk; ++c) {
+    const int t = ((c0 + c) << 5) + lane;
+    bool mem = false;
+    if (t < n) {
+      const uint32_t row = permY_g[t];
+      mem = (fbX[row >> 5] >> (row & 31)) & 1u;
     }
+    const uint32_t f = __ballot_sync(FULL, mem);
+    const uint32_t gs = (c0 + c < nwords) ? gsY[c0 + c] : 0u;
+    if (gs) lastB = (int32_t)(T + __popc(f & below_top(gs)));
+    T += __popc(f);
   }
   if (lane == 0) {
     descT[warp] = T;
@@ -233,25 +243,28 @@ __device__ __forceinline__ void emit_first_group(uint32_t* __restrict__ S, const
   __syncthreads();
   uint32_t G, total;
   int32_t carry;
-  cross_warp<W, true>(descT, descB, lane, warp, G, total, carry);
+  cross_warp<true>(descT, descB, nwarps, lane, warp, G, total, carry);
   uint32_t P = G;
-#pragma unroll
-  for (int c = 0; c < K; ++c) {
-    if (c < mycnt) {
-      const int t = base + (c << 5) + lane;
-      const uint32_t f = F[c];
-      const uint32_t gs = gsY[c0 + c];
-      const uint32_t P1 = P + __popc(f & lt);
-      if ((f >> lane) & 1u) {
-        const uint32_t row = permY_g[t];
-        const uint32_t seg = gs & le;
-        const uint32_t startE = seg ? P + __popc(f & below_top(seg)) : (uint32_t)carry;
-        S[P1] = rankY[row];
-        ties += P1 - startE;
-      }
-      if (gs) carry = (int32_t)(P + __popc(f & below_top(gs)));
-      P += __popc(f);
+#pragma unroll 2
+  for (int c = 0; c < kk; ++c) {
+    const int t = ((c0 + c) << 5) + lane;
+    bool mem = false;
+    uint32_t row = 0;
+    if (t < n) {
+      row = permY_g[t];
+      mem = (fbX[row >> 5] >> (row & 31)) & 1u;
     }
+    const uint32_t f = __ballot_sync(FULL, mem);
+    const uint32_t gs = (c0 + c < nwords) ? gsY[c0 + c] : 0u;
+    const uint32_t P1 = P + __popc(f & lt);
+    if (mem) {
+      const uint32_t seg = gs & le;
+      const uint32_t startE = seg ? P + __popc(f & below_top(seg)) : (uint32_t)carry;
+      Sh<uint16_t>::st(buf, P1, rankY[row]);
+      ties += P1 - startE;
+    }
+    if (gs) carry = (int32_t)(P + __popc(f & below_top(gs)));
+    P += __popc(f);
   }
 }
 
@@ -276,53 +289,59 @@ struct TiledParams {
   unsigned long long* unit_counter;
   long long n_units;
   int n, n32, nstride, wstride;
+  int kk;            // chunks per warp for the full sequence
+  int region_bytes;  // bytes of the ping-pong region
 };
 
-template <int W>
+// Shared-memory layout of one CTA (all offsets multiples of 16 bytes)
 struct Carve {
-  uint32_t* S;
-  uint16_t* rankY;
+  unsigned long long* red;  // [32][4]
+  long long* unit_slot;
+  uint32_t region;  // shared address of the ping-pong region
   uint32_t* gsY;
   uint32_t* nabY;
   uint32_t* fbX;
   uint32_t* descT;
   int32_t* descB;
-  unsigned long long* red;
-  long long* unit_slot;
-  __device__ Carve(unsigned char* p, int n32, int nstride, int wstride) {
+  uint16_t* rankY;
+  __device__ Carve(unsigned char* p, int region_bytes, int wstride) {
     red = reinterpret_cast<unsigned long long*>(p);
-    p += sizeof(unsigned long long) * (W * 4);
+    p += 8 * 32 * 4;
     unit_slot = reinterpret_cast<long long*>(p);
     p += 16;
-    S = reinterpret_cast<uint32_t*>(p);
-    p += 4 * (size_t)n32;
+    descT = reinterpret_cast<uint32_t*>(p);
+    p += 4 * 32;
+    descB = reinterpret_cast<int32_t*>(p);
+    p += 4 * 32;
     gsY = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)wstride;
     nabY = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)wstride;
     fbX = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)wstride;
-    descT = reinterpret_cast<uint32_t*>(p);
-    p += 4 * 32;
-    descB = reinterpret_cast<int32_t*>(p);
-    p += 4 * 32;
+    region = smem_addr(p);
+    p += region_bytes;
     rankY = reinterpret_cast<uint16_t*>(p);
   }
 };
 
-inline size_t tiled_smem_bytes(int W, int n32, int nstride, int wstride, bool with_rank) {
-  return 8 * (size_t)(W * 4) + 16 + 4 * (size_t)n32 + 12 * (size_t)wstride + 256 +
+inline size_t tiled_smem_bytes(int region_bytes, int nstride, int wstride, bool with_rank) {
+  return 8 * 32 * 4 + 16 + 256 + 12 * (size_t)wstride + (size_t)region_bytes +
          (with_rank ? 2 * (size_t)nstride : 0);
 }
 
-template <int W, int K, int MINB>
-__global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledParams p) {
+// MAXT/MINB only steer the register allocation (occupancy classes); the code is identical.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Carve<W> sm(smem_raw, p.n32, p.nstride, p.wstride);
+  Carve sm(smem_raw, p.region_bytes, p.wstride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int T = 32 * W;
-  const int n = p.n, n32 = p.n32;
-  const int nwords = n32 >> 5;
+  const int T = blockDim.x, nwarps = T >> 5;
+  const int n = p.n;
+  const int nwords = p.n32 >> 5;
+  const int kk = p.kk;
+  const int cap = (nwarps * kk) << 5;
+  const uint32_t bufA = sm.region, bufB16 = sm.region + 2u * cap;
 
   for (;;) {
     if (tid == 0) *sm.unit_slot = (long long)atomicAdd(p.unit_counter, 1ull);
@@ -344,6 +363,7 @@ __global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledPa
       }
     }
     const uint16_t* permY_g = p.perm + (size_t)ycol * p.nstride;
+    const uint32_t* g0Yg = ((YS.flags & 1) ? p.firstbits : p.nabits) + (size_t)ycol * p.wstride;
     const int L = YS.levels;
     const uint32_t padA = (1u << L) - 1u;
     __syncthreads();
@@ -355,10 +375,15 @@ __global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledPa
       const uint16_t* permX = p.perm + (size_t)xcol * p.nstride;
       const uint32_t* fbXg = p.firstbits + (size_t)xcol * p.wstride;
       const uint32_t* nbXg = p.nabits + (size_t)xcol * p.wstride;
-      uint32_t bpart = 0;
+      const bool absorbed = ((XS.flags | YS.flags) & 1) != 0;
+      uint32_t bpart = 0, g00part = 0;
       for (int i = tid; i < nwords; i += T) {
-        sm.fbX[i] = fbXg[i];
-        bpart += __popc(nbXg[i] & sm.nabY[i]);
+        const uint32_t fb = fbXg[i], nb = nbXg[i];
+        sm.fbX[i] = fb;
+        bpart += __popc(nb & sm.nabY[i]);
+        // joint group 0 = rows in the lowest tie group of both columns; it equals the
+        // joint-missing rows unless a column's missing rows tie with its minimum
+        if (absorbed) g00part += __popc(((XS.flags & 1) ? fb : nb) & g0Yg[i]);
       }
       if (YS.n_groups < 2 || XS.n_groups < 2) {
         // a constant or all-missing column: K3 reports NA; only the joint-missing count is kept
@@ -367,38 +392,46 @@ __global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledPa
         __syncthreads();
         if (tid == 0) {
           unsigned long long bb = 0;
-          for (int w = 0; w < W; ++w) bb += sm.red[w * 4 + 3];
+          for (int w = 0; w < nwarps; ++w) bb += sm.red[w * 4 + 3];
           PairRaw r;
           r.dis = 0;
           r.ntie = 0;
           r.b = (long long)bb;
+          r.g00 = (long long)bb;
           p.raw[slot] = r;
         }
         __syncthreads();
         continue;
       }
       const int f = XS.first_run;
-      for (int q = f + tid; q < n32; q += T) sm.S[q] = (q < n) ? (uint32_t)sm.rankY[permX[q]] : padA;
+      for (int q = f + tid; q < cap; q += T)
+        Sh<uint16_t>::st(bufA, q, (q < n) ? (uint32_t)sm.rankY[permX[q]] : padA);
       __syncthreads();
       uint32_t ties = 0;
-      if (f > 0)
-        emit_first_group<W, K>(sm.S, n, n32, permY_g, sm.rankY, sm.gsY, sm.fbX, sm.descT, sm.descB,
-                               lane, warp, ties);
-      __syncthreads();
+      if (f > 0) {
+        emit_first_group(bufA, n, kk, nwarps, permY_g, sm.rankY, sm.gsY, sm.fbX, sm.descT, sm.descB,
+                         lane, warp, ties);
+        __syncthreads();
+      }
       uint32_t accA = 0, accB = 0, dummy = 0;
-      partition_pass<W, K, false>(sm.S, n32, n, L, sm.descT, sm.descB, lane, warp, accA, dummy);
+      partition_pass<uint16_t, false>(bufA, bufB16, kk, nwarps, n, L, sm.descT, sm.descB, lane, warp,
+                                      accA, dummy);
       const int m = XS.n_tied;
       if (m > 0) {
-        const int m32 = (m + 31) & ~31;
+        const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
+        const int capB = (nwarps * kkB) << 5;
         const uint16_t* trow = p.trow + (size_t)xcol * p.nstride;
         const uint16_t* trun = p.trun + (size_t)xcol * p.nstride;
-        for (int t = tid; t < m32; t += T)
-          sm.S[t] = (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)sm.rankY[trow[t]]) : 0xffffffffu;
+        for (int t = tid; t < capB; t += T)
+          Sh<uint32_t>::st(bufA, t,
+                           (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)sm.rankY[trow[t]]) : 0xffffffffu);
         __syncthreads();
-        partition_pass<W, K, true>(sm.S, m32, m, L, sm.descT, sm.descB, lane, warp, accB, ties);
+        partition_pass<uint32_t, true>(bufA, bufA + 4u * capB, kkB, nwarps, m, L, sm.descT, sm.descB,
+                                       lane, warp, accB, ties);
       }
       const unsigned long long sA = warp_sum_u64(accA), sB = warp_sum_u64(accB),
-                               sT = warp_sum_u64(ties), sb = warp_sum_u64(bpart);
+                               sT = warp_sum_u64(ties),
+                               sb = warp_sum_u64(((unsigned long long)g00part << 32) | bpart);
       if (lane == 0) {
         sm.red[warp * 4 + 0] = sA;
         sm.red[warp * 4 + 1] = sB;
@@ -408,7 +441,7 @@ __global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledPa
       __syncthreads();
       if (tid == 0) {
         unsigned long long a = 0, b2 = 0, t2 = 0, bb = 0;
-        for (int w = 0; w < W; ++w) {
+        for (int w = 0; w < nwarps; ++w) {
           a += sm.red[w * 4 + 0];
           b2 += sm.red[w * 4 + 1];
           t2 += sm.red[w * 4 + 2];
@@ -417,7 +450,8 @@ __global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledPa
         PairRaw r;
         r.dis = (long long)(a - YS.cconst - b2);
         r.ntie = (long long)t2;
-        r.b = (long long)bb;
+        r.b = (long long)(bb & 0xffffffffull);
+        r.g00 = absorbed ? (long long)(bb >> 32) : r.b;
         p.raw[slot] = r;
       }
       __syncthreads();
@@ -427,15 +461,15 @@ __global__ void __launch_bounds__(32 * W, MINB) pairs_tiled_kernel(const TiledPa
 }
 
 // cconst of every column: the raw pass-A count of the column's own sorted rank sequence
-// (no inversions), evaluated by the same code path and padding as the pair kernel.
-template <int W, int K, int MINB>
-__global__ void __launch_bounds__(32 * W, MINB)
-    column_const_kernel(const uint16_t* __restrict__ perm, const uint16_t* __restrict__ rank,
-                        ColStats* stats, int n, int n32, int nstride, int wstride) {
+// (no inversions), evaluated by the same code path as the pair kernel.
+__global__ void column_const_kernel(const uint16_t* __restrict__ perm, const uint16_t* __restrict__ rank,
+                                    ColStats* stats, int n, int kk, int region_bytes, int nstride,
+                                    int wstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Carve<W> sm(smem_raw, n32, nstride, wstride);
+  Carve sm(smem_raw, region_bytes, wstride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int T = 32 * W;
+  const int T = blockDim.x, nwarps = T >> 5;
+  const int cap = (nwarps * kk) << 5;
   const int col = blockIdx.x;
   const ColStats CS = stats[col];
   if (CS.n_groups < 2) {
@@ -445,16 +479,18 @@ __global__ void __launch_bounds__(32 * W, MINB)
   const uint16_t* pm = perm + (size_t)col * nstride;
   const uint16_t* rk = rank + (size_t)col * nstride;
   const uint32_t padA = (1u << CS.levels) - 1u;
-  for (int q = tid; q < n32; q += T) sm.S[q] = (q < n) ? (uint32_t)rk[pm[q]] : padA;
+  const uint32_t bufA = sm.region, bufB = sm.region + 2u * cap;
+  for (int q = tid; q < cap; q += T) Sh<uint16_t>::st(bufA, q, (q < n) ? (uint32_t)rk[pm[q]] : padA);
   __syncthreads();
   uint32_t acc = 0, dummy = 0;
-  partition_pass<W, K, false>(sm.S, n32, n, CS.levels, sm.descT, sm.descB, lane, warp, acc, dummy);
+  partition_pass<uint16_t, false>(bufA, bufB, kk, nwarps, n, CS.levels, sm.descT, sm.descB, lane, warp, acc,
+                                  dummy);
   const unsigned long long s = warp_sum_u64(acc);
   if (lane == 0) sm.red[warp] = s;
   __syncthreads();
   if (tid == 0) {
     unsigned long long a = 0;
-    for (int w = 0; w < W; ++w) a += sm.red[w];
+    for (int w = 0; w < nwarps; ++w) a += sm.red[w];
     stats[col].cconst = a;
   }
 }
@@ -482,6 +518,7 @@ __global__ void pairs_naive_kernel(const TiledParams p, long long P, uint32_t* s
       r.dis = 0;
       r.ntie = 0;
       r.b = 0;
+      r.g00 = 0;
       if (XS.n_groups >= 2 && YS.n_groups >= 2) {
         const uint16_t* permX = p.perm + (size_t)xcol * p.nstride;
         const uint16_t* rankX = p.rank + (size_t)xcol * p.nstride;
@@ -519,9 +556,15 @@ __global__ void pairs_naive_kernel(const TiledParams p, long long P, uint32_t* s
       {
         const uint32_t* nbX = p.nabits + (size_t)xcol * p.wstride;
         const uint32_t* nbY = p.nabits + (size_t)ycol * p.wstride;
-        long long b = 0;
-        for (int w = 0; w < (p.n32 >> 5); ++w) b += __popc(nbX[w] & nbY[w]);
+        const uint32_t* g0X = ((XS.flags & 1) ? p.firstbits : p.nabits) + (size_t)xcol * p.wstride;
+        const uint32_t* g0Y = ((YS.flags & 1) ? p.firstbits : p.nabits) + (size_t)ycol * p.wstride;
+        long long b = 0, g00 = 0;
+        for (int w = 0; w < (p.n32 >> 5); ++w) {
+          b += __popc(nbX[w] & nbY[w]);
+          g00 += __popc(g0X[w] & g0Y[w]);
+        }
         r.b = b;
+        r.g00 = g00;
       }
       p.raw[slot] = r;
     }
@@ -559,7 +602,7 @@ __global__ void __launch_bounds__(128) epilogue_kernel(const EpiParams p) {
       const PairRaw r = p.raw[slot];
       PairOut o;
       // reference naming: x = first column of the pair (unit.col), y = the second
-      pair_epilogue(p.n, p.stats[unit.col], p.stats[xcol], r.dis, r.ntie, r.b, p.perspective,
+      pair_epilogue(p.n, p.stats[unit.col], p.stats[xcol], r.dis, r.ntie, r.b, r.g00, p.perspective,
                     p.alternative, p.continuity, o);
       p.tau[slot] = o.tau;
       if (p.pvalue) p.pvalue[slot] = o.pvalue;
@@ -569,7 +612,7 @@ __global__ void __launch_bounds__(128) epilogue_kernel(const EpiParams p) {
       if (p.counts) {
         long long* c = p.counts + 7 * slot;
         c[0] = r.dis;
-        c[1] = (p.perspective == 1) ? r.ntie - r.b * (r.b - 1) / 2 : r.ntie;
+        c[1] = o.ntie;
         c[2] = o.xtie;
         c[3] = o.ytie;
         c[4] = o.tot;
@@ -672,34 +715,6 @@ TiledParams make_params(const PairLaunch& pl) {
   return p;
 }
 
-template <int W, int K, int MINB>
-int launch_tiled_t(const TiledParams& p, int n_sm, cudaStream_t stream) {
-  const size_t smem = tiled_smem_bytes(W, p.n32, p.nstride, p.wstride, true);
-  auto kern = pairs_tiled_kernel<W, K, MINB>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return -1;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem) != cudaSuccess || per_sm < 1)
-    return -1;
-  long long grid = (long long)n_sm * per_sm;
-  if (grid > p.n_units) grid = p.n_units;
-  if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, 32 * W, smem, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-template <int W, int K, int MINB>
-int launch_const_t(ColumnTables& t, cudaStream_t stream) {
-  const int n32 = (int)((t.n + 31) & ~31LL);
-  const size_t smem = tiled_smem_bytes(W, n32, (int)t.nstride, (int)t.wstride, false);
-  auto kern = column_const_kernel<W, K, MINB>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return -1;
-  kern<<<(unsigned)t.C, 32 * W, smem, stream>>>(t.perm, t.rank, t.stats, (int)t.n, n32, (int)t.nstride,
-                                               (int)t.wstride);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
 }  // namespace
 
 int64_t tiled_max_n() { return 32768; }
@@ -719,30 +734,76 @@ int measure_smem_bandwidth(double* gbps32, double* gbps128) {
   return 0;
 }
 
-// The (warps, chunks-per-warp) shape is chosen from n; both launchers must agree because
-// cconst depends on the padded length only, not on the shape -- they do by construction,
-// the shape only has to cover n32.
-#define ICIKT_DISPATCH(FN, ...)                                   \
-  do {                                                            \
-    if (n32 <= 2048) return FN<4, 16, 8>(__VA_ARGS__);            \
-    if (n32 <= 4096) return FN<8, 16, 4>(__VA_ARGS__);            \
-    if (n32 <= 8192) return FN<16, 16, 2>(__VA_ARGS__);           \
-    if (n32 <= 16384) return FN<32, 16, 1>(__VA_ARGS__);          \
-    if (n32 <= 24576) return FN<32, 24, 1>(__VA_ARGS__);          \
-    if (n32 <= 32768) return FN<32, 32, 1>(__VA_ARGS__);          \
-    return -1;                                                    \
-  } while (0)
-
-int launch_pairs_tiled(const PairLaunch& pl, int n_sm, cudaStream_t stream) {
-  if (cudaMemsetAsync(pl.unit_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return -1;
-  const TiledParams p = make_params(pl);
-  const int n32 = p.n32;
-  ICIKT_DISPATCH(launch_tiled_t, p, n_sm, stream);
+// Launch shape for vectors of length n: warps per CTA, chunks per warp, bytes of the ping-pong
+// region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied list).
+TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override) {
+  TiledShape sh;
+  const int nchunks = (int)((n + 31) / 32);
+  int W = n <= 1024 ? 2 : n <= 4096 ? 4 : n <= 8192 ? 8 : n <= 16384 ? 16 : 32;
+  if (const char* e = getenv("ICIKT_WARPS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 32) W = v;
+  }
+  if (warps_override >= 1 && warps_override <= 32) W = warps_override;
+  sh.warps = W;
+  sh.kk = (nchunks + W - 1) / W;
+  const int cap = W * sh.kk * 32;
+  const int mchunks = (int)((max_tied + 31) / 32);
+  const int kkB = (mchunks + W - 1) / W;
+  const int capB = W * kkB * 32;
+  sh.region_bytes = (std::max(2 * 2 * cap, 2 * 4 * capB) + 15) & ~15;
+  return sh;
 }
 
-int launch_column_consts(ColumnTables& tab, cudaStream_t stream) {
-  const int n32 = (int)((tab.n + 31) & ~31LL);
-  ICIKT_DISPATCH(launch_const_t, tab, stream);
+template <int MAXT, int MINB>
+static int launch_tiled_variant(const TiledParams& p, const TiledShape& sh, size_t smem, int n_sm,
+                                cudaStream_t stream) {
+  auto kern = pairs_tiled_kernel<MAXT, MINB>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * sh.warps, smem) != cudaSuccess ||
+      per_sm < 1)
+    return -1;
+  long long grid = (long long)n_sm * per_sm;
+  if (grid > p.n_units) grid = p.n_units;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, 32 * sh.warps, smem, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream) {
+  if (cudaMemsetAsync(pl.unit_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+  TiledParams p = make_params(pl);
+  p.kk = sh.kk;
+  p.region_bytes = sh.region_bytes;
+  const size_t smem = tiled_smem_bytes(sh.region_bytes, p.nstride, p.wstride, true);
+  if (smem > 227 * 1024) return -2;
+  // register class: how many CTAs the shared-memory footprint allows decides how few registers
+  // per thread are worth having
+  const int threads = 32 * sh.warps;
+  const int by_smem = (int)std::min<size_t>(32, (227 * 1024) / (smem + 1024));
+  int want_threads = std::min(2048, by_smem * threads);
+  if (const char* e = getenv("ICIKT_REGCLASS")) {
+    const int v = atoi(e);
+    want_threads = v == 0 ? 1024 : v == 1 ? 1536 : 2048;
+  }
+  if (threads <= 256 && want_threads > 1536) return launch_tiled_variant<256, 8>(p, sh, smem, n_sm, stream);
+  if (threads <= 512 && want_threads > 1024) return launch_tiled_variant<512, 3>(p, sh, smem, n_sm, stream);
+  return launch_tiled_variant<1024, 1>(p, sh, smem, n_sm, stream);
+}
+
+int launch_column_consts(ColumnTables& tab, const TiledShape& sh, cudaStream_t stream) {
+  // the constant does not depend on the tied lists: only the pass-A buffers are needed
+  const int cap = sh.warps * sh.kk * 32;
+  const int region = (2 * 2 * cap + 15) & ~15;
+  const size_t smem = tiled_smem_bytes(region, (int)tab.nstride, (int)tab.wstride, false);
+  if (cudaFuncSetAttribute(column_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess)
+    return -1;
+  column_const_kernel<<<(unsigned)tab.C, 32 * sh.warps, smem, stream>>>(
+      tab.perm, tab.rank, tab.stats, (int)tab.n, sh.kk, region, (int)tab.nstride, (int)tab.wstride);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 size_t naive_scratch_bytes(int64_t n, int64_t n_threads) {

@@ -23,7 +23,7 @@ def epi(tmp_path_factory):
     L = ctypes.CDLL(out)
     lp = ctypes.POINTER(ctypes.c_longlong)
     L.epilogue_host.argtypes = [ctypes.c_longlong, lp, lp, ctypes.c_longlong, ctypes.c_longlong,
-                                ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                 ctypes.POINTER(ctypes.c_double), lp]
     L.epilogue_host.restype = ctypes.c_int
     return L
@@ -47,6 +47,16 @@ def col_stats(v):
     return np.array([a, len(sizes) + (1 if a > 0 else 0), g0extra, s2, s3, s5], dtype=np.int64)
 
 
+def group0(v):
+    """rows in the lowest tie group: the missing rows, plus the minimum if min - 0.1 == min"""
+    na = np.isnan(v)
+    if na.any() and (~na).any():
+        mn = np.nanmin(v)
+        if mn - 0.1 == mn:
+            return na | (v == mn)
+    return na
+
+
 def run(epi, x, y, persp, alt, cont):
     n = x.size
     g = O.ici_kt(x, y, "global")  # integer inputs of the epilogue come from the global problem
@@ -56,10 +66,11 @@ def run(epi, x, y, persp, alt, cont):
     else:
         dis, ntie = 0, 0
     xs, ys = col_stats(x), col_stats(y)
+    g00 = int((group0(x) & group0(y)).sum())
     out4 = np.zeros(4)
     oc = np.zeros(4, dtype=np.int64)
     lp = ctypes.POINTER(ctypes.c_longlong)
-    st = epi.epilogue_host(n, xs.ctypes.data_as(lp), ys.ctypes.data_as(lp), dis, ntie, b,
+    st = epi.epilogue_host(n, xs.ctypes.data_as(lp), ys.ctypes.data_as(lp), dis, ntie, b, g00,
                            O.PERSPECTIVE.get(persp, 0), O.ALTERNATIVE.get(alt, 3), int(cont),
                            out4.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), oc.ctypes.data_as(lp))
     return st, out4, oc
@@ -118,6 +129,27 @@ def test_epilogue_absorbed_minimum(epi):
         assert st == ref.status == 0
         assert (oc[0], oc[1]) == (ref.xtie, ref.ytie)
         assert close(out4[0], ref.tau, 1e-12) and close(out4[1], ref.pvalue, 1e-9)
+
+
+def test_epilogue_absorbed_minimum_joint_group(epi):
+    # both columns absorb: the joint lowest group holds more rows than the joint-missing rows
+    rng = np.random.default_rng(8)
+    for trial in range(200):
+        n = int(rng.integers(4, 60))
+        x = np.round(rng.normal(size=n) * 2)
+        y = np.round(rng.normal(size=n) * 2)
+        x[rng.random(n) < 0.3] = -np.inf
+        y[rng.random(n) < 0.3] = -np.inf if trial % 2 else -1e18
+        x[rng.random(n) < 0.3] = np.nan
+        y[rng.random(n) < 0.3] = np.nan
+        for persp in ("global", "local"):
+            ref = O.ici_kt(x, y, persp)
+            st, out4, oc = run(epi, x, y, persp, "two.sided", False)
+            assert st == ref.status
+            if st == 0:
+                assert (oc[0], oc[1], oc[2], oc[3]) == (ref.xtie, ref.ytie, ref.tot, ref.n_entry)
+                assert close(out4[0], ref.tau, 1e-12) and close(out4[2], ref.tau_max, 1e-12)
+                assert close(out4[1], ref.pvalue, 1e-9)
 
 
 def test_epilogue_n2_gives_nan_pvalue(epi):
