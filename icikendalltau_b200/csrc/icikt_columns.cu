@@ -10,7 +10,7 @@
 //                       tie group are interchangeable for every downstream count).
 //   column_rank_kernel  compare_self + cumsum (:15-31, :250-251) -> dense ranks; tie-group
 //                       sizes -> count_rank_tie sums (:103-118) in exact int64; the bit masks
-//                       and the tied-row list the pair kernel needs.
+//                       and the tied-row list (rows + dense group index) the pair kernel needs.
 #include <cub/device/device_segmented_sort.cuh>
 
 #include "icikt_internal.h"
@@ -167,24 +167,28 @@ __global__ void __launch_bounds__(RANK_THREADS)
   __syncthreads();
   for (int w = tid; w < nwords; w += RANK_THREADS) firstbits[(size_t)col * wstride + w] = bits[w];
 
-  // rows of the other tied groups, in sorted order, with their group id
+  // rows of the other tied groups, in sorted order, with a dense index of their group
   carry = 0;
+  int gcarry = 0;
   for (int t0 = 0; t0 < n32; t0 += RANK_THREADS) {
     const int t = t0 + tid;
-    int flag = 0, r = 0;
+    int flag = 0, r = 0, gstart = 0;
     uint16_t row = 0;
     if (t < n && t >= g0size) {
       row = pm[t];
       r = rk[row];
       flag = (gpos[r + 1] - gpos[r]) > 1;
+      gstart = flag && (gpos[r] == (uint32_t)t);
     }
-    int total;
+    int total, gtotal;
     const int excl = block_scan_excl(flag, warp_sums, total);
+    const int gincl = block_scan_excl(gstart, warp_sums, gtotal) + gstart;
     if (flag) {
       tr[carry + excl] = row;
-      tg[carry + excl] = (uint16_t)r;
+      tg[carry + excl] = (uint16_t)(gcarry + gincl - 1);
     }
     carry += total;
+    gcarry += gtotal;
   }
 
   if (tid == 0) {
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
     s.levels = L;
     s.g0extra = (a > 0) ? g0size - a : 0;
     s.flags = absorb ? 1 : 0;
-    s.pad_ = 0;
+    s.n_tgroups = gcarry;
     s.s2o = s2;
     s.s3o = s3;
     s.s5o = s5;

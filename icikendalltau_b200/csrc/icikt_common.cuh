@@ -29,8 +29,8 @@ struct ColStats {
   int32_t n_groups;   // K: number of groups (distinct values, NA group included)
   int32_t levels;     // L = max(1, ceil(log2 K)): bits of a dense rank
   int32_t g0extra;    // non-missing rows merged into the NA group
-  int32_t flags;
-  int32_t pad_;
+  int32_t flags;      // bit 0: the missing rows tie with the minimum
+  int32_t n_tgroups;  // number of tie groups of size > 1 other than the first group
   int64_t s2o;        // sum t(t-1)        over groups other than the NA group
   int64_t s3o;        // sum t(t-1)(t-2)
   int64_t s5o;        // sum t(t-1)(2t+5)

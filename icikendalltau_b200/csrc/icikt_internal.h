@@ -18,7 +18,7 @@ struct ColumnTables {
   uint16_t* perm = nullptr;       // [C][nstride] row ids in ascending value order, missing first
   uint16_t* rank = nullptr;       // [C][nstride] dense rank of every row
   uint16_t* trow = nullptr;       // [C][nstride] rows of tied (non-first-group) elements, sorted order
-  uint16_t* trun = nullptr;       // [C][nstride] their group ids (= rank)
+  uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1)
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
   uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group

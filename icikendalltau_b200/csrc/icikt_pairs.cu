@@ -204,66 +204,107 @@ __device__ __forceinline__ void partition_pass(uint32_t a, uint32_t b, const int
   }
 }
 
-// Writes the rows of x's first tie group into buf[0, f) ordered by y: sweep y's sorted order,
-// keep the rows whose bit is set in x's membership mask (ordered stream compaction).  Rows
-// of one y tie group are contiguous in that order (gsY marks group starts), so the joint
-// (x-first-group, y) ties are counted on the way: every kept row adds the number of kept
-// rows before it in its y group.
+// Pass A: the bucket-free counting pass on 16-bit keys (see the file header).  Per level two
+// sweeps over the warp's kk chunks: sweep 1 counts the ones of the segment (ballot + popc on
+// the uniform datapath), the W totals are scanned by every warp, sweep 2 scatters every key to
+// its slot of the other buffer and adds, for every zero-bit key, the number of ones before it.
+// Everything is kept in byte offsets (doubled counts) so that a slot address is one add.
+//   acc2  += 2 * sum over my zero-bit keys of (ones before them inside my warp segment)
+//   fix64 += the part of the count that is uniform per warp: zeros_in_segment * ones_before_segment
+__device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk, const int nwarps,
+                                           const int L, uint32_t* descT, const int lane,
+                                           const int warp, uint32_t& acc2,
+                                           unsigned long long& fix64) {
+  const uint32_t my_off = ((uint32_t)(warp * kk) << 6) + ((uint32_t)lane << 1);
+  const uint32_t total_len = (uint32_t)(nwarps * kk) << 5;
+  const uint32_t lt = lanemask_lt();
+  for (int s = L - 1; s >= 0; --s) {
+    uint32_t bitmask = 1u << s;
+    asm volatile("" : "+r"(bitmask));  // keep `e & bitmask` a single LOP3 with predicate output
+    const uint32_t ra = a + my_off;
+    uint32_t T = 0;
+#pragma unroll 4
+    for (int c = 0; c < kk; ++c) {
+      unsigned short e;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(ra + ((uint32_t)c << 6)) : "memory");
+      T += __popc(__ballot_sync(FULL, ((uint32_t)e & bitmask) != 0u));
+    }
+    if (lane == 0) descT[warp] = T;
+    __syncthreads();
+    const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const uint32_t G = __shfl_sync(FULL, incl - v, warp);  // ones before my segment
+    if (lane == 0) fix64 += (unsigned long long)G * (((uint32_t)kk << 5) - T);
+    const uint32_t one_base = b + 2u * (total_len - total) + 2u * G;  // slot of the first one of my segment
+    const uint32_t zero_base = b + my_off - 2u * G;                    // my slot if no one preceded me
+    uint32_t Tu2 = 0;  // 2 * ones seen so far in my segment (uniform across the warp)
+#pragma unroll 4
+    for (int c = 0; c < kk; ++c) {
+      unsigned short e;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(ra + ((uint32_t)c << 6)) : "memory");
+      const bool one = ((uint32_t)e & bitmask) != 0u;
+      const uint32_t m = __ballot_sync(FULL, one);
+      const uint32_t t = Tu2 + 2u * (uint32_t)__popc(m & lt);
+      const uint32_t addr = one ? one_base + t : zero_base + ((uint32_t)c << 6) - t;
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(e) : "memory");
+      if (!one) acc2 += t;
+      Tu2 += 2u * (uint32_t)__popc(m);
+    }
+    __syncthreads();  // also protects descT for the next level
+    const uint32_t t = a;
+    a = b;
+    b = t;
+  }
+}
+
+// Ordered stream compaction: writes the y-ranks of the rows of x's first tie group into
+// buf[0, f) in ascending y order by sweeping y's sorted order (permY) and keeping the rows whose
+// bit is set in x's membership mask.  Sweep 1 counts the kept rows per warp segment and parks
+// the ballot masks in `fmask`; sweep 2 scatters.  The group is then free of inversions.
 __device__ __forceinline__ void emit_first_group(uint32_t buf, const int n, const int kk,
                                                  const int nwarps,
                                                  const uint16_t* __restrict__ permY_g,
-                                                 const uint16_t* __restrict__ rankY,
-                                                 const uint32_t* __restrict__ gsY,
-                                                 const uint32_t* __restrict__ fbX, uint32_t* descT,
-                                                 int32_t* descB, const int lane, const int warp,
-                                                 uint32_t& ties) {
+                                                 uint32_t rankY_sh, const uint32_t* __restrict__ fbX,
+                                                 uint32_t* __restrict__ fmask, uint32_t* descT,
+                                                 const int lane, const int warp) {
   const int c0 = warp * kk;
-  const int nwords = (n + 31) >> 5;
   const uint32_t lt = lanemask_lt();
-  const uint32_t le = lanemask_le();
   uint32_t T = 0;
-  int32_t lastB = -1;
 #pragma unroll 2
   for (int c = 0; c < kk; ++c) {
     const int t = ((c0 + c) << 5) + lane;
     bool mem = false;
     if (t < n) {
       const uint32_t row = permY_g[t];
-      mem = (fbX[row >> 5] >> (row & 31)) & 1u;
+      mem = (__funnelshift_r(fbX[row >> 5], 0u, row) & 1u) != 0u;  // shift amount is taken mod 32
     }
     const uint32_t f = __ballot_sync(FULL, mem);
-    const uint32_t gs = (c0 + c < nwords) ? gsY[c0 + c] : 0u;
-    if (gs) lastB = (int32_t)(T + __popc(f & below_top(gs)));
+    if (lane == 0) fmask[c0 + c] = f;
     T += __popc(f);
   }
-  if (lane == 0) {
-    descT[warp] = T;
-    descB[warp] = lastB;
-  }
+  if (lane == 0) descT[warp] = T;
   __syncthreads();
-  uint32_t G, total;
-  int32_t carry;
-  cross_warp<true>(descT, descB, nwarps, lane, warp, G, total, carry);
-  uint32_t P = G;
+  const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  uint32_t P = __shfl_sync(FULL, incl - v, warp);
 #pragma unroll 2
   for (int c = 0; c < kk; ++c) {
-    const int t = ((c0 + c) << 5) + lane;
-    bool mem = false;
-    uint32_t row = 0;
-    if (t < n) {
-      row = permY_g[t];
-      mem = (fbX[row >> 5] >> (row & 31)) & 1u;
+    const uint32_t f = fmask[c0 + c];
+    if ((f >> lane) & 1u) {
+      const uint32_t row = permY_g[((c0 + c) << 5) + lane];
+      Sh<uint16_t>::st(buf, P + __popc(f & lt), Sh<uint16_t>::ld(rankY_sh, row));
     }
-    const uint32_t f = __ballot_sync(FULL, mem);
-    const uint32_t gs = (c0 + c < nwords) ? gsY[c0 + c] : 0u;
-    const uint32_t P1 = P + __popc(f & lt);
-    if (mem) {
-      const uint32_t seg = gs & le;
-      const uint32_t startE = seg ? P + __popc(f & below_top(seg)) : (uint32_t)carry;
-      Sh<uint16_t>::st(buf, P1, rankY[row]);
-      ties += P1 - startE;
-    }
-    if (gs) carry = (int32_t)(P + __popc(f & below_top(gs)));
     P += __popc(f);
   }
 }
@@ -298,13 +339,12 @@ struct Carve {
   unsigned long long* red;  // [32][4]
   long long* unit_slot;
   uint32_t region;  // shared address of the ping-pong region
-  uint32_t* gsY;
   uint32_t* nabY;
   uint32_t* fbX;
+  uint32_t* fmask;
   uint32_t* descT;
   int32_t* descB;
-  uint16_t* rankY;
-  __device__ Carve(unsigned char* p, int region_bytes, int wstride) {
+  __device__ Carve(unsigned char* p, int wstride, int fwords) {
     red = reinterpret_cast<unsigned long long*>(p);
     p += 8 * 32 * 4;
     unit_slot = reinterpret_cast<long long*>(p);
@@ -313,34 +353,32 @@ struct Carve {
     p += 4 * 32;
     descB = reinterpret_cast<int32_t*>(p);
     p += 4 * 32;
-    gsY = reinterpret_cast<uint32_t*>(p);
-    p += 4 * (size_t)wstride;
     nabY = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)wstride;
     fbX = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)wstride;
+    fmask = reinterpret_cast<uint32_t*>(p);
+    p += 4 * (size_t)fwords;
     region = smem_addr(p);
-    p += region_bytes;
-    rankY = reinterpret_cast<uint16_t*>(p);
   }
 };
 
-inline size_t tiled_smem_bytes(int region_bytes, int nstride, int wstride, bool with_rank) {
-  return 8 * 32 * 4 + 16 + 256 + 12 * (size_t)wstride + (size_t)region_bytes +
-         (with_rank ? 2 * (size_t)nstride : 0);
+__host__ __device__ inline int fmask_words(int warps, int kk) { return (warps * kk + 3) & ~3; }
+inline size_t tiled_smem_bytes(int region_bytes, int wstride, int fwords) {
+  return 8 * 32 * 4 + 16 + 256 + 8 * (size_t)wstride + 4 * (size_t)fwords + (size_t)region_bytes;
 }
 
 // MAXT/MINB only steer the register allocation (occupancy classes); the code is identical.
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Carve sm(smem_raw, p.region_bytes, p.wstride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
   const int n = p.n;
   const int nwords = p.n32 >> 5;
   const int kk = p.kk;
   const int cap = (nwarps * kk) << 5;
+  Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk));
   const uint32_t bufA = sm.region, bufB16 = sm.region + 2u * cap;
 
   for (;;) {
@@ -351,18 +389,13 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
     const PairUnit unit = p.units[u];
     const int ycol = unit.col;
     const ColStats YS = p.stats[ycol];
-    {  // stage column y: dense ranks + tie-group starts + missing mask
-      const uint4* src = reinterpret_cast<const uint4*>(p.rank + (size_t)ycol * p.nstride);
-      uint4* dst = reinterpret_cast<uint4*>(sm.rankY);
-      for (int i = tid; i < (p.nstride >> 3); i += T) dst[i] = src[i];
-      const uint32_t* g = p.grpstart + (size_t)ycol * p.wstride;
+    {  // stage the missing mask of column y (shared by all pairs of the unit)
       const uint32_t* nb = p.nabits + (size_t)ycol * p.wstride;
-      for (int i = tid; i < nwords; i += T) {
-        sm.gsY[i] = g[i];
-        sm.nabY[i] = nb[i];
-      }
+      for (int i = tid; i < nwords; i += T) sm.nabY[i] = nb[i];
     }
     const uint16_t* permY_g = p.perm + (size_t)ycol * p.nstride;
+    const uint16_t* rankY_g = p.rank + (size_t)ycol * p.nstride;
+    const uint32_t* fbYg = p.firstbits + (size_t)ycol * p.wstride;
     const uint32_t* g0Yg = ((YS.flags & 1) ? p.firstbits : p.nabits) + (size_t)ycol * p.wstride;
     const int L = YS.levels;
     const uint32_t padA = (1u << L) - 1u;
@@ -376,13 +409,14 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const uint32_t* fbXg = p.firstbits + (size_t)xcol * p.wstride;
       const uint32_t* nbXg = p.nabits + (size_t)xcol * p.wstride;
       const bool absorbed = ((XS.flags | YS.flags) & 1) != 0;
-      uint32_t bpart = 0, g00part = 0;
+      // joint-missing rows (b), joint lowest group (g00, differs from b only if a column's
+      // missing rows tie with its minimum), and first-group(x) x first-group(y) rows (g11)
+      uint32_t bpart = 0, g00part = 0, g11part = 0;
       for (int i = tid; i < nwords; i += T) {
         const uint32_t fb = fbXg[i], nb = nbXg[i];
         sm.fbX[i] = fb;
         bpart += __popc(nb & sm.nabY[i]);
-        // joint group 0 = rows in the lowest tie group of both columns; it equals the
-        // joint-missing rows unless a column's missing rows tie with its minimum
+        g11part += __popc(fb & fbYg[i]);
         if (absorbed) g00part += __popc(((XS.flags & 1) ? fb : nb) & g0Yg[i]);
       }
       if (YS.n_groups < 2 || XS.n_groups < 2) {
@@ -404,18 +438,40 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         continue;
       }
       const int f = XS.first_run;
-      for (int q = f + tid; q < cap; q += T)
-        Sh<uint16_t>::st(bufA, q, (q < n) ? (uint32_t)sm.rankY[permX[q]] : padA);
-      __syncthreads();
       uint32_t ties = 0;
-      if (f > 0) {
-        emit_first_group(bufA, n, kk, nwarps, permY_g, sm.rankY, sm.gsY, sm.fbX, sm.descT, sm.descB,
-                         lane, warp, ties);
+      __syncthreads();  // fbX is complete
+      if (f > 0 && YS.n_tied > 0) {
+        // joint ties of x's first group with the tied (non-first) groups of y: one shared-memory
+        // counter per tied y group; every member row adds the number of members seen before it
+        uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (sm.region - smem_addr(smem_raw))) + (cap >> 1);
+        const uint16_t* trowY = p.trow + (size_t)ycol * p.nstride;
+        const uint16_t* trunY = p.trun + (size_t)ycol * p.nstride;
+        for (int i = tid; i < YS.n_tgroups; i += T) cnt[i] = 0;
+        __syncthreads();
+        for (int t = tid; t < YS.n_tied; t += T) {
+          const uint32_t row = trowY[t];
+          if ((sm.fbX[row >> 5] >> (row & 31)) & 1u) ties += atomicAdd(&cnt[trunY[t]], 1u);
+        }
         __syncthreads();
       }
-      uint32_t accA = 0, accB = 0, dummy = 0;
-      partition_pass<uint16_t, false>(bufA, bufB16, kk, nwarps, n, L, sm.descT, sm.descB, lane, warp,
-                                      accA, dummy);
+      {  // dense ranks of y go to the second ping-pong buffer until pass A starts
+        const uint4* src = reinterpret_cast<const uint4*>(rankY_g);
+        const uint32_t dst = bufB16;
+        for (int i = tid; i < (p.nstride >> 3); i += T) {
+          const uint4 v = src[i];
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "r"(v.x), "r"(v.y),
+                       "r"(v.z), "r"(v.w)
+                       : "memory");
+        }
+      }
+      __syncthreads();
+      for (int q = f + tid; q < cap; q += T)
+        Sh<uint16_t>::st(bufA, q, (q < n) ? Sh<uint16_t>::ld(bufB16, permX[q]) : padA);
+      if (f > 0) emit_first_group(bufA, n, kk, nwarps, permY_g, bufB16, sm.fbX, sm.fmask, sm.descT, lane, warp);
+      __syncthreads();
+      uint32_t acc2 = 0, accB = 0;
+      unsigned long long fix64 = 0;
+      count_pass(bufA, bufB16, kk, nwarps, L, sm.descT, lane, warp, acc2, fix64);
       const int m = XS.n_tied;
       if (m > 0) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
@@ -424,13 +480,14 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         const uint16_t* trun = p.trun + (size_t)xcol * p.nstride;
         for (int t = tid; t < capB; t += T)
           Sh<uint32_t>::st(bufA, t,
-                           (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)sm.rankY[trow[t]]) : 0xffffffffu);
+                           (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)rankY_g[trow[t]]) : 0xffffffffu);
         __syncthreads();
         partition_pass<uint32_t, true>(bufA, bufA + 4u * capB, kkB, nwarps, m, L, sm.descT, sm.descB,
                                        lane, warp, accB, ties);
       }
-      const unsigned long long sA = warp_sum_u64(accA), sB = warp_sum_u64(accB),
-                               sT = warp_sum_u64(ties),
+      const unsigned long long sA = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64),
+                               sB = warp_sum_u64(accB),
+                               sT = warp_sum_u64(((unsigned long long)g11part << 32) | ties),
                                sb = warp_sum_u64(((unsigned long long)g00part << 32) | bpart);
       if (lane == 0) {
         sm.red[warp * 4 + 0] = sA;
@@ -447,9 +504,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
           t2 += sm.red[w * 4 + 2];
           bb += sm.red[w * 4 + 3];
         }
+        const long long g11 = (long long)(t2 >> 32);  // rows in the first group of both columns
         PairRaw r;
         r.dis = (long long)(a - YS.cconst - b2);
-        r.ntie = (long long)t2;
+        r.ntie = (long long)(t2 & 0xffffffffull) + ((f > 0 && YS.first_run > 0) ? g11 * (g11 - 1) / 2 : 0);
         r.b = (long long)(bb & 0xffffffffull);
         r.g00 = absorbed ? (long long)(bb >> 32) : r.b;
         p.raw[slot] = r;
@@ -463,13 +521,12 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
 // cconst of every column: the raw pass-A count of the column's own sorted rank sequence
 // (no inversions), evaluated by the same code path as the pair kernel.
 __global__ void column_const_kernel(const uint16_t* __restrict__ perm, const uint16_t* __restrict__ rank,
-                                    ColStats* stats, int n, int kk, int region_bytes, int nstride,
-                                    int wstride) {
+                                    ColStats* stats, int n, int kk, int nstride, int wstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Carve sm(smem_raw, region_bytes, wstride);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
   const int cap = (nwarps * kk) << 5;
+  Carve sm(smem_raw, wstride, fmask_words(nwarps, kk));
   const int col = blockIdx.x;
   const ColStats CS = stats[col];
   if (CS.n_groups < 2) {
@@ -482,10 +539,10 @@ __global__ void column_const_kernel(const uint16_t* __restrict__ perm, const uin
   const uint32_t bufA = sm.region, bufB = sm.region + 2u * cap;
   for (int q = tid; q < cap; q += T) Sh<uint16_t>::st(bufA, q, (q < n) ? (uint32_t)rk[pm[q]] : padA);
   __syncthreads();
-  uint32_t acc = 0, dummy = 0;
-  partition_pass<uint16_t, false>(bufA, bufB, kk, nwarps, n, CS.levels, sm.descT, sm.descB, lane, warp, acc,
-                                  dummy);
-  const unsigned long long s = warp_sum_u64(acc);
+  uint32_t acc2 = 0;
+  unsigned long long fix64 = 0;
+  count_pass(bufA, bufB, kk, nwarps, CS.levels, sm.descT, lane, warp, acc2, fix64);
+  const unsigned long long s = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64);
   if (lane == 0) sm.red[warp] = s;
   __syncthreads();
   if (tid == 0) {
@@ -756,19 +813,28 @@ TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override) {
 }
 
 template <int MAXT, int MINB>
-static int launch_tiled_variant(const TiledParams& p, const TiledShape& sh, size_t smem, int n_sm,
-                                cudaStream_t stream) {
+static int tiled_occupancy(int threads, size_t smem) {
   auto kern = pairs_tiled_kernel<MAXT, MINB>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return -1;
+  if (threads > MAXT) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * sh.warps, smem) != cudaSuccess ||
-      per_sm < 1)
-    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return per_sm;
+}
+
+template <int MAXT, int MINB>
+static int launch_tiled_variant(const TiledParams& p, int threads, int per_sm, size_t smem, int n_sm,
+                                cudaStream_t stream) {
   long long grid = (long long)n_sm * per_sm;
   if (grid > p.n_units) grid = p.n_units;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, 32 * sh.warps, smem, stream>>>(p);
+  pairs_tiled_kernel<MAXT, MINB><<<(unsigned)grid, threads, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -777,32 +843,38 @@ int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cud
   TiledParams p = make_params(pl);
   p.kk = sh.kk;
   p.region_bytes = sh.region_bytes;
-  const size_t smem = tiled_smem_bytes(sh.region_bytes, p.nstride, p.wstride, true);
+  const size_t smem = tiled_smem_bytes(sh.region_bytes, p.wstride, fmask_words(sh.warps, sh.kk));
   if (smem > 227 * 1024) return -2;
-  // register class: how many CTAs the shared-memory footprint allows decides how few registers
-  // per thread are worth having
+  // Three register classes of the same code (64 / 40 / 32 registers per thread): take the one
+  // that keeps the most threads resident for this shared-memory footprint, the roomier on ties.
   const int threads = 32 * sh.warps;
-  const int by_smem = (int)std::min<size_t>(32, (227 * 1024) / (smem + 1024));
-  int want_threads = std::min(2048, by_smem * threads);
+  const int o64 = tiled_occupancy<1024, 1>(threads, smem);
+  const int o40 = tiled_occupancy<512, 3>(threads, smem);
+  const int o32 = tiled_occupancy<1024, 2>(threads, smem);
+  int cls = 0, best = o64;
+  if (o40 > best) { cls = 1; best = o40; }
+  if (o32 > best) { cls = 2; best = o32; }
   if (const char* e = getenv("ICIKT_REGCLASS")) {
     const int v = atoi(e);
-    want_threads = v == 0 ? 1024 : v == 1 ? 1536 : 2048;
+    if (v == 0 && o64 > 0) { cls = 0; best = o64; }
+    if (v == 1 && o40 > 0) { cls = 1; best = o40; }
+    if (v == 2 && o32 > 0) { cls = 2; best = o32; }
   }
-  if (threads <= 256 && want_threads > 1536) return launch_tiled_variant<256, 8>(p, sh, smem, n_sm, stream);
-  if (threads <= 512 && want_threads > 1024) return launch_tiled_variant<512, 3>(p, sh, smem, n_sm, stream);
-  return launch_tiled_variant<1024, 1>(p, sh, smem, n_sm, stream);
+  if (best < 1) return -1;
+  if (cls == 2) return launch_tiled_variant<1024, 2>(p, threads, best, smem, n_sm, stream);
+  if (cls == 1) return launch_tiled_variant<512, 3>(p, threads, best, smem, n_sm, stream);
+  return launch_tiled_variant<1024, 1>(p, threads, best, smem, n_sm, stream);
 }
 
 int launch_column_consts(ColumnTables& tab, const TiledShape& sh, cudaStream_t stream) {
   // the constant does not depend on the tied lists: only the pass-A buffers are needed
   const int cap = sh.warps * sh.kk * 32;
-  const int region = (2 * 2 * cap + 15) & ~15;
-  const size_t smem = tiled_smem_bytes(region, (int)tab.nstride, (int)tab.wstride, false);
+  const size_t smem = tiled_smem_bytes((2 * 2 * cap + 15) & ~15, (int)tab.wstride, fmask_words(sh.warps, sh.kk));
   if (cudaFuncSetAttribute(column_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
       cudaSuccess)
     return -1;
   column_const_kernel<<<(unsigned)tab.C, 32 * sh.warps, smem, stream>>>(
-      tab.perm, tab.rank, tab.stats, (int)tab.n, sh.kk, region, (int)tab.nstride, (int)tab.wstride);
+      tab.perm, tab.rank, tab.stats, (int)tab.n, sh.kk, (int)tab.nstride, (int)tab.wstride);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
