@@ -204,30 +204,33 @@ __device__ __forceinline__ void partition_pass(uint32_t a, uint32_t b, const int
   }
 }
 
-// Pass A: the bucket-free counting pass on 16-bit keys (see the file header).  Per level two
-// sweeps over the warp's kk chunks: sweep 1 counts the ones of the segment (ballot + popc on
-// the uniform datapath), the W totals are scanned by every warp, sweep 2 scatters every key to
-// its slot of the other buffer and adds, for every zero-bit key, the number of ones before it.
-// Everything is kept in byte offsets (doubled counts) so that a slot address is one add.
+// Pass A: the bucket-free counting pass on 16-bit keys (see the file header).  Every lane
+// handles TWO adjacent keys per step (one 32-bit shared load), so a warp covers 64 keys with
+// one load and two ballots.  Per level two sweeps over the warp's kk/2 double chunks: sweep 1
+// counts the ones of the segment (ballot + popc on the uniform datapath), the W totals are
+// scanned by every warp, sweep 2 scatters every key to its slot of the other buffer and adds,
+// for every zero-bit key, the number of ones before it.  Everything is kept in byte offsets
+// (doubled counts) so that a slot address is one add.  kk must be even.
 //   acc2  += 2 * sum over my zero-bit keys of (ones before them inside my warp segment)
 //   fix64 += the part of the count that is uniform per warp: zeros_in_segment * ones_before_segment
 __device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk, const int nwarps,
                                            const int L, uint32_t* descT, const int lane,
                                            const int warp, uint32_t& acc2,
                                            unsigned long long& fix64) {
-  const uint32_t my_off = ((uint32_t)(warp * kk) << 6) + ((uint32_t)lane << 1);
+  const uint32_t my_off = ((uint32_t)(warp * kk) << 6) + ((uint32_t)lane << 2);
   const uint32_t total_len = (uint32_t)(nwarps * kk) << 5;
   const uint32_t lt = lanemask_lt();
+  const int kk2 = kk >> 1;
   for (int s = L - 1; s >= 0; --s) {
-    uint32_t bitmask = 1u << s;
-    asm volatile("" : "+r"(bitmask));  // keep `e & bitmask` a single LOP3 with predicate output
+    uint32_t maskL = 1u << s, maskH = 1u << (s + 16);
+    asm volatile("" : "+r"(maskL), "+r"(maskH));  // keep the bit tests single LOP3s with predicate output
     const uint32_t ra = a + my_off;
     uint32_t T = 0;
 #pragma unroll 4
-    for (int c = 0; c < kk; ++c) {
-      unsigned short e;
-      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(ra + ((uint32_t)c << 6)) : "memory");
-      T += __popc(__ballot_sync(FULL, ((uint32_t)e & bitmask) != 0u));
+    for (int c = 0; c < kk2; ++c) {
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ra + ((uint32_t)c << 7)) : "memory");
+      T += __popc(__ballot_sync(FULL, (w & maskL) != 0u)) + __popc(__ballot_sync(FULL, (w & maskH) != 0u));
     }
     if (lane == 0) descT[warp] = T;
     __syncthreads();
@@ -242,19 +245,23 @@ __device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk,
     const uint32_t G = __shfl_sync(FULL, incl - v, warp);  // ones before my segment
     if (lane == 0) fix64 += (unsigned long long)G * (((uint32_t)kk << 5) - T);
     const uint32_t one_base = b + 2u * (total_len - total) + 2u * G;  // slot of the first one of my segment
-    const uint32_t zero_base = b + my_off - 2u * G;                    // my slot if no one preceded me
+    const uint32_t zero_base = b + my_off - 2u * G;                    // my low key's slot if no one preceded it
     uint32_t Tu2 = 0;  // 2 * ones seen so far in my segment (uniform across the warp)
 #pragma unroll 4
-    for (int c = 0; c < kk; ++c) {
-      unsigned short e;
-      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(ra + ((uint32_t)c << 6)) : "memory");
-      const bool one = ((uint32_t)e & bitmask) != 0u;
-      const uint32_t m = __ballot_sync(FULL, one);
-      const uint32_t t = Tu2 + 2u * (uint32_t)__popc(m & lt);
-      const uint32_t addr = one ? one_base + t : zero_base + ((uint32_t)c << 6) - t;
-      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(e) : "memory");
-      if (!one) acc2 += t;
-      Tu2 += 2u * (uint32_t)__popc(m);
+    for (int c = 0; c < kk2; ++c) {
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ra + ((uint32_t)c << 7)) : "memory");
+      const bool oneL = (w & maskL) != 0u, oneH = (w & maskH) != 0u;
+      const uint32_t mL = __ballot_sync(FULL, oneL), mH = __ballot_sync(FULL, oneH);
+      const uint32_t tL = Tu2 + 2u * (uint32_t)(__popc(mL & lt) + __popc(mH & lt));
+      const uint32_t tH = tL + (oneL ? 2u : 0u);
+      const uint32_t zb = zero_base + ((uint32_t)c << 7);
+      const uint32_t addrL = oneL ? one_base + tL : zb - tL;
+      const uint32_t addrH = oneH ? one_base + tH : zb + 2u - tH;
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addrL), "h"((unsigned short)(w & 0xffffu)) : "memory");
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addrH), "h"((unsigned short)(w >> 16)) : "memory");
+      acc2 += (oneL ? 0u : tL) + (oneH ? 0u : tH);
+      Tu2 += 2u * (uint32_t)(__popc(mL) + __popc(mH));
     }
     __syncthreads();  // also protects descT for the next level
     const uint32_t t = a;
@@ -265,28 +272,37 @@ __device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk,
 
 // Ordered stream compaction: writes the y-ranks of the rows of x's first tie group into
 // buf[0, f) in ascending y order by sweeping y's sorted order (permY) and keeping the rows whose
-// bit is set in x's membership mask.  Sweep 1 counts the kept rows per warp segment and parks
-// the ballot masks in `fmask`; sweep 2 scatters.  The group is then free of inversions.
+// bit is set in x's membership mask.  Two rows per lane (one 32-bit load of permY).  Sweep 1
+// counts the kept rows per warp segment and parks the ballot masks in `fmask`; sweep 2 scatters.
+// The group is then free of inversions.  kk must be even; permY is readable up to nstride.
 __device__ __forceinline__ void emit_first_group(uint32_t buf, const int n, const int kk,
                                                  const int nwarps,
                                                  const uint16_t* __restrict__ permY_g,
                                                  uint32_t rankY_sh, const uint32_t* __restrict__ fbX,
                                                  uint32_t* __restrict__ fmask, uint32_t* descT,
                                                  const int lane, const int warp) {
-  const int c0 = warp * kk;
+  const int kk2 = kk >> 1;
+  const int c0 = warp * kk;  // first 32-chunk of my segment; double chunk c covers chunks c0+2c, c0+2c+1
   const uint32_t lt = lanemask_lt();
+  const uint32_t* permY2 = reinterpret_cast<const uint32_t*>(permY_g);
+  const int nvalid2 = (n + 1) >> 1;  // 32-bit words of permY holding at least one valid row
   uint32_t T = 0;
 #pragma unroll 2
-  for (int c = 0; c < kk; ++c) {
-    const int t = ((c0 + c) << 5) + lane;
-    bool mem = false;
-    if (t < n) {
-      const uint32_t row = permY_g[t];
-      mem = (__funnelshift_r(fbX[row >> 5], 0u, row) & 1u) != 0u;  // shift amount is taken mod 32
+  for (int c = 0; c < kk2; ++c) {
+    const int widx = ((c0 + 2 * c) << 4) + lane;  // word index: rows 2*widx, 2*widx+1
+    bool memL = false, memH = false;
+    if (widx < nvalid2) {
+      const uint32_t rr = __ldg(permY2 + widx);
+      const uint32_t r0 = rr & 0xffffu, r1 = rr >> 16;
+      memL = (__funnelshift_r(fbX[r0 >> 5], 0u, r0) & 1u) != 0u;  // shift amount is taken mod 32
+      memH = (2 * widx + 1 < n) && ((__funnelshift_r(fbX[r1 >> 5], 0u, r1) & 1u) != 0u);
     }
-    const uint32_t f = __ballot_sync(FULL, mem);
-    if (lane == 0) fmask[c0 + c] = f;
-    T += __popc(f);
+    const uint32_t fL = __ballot_sync(FULL, memL), fH = __ballot_sync(FULL, memH);
+    if (lane == 0) {
+      fmask[c0 + 2 * c] = fL;
+      fmask[c0 + 2 * c + 1] = fH;
+    }
+    T += __popc(fL) + __popc(fH);
   }
   if (lane == 0) descT[warp] = T;
   __syncthreads();
@@ -299,13 +315,16 @@ __device__ __forceinline__ void emit_first_group(uint32_t buf, const int n, cons
   }
   uint32_t P = __shfl_sync(FULL, incl - v, warp);
 #pragma unroll 2
-  for (int c = 0; c < kk; ++c) {
-    const uint32_t f = fmask[c0 + c];
-    if ((f >> lane) & 1u) {
-      const uint32_t row = permY_g[((c0 + c) << 5) + lane];
-      Sh<uint16_t>::st(buf, P + __popc(f & lt), Sh<uint16_t>::ld(rankY_sh, row));
+  for (int c = 0; c < kk2; ++c) {
+    const uint32_t fL = fmask[c0 + 2 * c], fH = fmask[c0 + 2 * c + 1];
+    const bool memL = (fL >> lane) & 1u, memH = (fH >> lane) & 1u;
+    if (memL || memH) {
+      const uint32_t rr = __ldg(permY2 + (((c0 + 2 * c) << 4) + lane));
+      const uint32_t pL = P + __popc(fL & lt) + __popc(fH & lt);
+      if (memL) Sh<uint16_t>::st(buf, pL, Sh<uint16_t>::ld(rankY_sh, rr & 0xffffu));
+      if (memH) Sh<uint16_t>::st(buf, pL + (memL ? 1u : 0u), Sh<uint16_t>::ld(rankY_sh, rr >> 16));
     }
-    P += __popc(f);
+    P += __popc(fL) + __popc(fH);
   }
 }
 
@@ -465,8 +484,37 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         }
       }
       __syncthreads();
-      for (int q = f + tid; q < cap; q += T)
-        Sh<uint16_t>::st(bufA, q, (q < n) ? Sh<uint16_t>::ld(bufB16, permX[q]) : padA);
+      {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
+        const uint4* px8 = reinterpret_cast<const uint4*>(permX);
+        for (int q8 = (f >> 3) + tid; q8 < (cap >> 3); q8 += T) {
+          const int q0 = q8 << 3;
+          uint32_t o[4];
+          if (q0 + 8 <= n) {
+            const uint4 pv = __ldg(px8 + q8);
+            const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = Sh<uint16_t>::ld(bufB16, pw[j] & 0xffffu) | (Sh<uint16_t>::ld(bufB16, pw[j] >> 16) << 16);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int qa = q0 + 2 * j, qb = qa + 1;
+              const uint32_t lo = (qa < n) ? Sh<uint16_t>::ld(bufB16, permX[qa]) : padA;
+              const uint32_t hi = (qb < n) ? Sh<uint16_t>::ld(bufB16, permX[qb]) : padA;
+              o[j] = lo | (hi << 16);
+            }
+          }
+          if (q0 >= f) {
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(bufA + 2u * q0), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3])
+                         : "memory");
+          } else {  // the block that straddles f: positions below f belong to the emission
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (q0 + j >= f) Sh<uint16_t>::st(bufA, q0 + j, (o[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+          }
+        }
+      }
       if (f > 0) emit_first_group(bufA, n, kk, nwarps, permY_g, bufB16, sm.fbX, sm.fmask, sm.descT, lane, warp);
       __syncthreads();
       uint32_t acc2 = 0, accB = 0;
@@ -803,7 +851,7 @@ TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override) {
   }
   if (warps_override >= 1 && warps_override <= 32) W = warps_override;
   sh.warps = W;
-  sh.kk = (nchunks + W - 1) / W;
+  sh.kk = 2 * ((nchunks + 2 * W - 1) / (2 * W));  // even: the kernels handle two chunks per step
   const int cap = W * sh.kk * 32;
   const int mchunks = (int)((max_tied + 31) / 32);
   const int kkB = (mchunks + W - 1) / W;

@@ -2,20 +2,15 @@
 # Tuning sweep of the pair kernel's launch shape (warps per CTA, register class) per workload.
 out=gpurun_out/sweep.txt
 : > $out
-for w in config2 config5 target; do
-  for W in 2 4 8 16 32; do
-    for R in 0 1 2; do
-      if [ "$w" = "target" ] && [ $W -lt 16 ]; then continue; fi
-      if [ "$w" = "config5" ] && [ $W -gt 8 ]; then continue; fi
-      if [ $R -eq 2 ] && [ $W -gt 8 ]; then continue; fi
-      if [ $R -eq 1 ] && [ $W -gt 16 ]; then continue; fi
-      r=$(ICIKT_WARPS=$W ICIKT_REGCLASS=$R timeout 300 python bench.py --workload $w --steps 3 --warmup 3 --quick 2>/dev/null | python -c "
+run() { # workload W R
+  r=$(ICIKT_WARPS=$2 ICIKT_REGCLASS=$3 timeout 300 python bench.py --workload $1 --steps 3 --warmup 3 --quick 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); r=d['roofline']; print('%.4g pairs/s k2_ms=%.4g frac=%.3f' % (d['value'], r['k2_ms'], r['frac']))
+        d=json.loads(l); r=d['roofline']; print('%.4g pairs/s k2_ms=%.4g k1_ms=%.3g frac=%.3f' % (d['value'], r['k2_ms'], r['k1_ms'], r['frac']))
 ")
-      echo "$w W=$W R=$R $r" | tee -a $out
-    done
-  done
-done
+  echo "$1 W=$2 R=$3 $r" | tee -a $out
+}
+for W in 2 4 8 16; do for R in 0 2; do run config2 $W $R; done; done
+for W in 1 2 4; do for R in 0 2; do run config5 $W $R; done; done
+run target 16 0; run target 16 1; run target 32 0; run target 32 2; run target 8 0; run target 8 2
