@@ -61,6 +61,8 @@ struct icikt_plan {
   bool columns_done = false;
   TiledShape shape;            // launch shape of the tiled kernels
   int32_t* h_max_tied = nullptr;  // pinned
+  unsigned char* d_scratch = nullptr;  // global-memory variant of the pair kernel
+  size_t scratch_bytes = 0;
 
   std::vector<PairUnit> units;
   PairUnit* d_units = nullptr;
@@ -112,6 +114,7 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->d_counts);
   cudaFree(p->d_scalars);
   cudaFree(p->d_naive);
+  cudaFree(p->d_scratch);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -289,7 +292,7 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.stats, (size_t)C));
   PCK(dmalloc(&t.max_tied, 1));
   PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_max_tied), sizeof(int32_t)));
-  p->shape = tiled_shape(n, 0, 0);
+  p->shape = tiled_shape(n, 0, t.wstride, p->n_sm);
   PCK(dmalloc(&p->wk.keys_in, ne));
   PCK(dmalloc(&p->wk.keys_out, ne));
   PCK(dmalloc(&p->wk.vals_in, ne));
@@ -370,15 +373,30 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   }
   if (nlit) CK(cudaMemcpyAsync(p->d_global_na, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, p->stream));
   CK(cudaEventRecord(p->ev[2], p->stream));
-  p->shape = tiled_shape(p->n, 0, 0);
+  // worst-case shape (every row tied) decides whether the global scratch may be needed at all
+  p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm);
+  const TiledShape worst = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
+  const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
+  if (worst.gmem && !p->d_scratch) {
+    p->scratch_bytes = (size_t)worst.max_ctas * (size_t)slot_bytes;
+    CK(cudaMalloc(reinterpret_cast<void**>(&p->d_scratch), p->scratch_bytes));
+  }
+  if (p->shape.gmem) p->shape.region_bytes = slot_bytes;
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
-                               p->stream);
+                               p->d_scratch, p->stream);
   if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
   CK(cudaEventRecord(p->ev[3], p->stream));
   // the pair kernel's shared-memory region is sized for the longest tied list
   CK(cudaMemcpyAsync(p->h_max_tied, p->tab.max_tied, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));  // also: lit[] lives on this stack frame
-  p->shape = tiled_shape(p->n, *p->h_max_tied, 0);
+  {
+    TiledShape sh = tiled_shape(p->n, *p->h_max_tied, p->tab.wstride, p->n_sm);
+    if (sh.gmem) {  // scratch stride
+      const TiledShape worst = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
+      sh.region_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
+    }
+    p->shape = sh;
+  }
   p->tm.n_launches = l;
   p->columns_done = true;
   return ICIKT_OK;
@@ -397,6 +415,7 @@ int icikt_plan_pairs(icikt_plan* p) {
   pl.pj_list = p->d_pj;
   pl.raw = p->d_raw;
   pl.unit_counter = p->d_scalars;
+  pl.scratch = p->d_scratch;
   int launches = 0;
   if (p->P > 0) {
     int l;

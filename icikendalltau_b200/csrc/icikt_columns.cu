@@ -234,7 +234,7 @@ size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride) {
 
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
                    int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
-                   cudaStream_t stream) {
+                   unsigned char* scratch, cudaStream_t stream) {
   const int n = (int)tab.n, C = (int)tab.C;
   const int nstride = (int)tab.nstride, wstride = (int)tab.wstride;
   int launches = 0;
@@ -265,7 +265,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
                                                      wk.gpos, tab.stats, tab.max_tied);
   ++launches;
   if (cudaGetLastError() != cudaSuccess) return -1;
-  const int cl = launch_column_consts(tab, sh, stream);
+  const int cl = launch_column_consts(tab, sh, scratch, stream);
   if (cl < 0) return -1;
   return launches + cl;
 }

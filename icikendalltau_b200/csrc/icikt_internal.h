@@ -42,10 +42,13 @@ struct PairRaw {  // what K2 hands to K3
 
 struct TiledShape {
   int warps = 0;         // warps per CTA
-  int kk = 0;            // 32-element chunks per warp
-  int region_bytes = 0;  // ping-pong region
+  int kk = 0;            // 32-element chunks per warp (even)
+  int region_bytes = 0;  // ping-pong region per CTA
+  int const_region_bytes = 0;  // pass-A buffers of the per-column constant kernel (32 warps)
+  bool gmem = false;     // region lives in the global scratch (does not fit shared memory)
+  int max_ctas = 0;      // CTAs the scratch must provide for
 };
-TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override);
+TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm);
 
 struct PairLaunch {
   const ColumnTables* tab;
@@ -54,6 +57,7 @@ struct PairLaunch {
   const int32_t* pj_list;  // device, may be null
   PairRaw* raw;            // device [P]
   unsigned long long* unit_counter;  // device, zeroed by the launcher
+  unsigned char* scratch = nullptr;  // device, global-memory variant only: max_ctas * region_bytes
 };
 
 // Scratch of the column kernels (allocated by the plan).
@@ -72,10 +76,10 @@ size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride);
 // K1: data (device, column-major, ld) -> tables.  Returns number of kernel launches or <0.
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
                    int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
-                   cudaStream_t stream);
+                   unsigned char* scratch, cudaStream_t stream);
 
 // pass-A correction constant per column (needs the pair kernel's code path)
-int launch_column_consts(ColumnTables& tab, const TiledShape& sh, cudaStream_t stream);
+int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream);
 
 // K2 (tiled) and K2-naive; both fill raw[P].
 int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream);

@@ -54,37 +54,56 @@ __device__ __forceinline__ uint32_t below_top(uint32_t bits) {
   return (1u << (31 - __clz((int)bits))) - 1u;
 }
 
-// ---- explicit shared-memory accessors (32-bit shared-window addresses) --------------------
+// ---- memory-space accessors ----------------------------------------------------------------
+// The counting passes run either on shared memory (32-bit shared-window addresses, explicit
+// ld/st.shared) or, for vectors too long for one CTA's shared memory, on a per-CTA scratch in
+// global memory that stays L2-resident.  Offsets are in bytes.
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-template <typename E>
-struct Sh;
+template <bool G>
+struct Mem;
 template <>
-struct Sh<uint16_t> {
-  static __device__ __forceinline__ uint32_t ld(uint32_t base, uint32_t idx) {
+struct Mem<false> {
+  typedef uint32_t ptr;
+  static __device__ __forceinline__ ptr add(ptr p, int32_t bytes) { return p + (uint32_t)bytes; }
+  static __device__ __forceinline__ uint32_t ld16(ptr p) {
     unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + idx * 2u) : "memory");
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(p) : "memory");
     return v;
   }
-  static __device__ __forceinline__ void st(uint32_t base, uint32_t idx, uint32_t v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + idx * 2u), "h"((unsigned short)v) : "memory");
+  static __device__ __forceinline__ uint32_t ld32(ptr p) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(p), "h"((unsigned short)v) : "memory");
+  }
+  static __device__ __forceinline__ void st32(ptr p, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ void st128(ptr p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
   }
 };
 template <>
-struct Sh<uint32_t> {
-  static __device__ __forceinline__ uint32_t ld(uint32_t base, uint32_t idx) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + idx * 4u) : "memory");
-    return v;
+struct Mem<true> {
+  typedef unsigned char* ptr;
+  static __device__ __forceinline__ ptr add(ptr p, int32_t bytes) { return p + bytes; }
+  static __device__ __forceinline__ uint32_t ld16(ptr p) { return *reinterpret_cast<const unsigned short*>(p); }
+  static __device__ __forceinline__ uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t*>(p); }
+  static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
+    *reinterpret_cast<unsigned short*>(p) = (unsigned short)v;
   }
-  static __device__ __forceinline__ void st(uint32_t base, uint32_t idx, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + idx * 4u), "r"(v) : "memory");
+  static __device__ __forceinline__ void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+  static __device__ __forceinline__ void st128(ptr p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
   }
 };
 
 // Exclusive scan of the per-warp totals (every warp computes it redundantly from shared
-// memory) and, for the bucketed variants, the count at the nearest bucket start that lies in
+// memory) and, for the bucketed pass, the count at the nearest bucket start that lies in
 // an earlier warp's segment (counts are monotone in position, so that is a running max).
 template <bool BUCKETS>
 __device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t* descB, int nwarps,
@@ -110,113 +129,106 @@ __device__ __forceinline__ void cross_warp(const uint32_t* descT, const int32_t*
   }
 }
 
-// One counting pass over a sequence of nwarps*kk*32 elements held in shared memory (positions
-// >= nreal hold all-ones pad keys).  Every warp owns kk consecutive 32-element chunks; kk is
-// uniform over the CTA, so the chunk loops are plain uniform loops.  Each level reads buffer
-// `a` and scatters into buffer `b` (ping-pong), then the two swap.
-//   BUCKETS = false: acc += sum over zero-bit elements of the GLOBAL count of preceding ones.
-//   BUCKETS = true : buckets are runs of equal (key >> (s+1)); acc += ones preceding inside
-//                    the bucket; after level 0 one more sweep on the full key adds, for every
-//                    real element, its index inside its run of equal keys to `ties`.
-template <typename E, bool BUCKETS>
-__device__ __forceinline__ void partition_pass(uint32_t a, uint32_t b, const int kk, const int nwarps,
-                                               const int nreal, const int L, uint32_t* descT,
-                                               int32_t* descB, const int lane, const int warp,
-                                               uint32_t& acc, uint32_t& ties) {
+// Pass B: one counting pass with explicit buckets over a sequence of nwarps*kk*32 32-bit keys
+// (x tie group << 16 | y rank; positions >= nreal hold all-ones pads).  Every warp owns kk
+// consecutive 32-element chunks; kk is uniform over the CTA.  Each level reads buffer `a` and
+// scatters into `b` (ping-pong).  Buckets are runs of equal (key >> (s+1)); acc += ones
+// preceding inside the bucket; after level 0 one more sweep on the full key adds, for every real
+// element, its index inside its run of equal keys to `ties` (the joint ties).
+template <bool G>
+__device__ __forceinline__ void bucket_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
+                                            const int nwarps, const int nreal, const int L,
+                                            uint32_t* descT, int32_t* descB, const int lane,
+                                            const int warp, uint32_t& acc, uint32_t& ties) {
+  typedef Mem<G> M;
   const uint32_t base = (uint32_t)(warp * kk) << 5;
   const uint32_t total_len = (uint32_t)(nwarps * kk) << 5;
   const uint32_t lt = lanemask_lt();
   const uint32_t le = lanemask_le();
 
-  for (int s = L - 1; s >= (BUCKETS ? -1 : 0); --s) {
-    const bool tie_step = (s < 0);  // BUCKETS only: every element counts as a "one"
+  for (int s = L - 1; s >= -1; --s) {
+    const bool tie_step = (s < 0);  // every element counts as a "one": counts become positions
     uint32_t bitmask = tie_step ? 0u : (1u << s);
-    asm volatile("" : "+r"(bitmask));  // keep `e & bitmask` a single LOP3 with predicate output
+    asm volatile("" : "+r"(bitmask));
     const int sh = s + 1;
 
-    // ---- sweep 1: ones per warp segment (+ count at the last bucket start) ----
     uint32_t T = 0;
     int32_t lastB = -1;
     uint32_t carrylast = 0;
-    if (BUCKETS && base > 0) carrylast = Sh<E>::ld(a, base - 1);
+    if (base > 0) carrylast = M::ld32(M::add(a, (int32_t)((base - 1) << 2)));
     const uint32_t prevlast = carrylast;
-#pragma unroll 4
+#pragma unroll 2
     for (int c = 0; c < kk; ++c) {
       const uint32_t pos = base + ((uint32_t)c << 5) + lane;
-      const uint32_t e = Sh<E>::ld(a, pos);
+      const uint32_t e = M::ld32(M::add(a, (int32_t)(pos << 2)));
       const bool one = tie_step || ((e & bitmask) != 0u);
       const uint32_t m = __ballot_sync(FULL, one);
-      if (BUCKETS) {
-        uint32_t prev = __shfl_up_sync(FULL, e, 1);
-        if (lane == 0) prev = carrylast;
-        const uint32_t bd = __ballot_sync(FULL, (pos == 0u) || (((e ^ prev) >> sh) != 0u));
-        carrylast = __shfl_sync(FULL, e, 31);
-        if (bd) lastB = (int32_t)(T + __popc(m & below_top(bd)));
-      }
+      uint32_t prev = __shfl_up_sync(FULL, e, 1);
+      if (lane == 0) prev = carrylast;
+      const uint32_t bd = __ballot_sync(FULL, (pos == 0u) || (((e ^ prev) >> sh) != 0u));
+      carrylast = __shfl_sync(FULL, e, 31);
+      if (bd) lastB = (int32_t)(T + __popc(m & below_top(bd)));
       T += __popc(m);
     }
     if (lane == 0) {
       descT[warp] = T;
-      if (BUCKETS) descB[warp] = lastB;
+      descB[warp] = lastB;
     }
     __syncthreads();
 
-    uint32_t G, total;
+    uint32_t Gp, total;
     int32_t carry;
-    cross_warp<BUCKETS>(descT, descB, nwarps, lane, warp, G, total, carry);
+    cross_warp<true>(descT, descB, nwarps, lane, warp, Gp, total, carry);
     const uint32_t Z = total_len - total;
 
-    // ---- sweep 2: count and scatter ----
-    uint32_t P = G;
+    uint32_t P = Gp;
     carrylast = prevlast;
-#pragma unroll 4
+#pragma unroll 2
     for (int c = 0; c < kk; ++c) {
       const uint32_t pos = base + ((uint32_t)c << 5) + lane;
-      const uint32_t e = Sh<E>::ld(a, pos);
+      const uint32_t e = M::ld32(M::add(a, (int32_t)(pos << 2)));
       const bool one = tie_step || ((e & bitmask) != 0u);
       const uint32_t m = __ballot_sync(FULL, one);
       const uint32_t P1 = P + __popc(m & lt);
-      if (BUCKETS) {
-        uint32_t prev = __shfl_up_sync(FULL, e, 1);
-        if (lane == 0) prev = carrylast;
-        const uint32_t bd = __ballot_sync(FULL, (pos == 0u) || (((e ^ prev) >> sh) != 0u));
-        carrylast = __shfl_sync(FULL, e, 31);
-        const uint32_t seg = bd & le;
-        const uint32_t startP = seg ? P + __popc(m & below_top(seg)) : (uint32_t)carry;
-        const uint32_t cnt = P1 - startP;
-        if (tie_step) {
-          if (pos < (uint32_t)nreal) ties += cnt;
-        } else if (!one) {
-          acc += cnt;
-        }
-        if (bd) carry = (int32_t)(P + __popc(m & below_top(bd)));
-      } else {
-        if (!one) acc += P1;
+      uint32_t prev = __shfl_up_sync(FULL, e, 1);
+      if (lane == 0) prev = carrylast;
+      const uint32_t bd = __ballot_sync(FULL, (pos == 0u) || (((e ^ prev) >> sh) != 0u));
+      carrylast = __shfl_sync(FULL, e, 31);
+      const uint32_t seg = bd & le;
+      const uint32_t startP = seg ? P + __popc(m & below_top(seg)) : (uint32_t)carry;
+      const uint32_t cnt = P1 - startP;
+      if (tie_step) {
+        if (pos < (uint32_t)nreal) ties += cnt;
+      } else if (!one) {
+        acc += cnt;
       }
-      if (!tie_step) Sh<E>::st(b, one ? Z + P1 : pos - P1, e);
+      if (bd) carry = (int32_t)(P + __popc(m & below_top(bd)));
+      if (!tie_step) M::st32(M::add(b, (int32_t)((one ? Z + P1 : pos - P1) << 2)), e);
       P += __popc(m);
     }
     if (tie_step) break;
     __syncthreads();  // also protects descT/descB for the next level
-    const uint32_t t = a;
+    const typename M::ptr t = a;
     a = b;
     b = t;
   }
 }
 
 // Pass A: the bucket-free counting pass on 16-bit keys (see the file header).  Every lane
-// handles TWO adjacent keys per step (one 32-bit shared load), so a warp covers 64 keys with
-// one load and two ballots.  Per level two sweeps over the warp's kk/2 double chunks: sweep 1
+// handles TWO adjacent keys per step (one 32-bit load), so a warp covers 64 keys with one
+// load and two ballots.  Per level two sweeps over the warp's kk/2 double chunks: sweep 1
 // counts the ones of the segment (ballot + popc on the uniform datapath), the W totals are
 // scanned by every warp, sweep 2 scatters every key to its slot of the other buffer and adds,
 // for every zero-bit key, the number of ones before it.  Everything is kept in byte offsets
 // (doubled counts) so that a slot address is one add.  kk must be even.
 //   acc2  += 2 * sum over my zero-bit keys of (ones before them inside my warp segment)
 //   fix64 += the part of the count that is uniform per warp: zeros_in_segment * ones_before_segment
-__device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk, const int nwarps,
-                                           const int L, uint32_t* descT, const int lane,
-                                           const int warp, uint32_t& acc2,
+template <bool G>
+__device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
+                                           const int nwarps, const int L, uint32_t* descT,
+                                           const int lane, const int warp, uint32_t& acc2,
                                            unsigned long long& fix64) {
+  typedef Mem<G> M;
   const uint32_t my_off = ((uint32_t)(warp * kk) << 6) + ((uint32_t)lane << 2);
   const uint32_t total_len = (uint32_t)(nwarps * kk) << 5;
   const uint32_t lt = lanemask_lt();
@@ -224,12 +236,11 @@ __device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk,
   for (int s = L - 1; s >= 0; --s) {
     uint32_t maskL = 1u << s, maskH = 1u << (s + 16);
     asm volatile("" : "+r"(maskL), "+r"(maskH));  // keep the bit tests single LOP3s with predicate output
-    const uint32_t ra = a + my_off;
+    const typename M::ptr ra = M::add(a, (int32_t)my_off);
     uint32_t T = 0;
 #pragma unroll 4
     for (int c = 0; c < kk2; ++c) {
-      uint32_t w;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ra + ((uint32_t)c << 7)) : "memory");
+      const uint32_t w = M::ld32(M::add(ra, c << 7));
       T += __popc(__ballot_sync(FULL, (w & maskL) != 0u)) + __popc(__ballot_sync(FULL, (w & maskH) != 0u));
     }
     if (lane == 0) descT[warp] = T;
@@ -242,29 +253,27 @@ __device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk,
       if (lane >= d) incl += t;
     }
     const uint32_t total = __shfl_sync(FULL, incl, 31);
-    const uint32_t G = __shfl_sync(FULL, incl - v, warp);  // ones before my segment
-    if (lane == 0) fix64 += (unsigned long long)G * (((uint32_t)kk << 5) - T);
-    const uint32_t one_base = b + 2u * (total_len - total) + 2u * G;  // slot of the first one of my segment
-    const uint32_t zero_base = b + my_off - 2u * G;                    // my low key's slot if no one preceded it
+    const uint32_t Gp = __shfl_sync(FULL, incl - v, warp);  // ones before my segment
+    if (lane == 0) fix64 += (unsigned long long)Gp * (((uint32_t)kk << 5) - T);
+    // slot of the first one of my segment / my low key's slot if no one preceded it
+    const typename M::ptr one_base = M::add(b, (int32_t)(2u * (total_len - total) + 2u * Gp));
+    const typename M::ptr zero_base = M::add(b, (int32_t)(my_off - 2u * Gp));
     uint32_t Tu2 = 0;  // 2 * ones seen so far in my segment (uniform across the warp)
 #pragma unroll 4
     for (int c = 0; c < kk2; ++c) {
-      uint32_t w;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ra + ((uint32_t)c << 7)) : "memory");
+      const uint32_t w = M::ld32(M::add(ra, c << 7));
       const bool oneL = (w & maskL) != 0u, oneH = (w & maskH) != 0u;
       const uint32_t mL = __ballot_sync(FULL, oneL), mH = __ballot_sync(FULL, oneH);
       const uint32_t tL = Tu2 + 2u * (uint32_t)(__popc(mL & lt) + __popc(mH & lt));
       const uint32_t tH = tL + (oneL ? 2u : 0u);
-      const uint32_t zb = zero_base + ((uint32_t)c << 7);
-      const uint32_t addrL = oneL ? one_base + tL : zb - tL;
-      const uint32_t addrH = oneH ? one_base + tH : zb + 2u - tH;
-      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addrL), "h"((unsigned short)(w & 0xffffu)) : "memory");
-      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addrH), "h"((unsigned short)(w >> 16)) : "memory");
+      const int32_t zb = c << 7;
+      M::st16(oneL ? M::add(one_base, (int32_t)tL) : M::add(zero_base, zb - (int32_t)tL), w & 0xffffu);
+      M::st16(oneH ? M::add(one_base, (int32_t)tH) : M::add(zero_base, zb + 2 - (int32_t)tH), w >> 16);
       acc2 += (oneL ? 0u : tL) + (oneH ? 0u : tH);
       Tu2 += 2u * (uint32_t)(__popc(mL) + __popc(mH));
     }
     __syncthreads();  // also protects descT for the next level
-    const uint32_t t = a;
+    const typename M::ptr t = a;
     a = b;
     b = t;
   }
@@ -275,12 +284,16 @@ __device__ __forceinline__ void count_pass(uint32_t a, uint32_t b, const int kk,
 // bit is set in x's membership mask.  Two rows per lane (one 32-bit load of permY).  Sweep 1
 // counts the kept rows per warp segment and parks the ballot masks in `fmask`; sweep 2 scatters.
 // The group is then free of inversions.  kk must be even; permY is readable up to nstride.
-__device__ __forceinline__ void emit_first_group(uint32_t buf, const int n, const int kk,
+// `rank_tbl` is y's dense-rank table (u16 per row) in the same memory space as `buf`.
+template <bool G>
+__device__ __forceinline__ void emit_first_group(typename Mem<G>::ptr buf, const int n, const int kk,
                                                  const int nwarps,
                                                  const uint16_t* __restrict__ permY_g,
-                                                 uint32_t rankY_sh, const uint32_t* __restrict__ fbX,
+                                                 typename Mem<G>::ptr rank_tbl,
+                                                 const uint32_t* __restrict__ fbX,
                                                  uint32_t* __restrict__ fmask, uint32_t* descT,
                                                  const int lane, const int warp) {
+  typedef Mem<G> M;
   const int kk2 = kk >> 1;
   const int c0 = warp * kk;  // first 32-chunk of my segment; double chunk c covers chunks c0+2c, c0+2c+1
   const uint32_t lt = lanemask_lt();
@@ -321,8 +334,9 @@ __device__ __forceinline__ void emit_first_group(uint32_t buf, const int n, cons
     if (memL || memH) {
       const uint32_t rr = __ldg(permY2 + (((c0 + 2 * c) << 4) + lane));
       const uint32_t pL = P + __popc(fL & lt) + __popc(fH & lt);
-      if (memL) Sh<uint16_t>::st(buf, pL, Sh<uint16_t>::ld(rankY_sh, rr & 0xffffu));
-      if (memH) Sh<uint16_t>::st(buf, pL + (memL ? 1u : 0u), Sh<uint16_t>::ld(rankY_sh, rr >> 16));
+      if (memL) M::st16(M::add(buf, (int32_t)(pL << 1)), M::ld16(M::add(rank_tbl, (int32_t)((rr & 0xffffu) << 1))));
+      if (memH)
+        M::st16(M::add(buf, (int32_t)((pL + (memL ? 1u : 0u)) << 1)), M::ld16(M::add(rank_tbl, (int32_t)((rr >> 16) << 1))));
     }
     P += __popc(fL) + __popc(fH);
   }
@@ -341,23 +355,24 @@ struct TiledParams {
   const uint16_t* trun;
   const uint32_t* nabits;
   const uint32_t* firstbits;
-  const uint32_t* grpstart;
   const ColStats* stats;
   const PairUnit* units;
   const int32_t* pj_list;
   PairRaw* raw;
   unsigned long long* unit_counter;
+  unsigned char* scratch;        // global-memory variant: per-CTA ping-pong region
+  long long scratch_stride;      // bytes per CTA
   long long n_units;
   int n, n32, nstride, wstride;
-  int kk;            // chunks per warp for the full sequence
-  int region_bytes;  // bytes of the ping-pong region
+  int kk;  // chunks per warp for the full sequence (even)
 };
 
 // Shared-memory layout of one CTA (all offsets multiples of 16 bytes)
 struct Carve {
   unsigned long long* red;  // [32][4]
   long long* unit_slot;
-  uint32_t region;  // shared address of the ping-pong region
+  unsigned char* region_ptr;  // ping-pong region (shared-memory variant)
+  uint32_t region;            // its shared-window address
   uint32_t* nabY;
   uint32_t* fbX;
   uint32_t* fmask;
@@ -378,6 +393,7 @@ struct Carve {
     p += 4 * (size_t)wstride;
     fmask = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)fwords;
+    region_ptr = p;
     region = smem_addr(p);
   }
 };
@@ -387,9 +403,22 @@ inline size_t tiled_smem_bytes(int region_bytes, int wstride, int fwords) {
   return 8 * 32 * 4 + 16 + 256 + 8 * (size_t)wstride + 4 * (size_t)fwords + (size_t)region_bytes;
 }
 
-// MAXT/MINB only steer the register allocation (occupancy classes); the code is identical.
-template <int MAXT, int MINB>
+template <bool G>
+__device__ __forceinline__ typename Mem<G>::ptr region_base(const Carve& sm, const TiledParams& p);
+template <>
+__device__ __forceinline__ uint32_t region_base<false>(const Carve& sm, const TiledParams&) {
+  return sm.region;
+}
+template <>
+__device__ __forceinline__ unsigned char* region_base<true>(const Carve&, const TiledParams& p) {
+  return p.scratch + (size_t)blockIdx.x * (size_t)p.scratch_stride;
+}
+
+// MAXT/MINB only steer the register allocation (occupancy classes); G selects where the
+// ping-pong buffers live (shared memory, or an L2-resident global scratch for long vectors).
+template <int MAXT, int MINB, bool G>
 __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledParams p) {
+  typedef Mem<G> M;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
@@ -398,7 +427,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   const int kk = p.kk;
   const int cap = (nwarps * kk) << 5;
   Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk));
-  const uint32_t bufA = sm.region, bufB16 = sm.region + 2u * cap;
+  const typename M::ptr bufA = region_base<G>(sm, p), bufB16 = M::add(bufA, 2 * cap);
+  // tie counters: second half of the region while it is otherwise unused
+  uint32_t* const cnt = G ? reinterpret_cast<uint32_t*>(p.scratch + (size_t)blockIdx.x * (size_t)p.scratch_stride + 2 * (size_t)cap)
+                          : reinterpret_cast<uint32_t*>(sm.region_ptr + 2 * (size_t)cap);
 
   for (;;) {
     if (tid == 0) *sm.unit_slot = (long long)atomicAdd(p.unit_counter, 1ull);
@@ -416,6 +448,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
     const uint16_t* rankY_g = p.rank + (size_t)ycol * p.nstride;
     const uint32_t* fbYg = p.firstbits + (size_t)ycol * p.wstride;
     const uint32_t* g0Yg = ((YS.flags & 1) ? p.firstbits : p.nabits) + (size_t)ycol * p.wstride;
+    // y's dense-rank table: staged into the second ping-pong buffer (shared variant) or read in place
+    const typename M::ptr rank_tbl = G ? (typename M::ptr)(size_t)rankY_g : bufB16;
     const int L = YS.levels;
     const uint32_t padA = (1u << L) - 1u;
     __syncthreads();
@@ -460,9 +494,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       uint32_t ties = 0;
       __syncthreads();  // fbX is complete
       if (f > 0 && YS.n_tied > 0) {
-        // joint ties of x's first group with the tied (non-first) groups of y: one shared-memory
-        // counter per tied y group; every member row adds the number of members seen before it
-        uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (sm.region - smem_addr(smem_raw))) + (cap >> 1);
+        // joint ties of x's first group with the tied (non-first) groups of y: one counter per
+        // tied y group; every member row adds the number of members seen before it
         const uint16_t* trowY = p.trow + (size_t)ycol * p.nstride;
         const uint16_t* trunY = p.trun + (size_t)ycol * p.nstride;
         for (int i = tid; i < YS.n_tgroups; i += T) cnt[i] = 0;
@@ -473,17 +506,14 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         }
         __syncthreads();
       }
-      {  // dense ranks of y go to the second ping-pong buffer until pass A starts
+      if (!G) {  // dense ranks of y go to the second ping-pong buffer until pass A starts
         const uint4* src = reinterpret_cast<const uint4*>(rankY_g);
-        const uint32_t dst = bufB16;
         for (int i = tid; i < (p.nstride >> 3); i += T) {
-          const uint4 v = src[i];
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "r"(v.x), "r"(v.y),
-                       "r"(v.z), "r"(v.w)
-                       : "memory");
+          const uint4 v = __ldg(src + i);
+          M::st128(M::add(bufB16, i << 4), v.x, v.y, v.z, v.w);
         }
+        __syncthreads();
       }
-      __syncthreads();
       {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
         const uint4* px8 = reinterpret_cast<const uint4*>(permX);
         for (int q8 = (f >> 3) + tid; q8 < (cap >> 3); q8 += T) {
@@ -494,32 +524,31 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
             const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = Sh<uint16_t>::ld(bufB16, pw[j] & 0xffffu) | (Sh<uint16_t>::ld(bufB16, pw[j] >> 16) << 16);
+              o[j] = M::ld16(M::add(rank_tbl, (int32_t)((pw[j] & 0xffffu) << 1))) |
+                     (M::ld16(M::add(rank_tbl, (int32_t)((pw[j] >> 16) << 1))) << 16);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int qa = q0 + 2 * j, qb = qa + 1;
-              const uint32_t lo = (qa < n) ? Sh<uint16_t>::ld(bufB16, permX[qa]) : padA;
-              const uint32_t hi = (qb < n) ? Sh<uint16_t>::ld(bufB16, permX[qb]) : padA;
+              const uint32_t lo = (qa < n) ? M::ld16(M::add(rank_tbl, (int32_t)permX[qa] << 1)) : padA;
+              const uint32_t hi = (qb < n) ? M::ld16(M::add(rank_tbl, (int32_t)permX[qb] << 1)) : padA;
               o[j] = lo | (hi << 16);
             }
           }
           if (q0 >= f) {
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(bufA + 2u * q0), "r"(o[0]), "r"(o[1]),
-                         "r"(o[2]), "r"(o[3])
-                         : "memory");
+            M::st128(M::add(bufA, q0 << 1), o[0], o[1], o[2], o[3]);
           } else {  // the block that straddles f: positions below f belong to the emission
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (q0 + j >= f) Sh<uint16_t>::st(bufA, q0 + j, (o[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+              if (q0 + j >= f) M::st16(M::add(bufA, (q0 + j) << 1), (o[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
           }
         }
       }
-      if (f > 0) emit_first_group(bufA, n, kk, nwarps, permY_g, bufB16, sm.fbX, sm.fmask, sm.descT, lane, warp);
+      if (f > 0) emit_first_group<G>(bufA, n, kk, nwarps, permY_g, rank_tbl, sm.fbX, sm.fmask, sm.descT, lane, warp);
       __syncthreads();
       uint32_t acc2 = 0, accB = 0;
       unsigned long long fix64 = 0;
-      count_pass(bufA, bufB16, kk, nwarps, L, sm.descT, lane, warp, acc2, fix64);
+      count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, lane, warp, acc2, fix64);
       const int m = XS.n_tied;
       if (m > 0) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
@@ -527,11 +556,11 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         const uint16_t* trow = p.trow + (size_t)xcol * p.nstride;
         const uint16_t* trun = p.trun + (size_t)xcol * p.nstride;
         for (int t = tid; t < capB; t += T)
-          Sh<uint32_t>::st(bufA, t,
-                           (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)rankY_g[trow[t]]) : 0xffffffffu);
+          M::st32(M::add(bufA, t << 2),
+                  (t < m) ? (((uint32_t)trun[t] << 16) | (uint32_t)rankY_g[trow[t]]) : 0xffffffffu);
         __syncthreads();
-        partition_pass<uint32_t, true>(bufA, bufA + 4u * capB, kkB, nwarps, m, L, sm.descT, sm.descB,
-                                       lane, warp, accB, ties);
+        bucket_pass<G>(bufA, M::add(bufA, capB << 2), kkB, nwarps, m, L, sm.descT, sm.descB, lane, warp, accB,
+                       ties);
       }
       const unsigned long long sA = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64),
                                sB = warp_sum_u64(accB),
@@ -567,36 +596,40 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
 }
 
 // cconst of every column: the raw pass-A count of the column's own sorted rank sequence
-// (no inversions), evaluated by the same code path as the pair kernel.
-__global__ void column_const_kernel(const uint16_t* __restrict__ perm, const uint16_t* __restrict__ rank,
-                                    ColStats* stats, int n, int kk, int nstride, int wstride) {
+// (no inversions), evaluated by the same code path as the pair kernel.  Grid-stride over columns.
+template <bool G>
+__global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams p, ColStats* stats, int C) {
+  typedef Mem<G> M;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
+  const int n = p.n, kk = p.kk;
   const int cap = (nwarps * kk) << 5;
-  Carve sm(smem_raw, wstride, fmask_words(nwarps, kk));
-  const int col = blockIdx.x;
-  const ColStats CS = stats[col];
-  if (CS.n_groups < 2) {
-    if (tid == 0) stats[col].cconst = 0;
-    return;
-  }
-  const uint16_t* pm = perm + (size_t)col * nstride;
-  const uint16_t* rk = rank + (size_t)col * nstride;
-  const uint32_t padA = (1u << CS.levels) - 1u;
-  const uint32_t bufA = sm.region, bufB = sm.region + 2u * cap;
-  for (int q = tid; q < cap; q += T) Sh<uint16_t>::st(bufA, q, (q < n) ? (uint32_t)rk[pm[q]] : padA);
-  __syncthreads();
-  uint32_t acc2 = 0;
-  unsigned long long fix64 = 0;
-  count_pass(bufA, bufB, kk, nwarps, CS.levels, sm.descT, lane, warp, acc2, fix64);
-  const unsigned long long s = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64);
-  if (lane == 0) sm.red[warp] = s;
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long a = 0;
-    for (int w = 0; w < nwarps; ++w) a += sm.red[w];
-    stats[col].cconst = a;
+  Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk));
+  const typename M::ptr bufA = region_base<G>(sm, p), bufB = M::add(bufA, 2 * cap);
+  for (int col = blockIdx.x; col < C; col += gridDim.x) {
+    const ColStats CS = stats[col];
+    if (CS.n_groups < 2) {
+      if (tid == 0) stats[col].cconst = 0;
+      continue;
+    }
+    const uint16_t* pm = p.perm + (size_t)col * p.nstride;
+    const uint16_t* rk = p.rank + (size_t)col * p.nstride;
+    const uint32_t padA = (1u << CS.levels) - 1u;
+    for (int q = tid; q < cap; q += T) M::st16(M::add(bufA, q << 1), (q < n) ? (uint32_t)rk[pm[q]] : padA);
+    __syncthreads();
+    uint32_t acc2 = 0;
+    unsigned long long fix64 = 0;
+    count_pass<G>(bufA, bufB, kk, nwarps, CS.levels, sm.descT, lane, warp, acc2, fix64);
+    const unsigned long long s = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64);
+    if (lane == 0) sm.red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long a = 0;
+      for (int w = 0; w < nwarps; ++w) a += sm.red[w];
+      stats[col].cconst = a;
+    }
+    __syncthreads();
   }
 }
 
@@ -806,7 +839,6 @@ TiledParams make_params(const PairLaunch& pl) {
   p.trun = t.trun;
   p.nabits = t.nabits;
   p.firstbits = t.firstbits;
-  p.grpstart = t.grpstart;
   p.stats = t.stats;
   p.units = pl.units;
   p.pj_list = pl.pj_list;
@@ -817,12 +849,15 @@ TiledParams make_params(const PairLaunch& pl) {
   p.n32 = (int)((t.n + 31) & ~31LL);
   p.nstride = (int)t.nstride;
   p.wstride = (int)t.wstride;
+  p.scratch = nullptr;
+  p.scratch_stride = 0;
+  p.kk = 0;
   return p;
 }
 
 }  // namespace
 
-int64_t tiled_max_n() { return 32768; }
+int64_t tiled_max_n() { return 65535; }
 
 int measure_smem_bandwidth(double* gbps32, double* gbps128) {
   int dev = 0, n_sm = 0;
@@ -840,16 +875,16 @@ int measure_smem_bandwidth(double* gbps32, double* gbps128) {
 }
 
 // Launch shape for vectors of length n: warps per CTA, chunks per warp, bytes of the ping-pong
-// region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied list).
-TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override) {
+// region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied list), and
+// whether the region fits shared memory or has to live in the global scratch.
+TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm) {
   TiledShape sh;
   const int nchunks = (int)((n + 31) / 32);
-  int W = n <= 1024 ? 2 : n <= 4096 ? 4 : n <= 8192 ? 8 : n <= 16384 ? 16 : 32;
+  int W = n <= 3072 ? 2 : n <= 8192 ? 4 : n <= 12288 ? 8 : n <= 24576 ? 16 : 32;  // tuned on B200, see profiles/
   if (const char* e = getenv("ICIKT_WARPS")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 32) W = v;
   }
-  if (warps_override >= 1 && warps_override <= 32) W = warps_override;
   sh.warps = W;
   sh.kk = 2 * ((nchunks + 2 * W - 1) / (2 * W));  // even: the kernels handle two chunks per step
   const int cap = W * sh.kk * 32;
@@ -857,12 +892,21 @@ TiledShape tiled_shape(int64_t n, int64_t max_tied, int warps_override) {
   const int kkB = (mchunks + W - 1) / W;
   const int capB = W * kkB * 32;
   sh.region_bytes = (std::max(2 * 2 * cap, 2 * 4 * capB) + 15) & ~15;
+  {  // the per-column constant kernel always runs 32 warps: its pass-A buffers must fit a scratch slot too
+    const int kk32 = 2 * ((nchunks + 63) / 64);
+    sh.const_region_bytes = (2 * 2 * (32 * kk32 * 32) + 15) & ~15;
+  }
+  const size_t smem = tiled_smem_bytes(sh.region_bytes, (int)wstride, fmask_words(W, sh.kk));
+  sh.gmem = smem > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr;
+  sh.max_ctas = n_sm * std::max(1, 2048 / (32 * W));
   return sh;
 }
 
-template <int MAXT, int MINB>
-static int tiled_occupancy(int threads, size_t smem) {
-  auto kern = pairs_tiled_kernel<MAXT, MINB>;
+namespace {
+
+template <int MAXT, int MINB, bool G>
+int tiled_occupancy(int threads, size_t smem) {
+  auto kern = pairs_tiled_kernel<MAXT, MINB, G>;
   if (threads > MAXT) return 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
@@ -876,29 +920,20 @@ static int tiled_occupancy(int threads, size_t smem) {
   return per_sm;
 }
 
-template <int MAXT, int MINB>
-static int launch_tiled_variant(const TiledParams& p, int threads, int per_sm, size_t smem, int n_sm,
-                                cudaStream_t stream) {
-  long long grid = (long long)n_sm * per_sm;
-  if (grid > p.n_units) grid = p.n_units;
-  if (grid < 1) grid = 1;
-  pairs_tiled_kernel<MAXT, MINB><<<(unsigned)grid, threads, smem, stream>>>(p);
+template <int MAXT, int MINB, bool G>
+int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size_t smem, cudaStream_t stream) {
+  pairs_tiled_kernel<MAXT, MINB, G><<<(unsigned)grid, threads, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream) {
-  if (cudaMemsetAsync(pl.unit_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return -1;
-  TiledParams p = make_params(pl);
-  p.kk = sh.kk;
-  p.region_bytes = sh.region_bytes;
-  const size_t smem = tiled_smem_bytes(sh.region_bytes, p.wstride, fmask_words(sh.warps, sh.kk));
-  if (smem > 227 * 1024) return -2;
-  // Three register classes of the same code (64 / 40 / 32 registers per thread): take the one
-  // that keeps the most threads resident for this shared-memory footprint, the roomier on ties.
+// Three register classes of the same code (64 / 40 / 32 registers per thread): take the one
+// that keeps the most threads resident for this shared-memory footprint, the roomier on ties.
+template <bool G>
+int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, cudaStream_t stream) {
   const int threads = 32 * sh.warps;
-  const int o64 = tiled_occupancy<1024, 1>(threads, smem);
-  const int o40 = tiled_occupancy<512, 3>(threads, smem);
-  const int o32 = tiled_occupancy<1024, 2>(threads, smem);
+  const int o64 = tiled_occupancy<1024, 1, G>(threads, smem);
+  const int o40 = tiled_occupancy<512, 3, G>(threads, smem);
+  const int o32 = tiled_occupancy<1024, 2, G>(threads, smem);
   int cls = 0, best = o64;
   if (o40 > best) { cls = 1; best = o40; }
   if (o32 > best) { cls = 2; best = o32; }
@@ -909,20 +944,58 @@ int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cud
     if (v == 2 && o32 > 0) { cls = 2; best = o32; }
   }
   if (best < 1) return -1;
-  if (cls == 2) return launch_tiled_variant<1024, 2>(p, threads, best, smem, n_sm, stream);
-  if (cls == 1) return launch_tiled_variant<512, 3>(p, threads, best, smem, n_sm, stream);
-  return launch_tiled_variant<1024, 1>(p, threads, best, smem, n_sm, stream);
+  long long grid = (long long)n_sm * best;
+  if (grid > p.n_units) grid = p.n_units;
+  if (G && grid > sh.max_ctas) grid = sh.max_ctas;
+  if (grid < 1) grid = 1;
+  if (cls == 2) return launch_tiled_variant<1024, 2, G>(p, threads, grid, smem, stream);
+  if (cls == 1) return launch_tiled_variant<512, 3, G>(p, threads, grid, smem, stream);
+  return launch_tiled_variant<1024, 1, G>(p, threads, grid, smem, stream);
 }
 
-int launch_column_consts(ColumnTables& tab, const TiledShape& sh, cudaStream_t stream) {
-  // the constant does not depend on the tied lists: only the pass-A buffers are needed
-  const int cap = sh.warps * sh.kk * 32;
-  const size_t smem = tiled_smem_bytes((2 * 2 * cap + 15) & ~15, (int)tab.wstride, fmask_words(sh.warps, sh.kk));
-  if (cudaFuncSetAttribute(column_const_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return -1;
-  column_const_kernel<<<(unsigned)tab.C, 32 * sh.warps, smem, stream>>>(
-      tab.perm, tab.rank, tab.stats, (int)tab.n, sh.kk, (int)tab.nstride, (int)tab.wstride);
+}  // namespace
+
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream) {
+  if (cudaMemsetAsync(pl.unit_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+  TiledParams p = make_params(pl);
+  p.kk = sh.kk;
+  p.scratch = pl.scratch;
+  p.scratch_stride = sh.region_bytes;
+  const int fw = fmask_words(sh.warps, sh.kk);
+  if (sh.gmem) {
+    if (!pl.scratch) return -2;
+    return launch_tiled_g<true>(p, sh, tiled_smem_bytes(0, p.wstride, fw), n_sm, stream);
+  }
+  return launch_tiled_g<false>(p, sh, tiled_smem_bytes(sh.region_bytes, p.wstride, fw), n_sm, stream);
+}
+
+int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream) {
+  // the constant does not depend on the tied lists nor on the launch shape: 32 warps per column
+  TiledShape cs = sh;
+  PairLaunch pl{};
+  pl.tab = &tab;
+  TiledParams p = make_params(pl);
+  const int nchunks = (int)((tab.n + 31) / 32);
+  const int W = 32;
+  p.kk = 2 * ((nchunks + 2 * W - 1) / (2 * W));
+  const int cap = W * p.kk * 32;
+  const int region = (2 * 2 * cap + 15) & ~15;
+  const int fw = fmask_words(W, p.kk);
+  const bool g = tiled_smem_bytes(region, p.wstride, fw) > 227 * 1024 || (sh.gmem && getenv("ICIKT_FORCE_GMEM"));
+  long long grid = tab.C;
+  if (g) {
+    if (!scratch || sh.region_bytes < region) return -2;  // the plan sizes the slot as max(region, const region)
+    p.scratch = scratch;
+    p.scratch_stride = sh.region_bytes;
+    grid = std::min<long long>(grid, cs.max_ctas);
+    const size_t smem = tiled_smem_bytes(0, p.wstride, fw);
+    if (cudaFuncSetAttribute(column_const_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    column_const_kernel<true><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)tab.C);
+  } else {
+    const size_t smem = tiled_smem_bytes(region, p.wstride, fw);
+    if (cudaFuncSetAttribute(column_const_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    column_const_kernel<false><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)tab.C);
+  }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -398,3 +398,61 @@ def test_target_shape_sample():
     x, persp = synth.make("target", C=120)
     got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
     _sampled_oracle_check(x, persp, got)
+
+
+# ---------------------------------------------------------------- long vectors (global-scratch variant)
+def test_snapshot_large_kendall(golden_dir):
+    """test-kendall-tau.R:72-78 + _snaps/kendall-tau.md:1-7: n = 50000, set.seed(1234)."""
+    snaps = json.load(open(os.path.join(golden_dir, "reference_snapshots.json")))["large_kendall"]
+    r = RRng(1234)
+    x, y = r.rnorm(50000), r.rnorm(50000)
+    v = ik.ici_kt(x, y, perspective="global")
+    assert round(v["tau"], 8) == snaps["tau"] and round(v["pvalue"], 8) == snaps["pvalue"]
+    assert v["tau_max"] == 1.0 and v["completeness"] == 1.0
+
+
+def test_big_kendall_matches_o_n2_reference():
+    """test-kendall-tau.R:80-89 (the reference's long test): n = 50000 with 5000 missing."""
+    rng = np.random.default_rng(50)
+    x = np.sort(rng.normal(size=50000))
+    y = x + 1
+    x[:5000] = np.nan
+    t1 = ik.ici_kt(x, y, perspective="global", continuity=True)
+    t2 = O.ici_kt_pairs(x, y, "global")
+    assert t1["tau"] == pytest.approx(t2[0], abs=1e-14)
+    assert t1["pvalue"] == pytest.approx(t2[1], rel=1e-8)
+
+
+@pytest.mark.parametrize("kind,n,C,na", [("normal", 40000, 3, 0.25), ("mixed", 50000, 4, 0.25),
+                                         ("heavy", 60000, 3, 0.4), ("normal", 65535, 3, 0.1),
+                                         ("ties", 65535, 2, 0.3)])
+def test_long_vectors(kind, n, C, na):
+    x = gen(n, C, kind, na, seed=n + C)
+    for persp in ("global", "local"):
+        got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+        assert_parity(got, oracle_pairs(x, perspective=persp), f"{kind} n={n} {persp}")
+
+
+def test_too_long_is_refused():
+    x = np.random.default_rng(0).normal(size=(65536, 2))
+    with pytest.raises(ik.IciktError) as e:
+        ik.run_pairs(x)
+    assert e.value.code == _lib.ERR_TOO_LONG
+
+
+@pytest.mark.parametrize("kind,n,C,na", [("mixed", 1000, 6, 0.25), ("heavy", 5000, 4, 0.3),
+                                         ("normal", 20000, 3, 0.25)])
+def test_forced_global_scratch_matches(kind, n, C, na, monkeypatch):
+    """The global-scratch code path on sizes where the shared-memory path is the default."""
+    x = gen(n, C, kind, na, seed=3 * n + C)
+    ref = oracle_pairs(x, perspective="local")
+    monkeypatch.setenv("ICIKT_FORCE_GMEM", "1")
+    got = ik.run_pairs(x, (), perspective="local", want_counts=True)
+    assert_parity(got, ref, f"forced gmem {kind} n={n}")
+
+
+def test_config4_shape_counts_with_heavy_ties():
+    """BASELINE config 4 shape (adenocarcinoma-like counts, n = 60000, zeros missing) on 8 samples."""
+    x, persp = synth.make("config4", C=8)
+    got = ik.run_pairs(x, (np.nan, np.inf, 0.0), perspective=persp, want_counts=True)
+    assert_parity(got, oracle_pairs(x, global_na=(np.nan, np.inf, 0.0), perspective=persp), "config4")
