@@ -377,11 +377,13 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm);
   const TiledShape worst = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
   const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
-  if (worst.gmem && !p->d_scratch) {
-    p->scratch_bytes = (size_t)worst.max_ctas * (size_t)slot_bytes;
+  const int slot_ctas = std::max(worst.max_ctas, p->n_sm * 2);
+  if ((worst.gmem || worst.const_gmem) && !p->d_scratch) {
+    p->scratch_bytes = (size_t)slot_ctas * (size_t)slot_bytes;
     CK(cudaMalloc(reinterpret_cast<void**>(&p->d_scratch), p->scratch_bytes));
   }
-  if (p->shape.gmem) p->shape.region_bytes = slot_bytes;
+  p->shape.scratch_stride = p->d_scratch ? slot_bytes : 0;
+  p->shape.scratch_ctas = p->d_scratch ? slot_ctas : 0;
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
                                p->d_scratch, p->stream);
   if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
@@ -391,10 +393,8 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   CK(cudaStreamSynchronize(p->stream));  // also: lit[] lives on this stack frame
   {
     TiledShape sh = tiled_shape(p->n, *p->h_max_tied, p->tab.wstride, p->n_sm);
-    if (sh.gmem) {  // scratch stride
-      const TiledShape worst = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
-      sh.region_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
-    }
+    sh.scratch_stride = p->d_scratch ? slot_bytes : 0;
+    sh.scratch_ctas = p->d_scratch ? slot_ctas : 0;
     p->shape = sh;
   }
   p->tm.n_launches = l;

@@ -46,7 +46,11 @@ struct TiledShape {
   int region_bytes = 0;  // ping-pong region per CTA
   int const_region_bytes = 0;  // pass-A buffers of the per-column constant kernel (32 warps)
   bool gmem = false;     // region lives in the global scratch (does not fit shared memory)
+  bool const_gmem = false;  // same for the per-column constant kernel
   int max_ctas = 0;      // CTAs the scratch must provide for
+  // filled in by the plan once the scratch exists: bytes per CTA slot and number of slots
+  int scratch_stride = 0;
+  int scratch_ctas = 0;
 };
 TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm);
 

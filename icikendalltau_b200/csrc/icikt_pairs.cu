@@ -29,6 +29,7 @@
 //   prefix sums), one cross-warp scan of W per-warp totals, and an in-place scatter in
 //   shared memory; two __syncthreads per level.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -77,6 +78,43 @@ struct Mem<false> {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p) : "memory");
     return v;
   }
+  static __device__ __forceinline__ void ld128(ptr p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(p) : "memory");
+  }
+  // position of p for the inversion accumulator: any value that differs from the byte offset
+  // inside the buffer by a per-level constant (here the shared-window address itself)
+  static __device__ __forceinline__ uint32_t off(ptr p, ptr) { return p; }
+  // one key of pass A's scatter sweep (two bits per level, see count_pass): Q01/Q23 hold the
+  // next free slot (element index, 16 bits each) of digit classes 0|1 and 2|3, S the number of
+  // keys seen so far whose high bit is set.  14 instructions per key.
+  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                               uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
+                                               uint32_t key, ptr base) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred ph, pl;\n\t"
+        ".reg .b32 t, qs, sel, idx, ad, inc, up;\n\t"
+        "and.b32 t, %5, %7;\n\t"
+        "setp.ne.u32 ph, t, 0;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 pl, t, 0;\n\t"
+        "selp.b32 qs, %1, %0, ph;\n\t"
+        "selp.b32 sel, 0x4432, 0x4410, pl;\n\t"
+        "prmt.b32 idx, qs, 0, sel;\n\t"
+        "mad.lo.u32 ad, idx, 2, %9;\n\t"
+        "st.shared.u16 [ad], %8;\n\t"
+        "selp.b32 inc, 0x10000, 1, pl;\n\t"
+        "shr.u32 up, qs, 16;\n\t"
+        "@ph add.u32 %1, %1, inc;\n\t"
+        "@!ph add.u32 %0, %0, inc;\n\t"
+        "@!ph add.u32 %3, %3, %2;\n\t"
+        "@ph add.u32 %2, %2, 1;\n\t"
+        "@!pl add.u32 %4, %4, up;\n\t"
+        "}"
+        : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base)
+        : "memory");
+  }
   static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(p), "h"((unsigned short)v) : "memory");
   }
@@ -93,6 +131,23 @@ struct Mem<true> {
   static __device__ __forceinline__ ptr add(ptr p, int32_t bytes) { return p + bytes; }
   static __device__ __forceinline__ uint32_t ld16(ptr p) { return *reinterpret_cast<const unsigned short*>(p); }
   static __device__ __forceinline__ uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t*>(p); }
+  static __device__ __forceinline__ void ld128(ptr p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    a = v.x; b = v.y; c = v.z; d = v.w;
+  }
+  static __device__ __forceinline__ uint32_t off(ptr p, ptr base) { return (uint32_t)(p - base); }
+  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                               uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
+                                               uint32_t key, ptr base) {
+    const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
+    const uint32_t qs = ph ? Q23 : Q01;
+    const uint32_t idx = pl ? (qs >> 16) : (qs & 0xffffu);
+    *reinterpret_cast<unsigned short*>(base + 2 * (size_t)idx) = (unsigned short)key;
+    const uint32_t inc = pl ? 0x10000u : 1u;
+    if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
+    if (ph) S += 1;
+    if (!pl) acc2 += qs >> 16;
+  }
   static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
     *reinterpret_cast<unsigned short*>(p) = (unsigned short)v;
   }
@@ -214,65 +269,94 @@ __device__ __forceinline__ void bucket_pass(typename Mem<G>::ptr a, typename Mem
   }
 }
 
-// Pass A: the bucket-free counting pass on 16-bit keys (see the file header).  Every lane
-// handles TWO adjacent keys per step (one 32-bit load), so a warp covers 64 keys with one
-// load and two ballots.  Per level two sweeps over the warp's kk/2 double chunks: sweep 1
-// counts the ones of the segment (ballot + popc on the uniform datapath), the W totals are
-// scanned by every warp, sweep 2 scatters every key to its slot of the other buffer and adds,
-// for every zero-bit key, the number of ones before it.  Everything is kept in byte offsets
-// (doubled counts) so that a slot address is one add.  kk must be even.
-//   acc2  += 2 * sum over my zero-bit keys of (ones before them inside my warp segment)
-//   fix64 += the part of the count that is uniform per warp: zeros_in_segment * ones_before_segment
+// Pass A: the bucket-free counting pass on 16-bit keys (see the file header), lane-sequential,
+// TWO bits per level.  Thread t of the CTA owns the contiguous range [t*R, (t+1)*R) of the
+// sequence, R = 8*kk keys, and walks it with 128-bit loads (kk must be ODD: the 16-byte accesses
+// of a quarter warp then fall into distinct bank groups).  A level on bits (s+1, s) is the fusion
+// of the two one-bit levels s+1 and s: a stable partition of the whole sequence into the digit
+// classes 0,1,2,3 (digit = 2*hi + lo), and the count
+//     sum over keys with hi = 0 of #(hi = 1 keys before it)                        [bit s+1]
+//   + sum over keys with lo = 0 of #(lo = 1 keys before it after the hi partition)  [bit s]
+// where the second term is, for a key of class 0, the class-1 keys before it, and for a key of
+// class 2 all N1 class-1 keys plus the class-3 keys before it.  Per level:
+//   sweep 1  counts the range's keys per class, two keys per 32-bit word at once
+//            ((w >> s) & 0x00010001 summed in two 16-bit fields);
+//   two packed warp scans + warp-total reductions give the class counts before the range;
+//   sweep 2  walks the range with four running slot indices (packed 2 x 16 bit in Q01, Q23),
+//            stores every key to its slot of the other buffer and accumulates the count.
+// No ballots, no per-key population counts: about 16 instructions per key and level of two bits.
+// With an odd number of bits the first level treats the missing top bit as zero.
+//   acc64 += the count over all levels (this thread's share)
 template <bool G>
 __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
-                                           const int nwarps, const int L, uint32_t* descT,
-                                           const int lane, const int warp, uint32_t& acc2,
-                                           unsigned long long& fix64) {
+                                           const int nwarps, const int L, uint32_t* descA, uint32_t* descB,
+                                           const int lane, const int warp, unsigned long long& acc64) {
   typedef Mem<G> M;
-  const uint32_t my_off = ((uint32_t)(warp * kk) << 6) + ((uint32_t)lane << 2);
-  const uint32_t total_len = (uint32_t)(nwarps * kk) << 5;
-  const uint32_t lt = lanemask_lt();
-  const int kk2 = kk >> 1;
-  for (int s = L - 1; s >= 0; --s) {
-    uint32_t maskL = 1u << s, maskH = 1u << (s + 16);
-    asm volatile("" : "+r"(maskL), "+r"(maskH));  // keep the bit tests single LOP3s with predicate output
+  const uint32_t tid = ((uint32_t)warp << 5) + (uint32_t)lane;
+  const uint32_t R = (uint32_t)kk << 3;                // keys per thread range
+  const uint32_t my_off = tid * (R << 1);              // bytes
+  const uint32_t my_pos = tid * R;
+  const uint32_t cap = ((uint32_t)nwarps << 5) * R;    // keys per buffer
+  for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
     const typename M::ptr ra = M::add(a, (int32_t)my_off);
-    uint32_t T = 0;
-#pragma unroll 4
-    for (int c = 0; c < kk2; ++c) {
-      const uint32_t w = M::ld32(M::add(ra, c << 7));
-      T += __popc(__ballot_sync(FULL, (w & maskL) != 0u)) + __popc(__ballot_sync(FULL, (w & maskH) != 0u));
+    uint32_t cl = 0, ch = 0, cb = 0;
+#pragma unroll 1
+    for (int c = 0; c < kk; ++c) {
+      uint32_t w[4];
+      M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = (w[j] >> s) & 0x00010001u, hi = (w[j] >> (s + 1)) & 0x00010001u;
+        cl += lo;
+        ch += hi;
+        cb += lo & hi;
+      }
     }
-    if (lane == 0) descT[warp] = T;
-    __syncthreads();
-    const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
-    uint32_t incl = v;
+    const uint32_t n3 = (cb & 0xffffu) + (cb >> 16);
+    const uint32_t n2 = (ch & 0xffffu) + (ch >> 16) - n3;
+    const uint32_t n1 = (cl & 0xffffu) + (cl >> 16) - n3;
+    const uint32_t A = n1 | (n2 << 16), B = n3;
+    uint32_t inclA = A, inclB = B;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl += t;
+      const uint32_t tA = __shfl_up_sync(FULL, inclA, d), tB = __shfl_up_sync(FULL, inclB, d);
+      if (lane >= d) {
+        inclA += tA;
+        inclB += tB;
+      }
     }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    const uint32_t Gp = __shfl_sync(FULL, incl - v, warp);  // ones before my segment
-    if (lane == 0) fix64 += (unsigned long long)Gp * (((uint32_t)kk << 5) - T);
-    // slot of the first one of my segment / my low key's slot if no one preceded it
-    const typename M::ptr one_base = M::add(b, (int32_t)(2u * (total_len - total) + 2u * Gp));
-    const typename M::ptr zero_base = M::add(b, (int32_t)(my_off - 2u * Gp));
-    uint32_t Tu2 = 0;  // 2 * ones seen so far in my segment (uniform across the warp)
-#pragma unroll 4
-    for (int c = 0; c < kk2; ++c) {
-      const uint32_t w = M::ld32(M::add(ra, c << 7));
-      const bool oneL = (w & maskL) != 0u, oneH = (w & maskH) != 0u;
-      const uint32_t mL = __ballot_sync(FULL, oneL), mH = __ballot_sync(FULL, oneH);
-      const uint32_t tL = Tu2 + 2u * (uint32_t)(__popc(mL & lt) + __popc(mH & lt));
-      const uint32_t tH = tL + (oneL ? 2u : 0u);
-      const int32_t zb = c << 7;
-      M::st16(oneL ? M::add(one_base, (int32_t)tL) : M::add(zero_base, zb - (int32_t)tL), w & 0xffffu);
-      M::st16(oneH ? M::add(one_base, (int32_t)tH) : M::add(zero_base, zb + 2 - (int32_t)tH), w >> 16);
-      acc2 += (oneL ? 0u : tL) + (oneH ? 0u : tH);
-      Tu2 += 2u * (uint32_t)(__popc(mL) + __popc(mH));
+    if (lane == 31) {
+      descA[warp] = inclA;
+      descB[warp] = inclB;
     }
-    __syncthreads();  // also protects descT for the next level
+    __syncthreads();
+    const uint32_t vA = (lane < nwarps) ? descA[lane] : 0u, vB = (lane < nwarps) ? descB[lane] : 0u;
+    const uint32_t totA = __reduce_add_sync(FULL, vA), totB = __reduce_add_sync(FULL, vB);
+    const uint32_t exA = __reduce_add_sync(FULL, (lane < warp) ? vA : 0u) + inclA - A;
+    const uint32_t exB = __reduce_add_sync(FULL, (lane < warp) ? vB : 0u) + inclB - B;
+    const uint32_t e1 = exA & 0xffffu, e2 = exA >> 16, e3 = exB;           // class counts before my range
+    const uint32_t N1 = totA & 0xffffu, N2 = totA >> 16, N3 = totB;
+    const uint32_t N0 = cap - N1 - N2 - N3;
+    uint32_t Q01 = ((N0 + e1) << 16) | (my_pos - e1 - e2 - e3);
+    uint32_t Q23 = ((N0 + N1 + N2 + e3) << 16) | (N0 + N1 + e2);
+    uint32_t S = e2 + e3, acc = 0, acc2 = 0;
+    uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
+    asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));  // keep the bit tests single LOP3s
+#pragma unroll 1
+    for (int c = 0; c < kk; ++c) {
+      uint32_t w[4];
+      M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        M::step4(Q01, Q23, S, acc, acc2, w[j], bLl, bHl, w[j], b);
+        M::step4(Q01, Q23, S, acc, acc2, w[j], bLh, bHh, w[j] >> 16, b);
+      }
+    }
+    // acc2 summed absolute slot indices: take out the class bases (class 1 starts at N0, class 3
+    // at N0+N1+N2) and add the N1 class-1 keys that precede every class-2 key after the hi partition
+    const uint32_t n0 = R - n1 - n2 - n3;
+    acc64 += (unsigned long long)(acc + acc2 - n0 * N0 - n2 * (N0 + N2));
+    __syncthreads();  // also protects descA/descB for the next level
     const typename M::ptr t = a;
     a = b;
     b = t;
@@ -364,7 +448,7 @@ struct TiledParams {
   long long scratch_stride;      // bytes per CTA
   long long n_units;
   int n, n32, nstride, wstride;
-  int kk;  // chunks per warp for the full sequence (even)
+  int kk;  // pass A: 8-key runs per thread (odd); a warp covers 8*kk 32-element chunks
 };
 
 // Shared-memory layout of one CTA (all offsets multiples of 16 bytes)
@@ -424,9 +508,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   const int T = blockDim.x, nwarps = T >> 5;
   const int n = p.n;
   const int nwords = p.n32 >> 5;
-  const int kk = p.kk;
-  const int cap = (nwarps * kk) << 5;
-  Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk));
+  const int kk = p.kk;       // 8-key runs per thread in pass A
+  const int kkc = kk << 3;   // 32-element chunks per warp
+  const int cap = (nwarps * kkc) << 5;
+  Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kkc));
   const typename M::ptr bufA = region_base<G>(sm, p), bufB16 = M::add(bufA, 2 * cap);
   // tie counters: second half of the region while it is otherwise unused
   uint32_t* const cnt = G ? reinterpret_cast<uint32_t*>(p.scratch + (size_t)blockIdx.x * (size_t)p.scratch_stride + 2 * (size_t)cap)
@@ -544,11 +629,11 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
           }
         }
       }
-      if (f > 0) emit_first_group<G>(bufA, n, kk, nwarps, permY_g, rank_tbl, sm.fbX, sm.fmask, sm.descT, lane, warp);
+      if (f > 0) emit_first_group<G>(bufA, n, kkc, nwarps, permY_g, rank_tbl, sm.fbX, sm.fmask, sm.descT, lane, warp);
       __syncthreads();
-      uint32_t acc2 = 0, accB = 0;
-      unsigned long long fix64 = 0;
-      count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, lane, warp, acc2, fix64);
+      uint32_t accB = 0;
+      unsigned long long accA = 0;
+      count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, accA);
       const int m = XS.n_tied;
       if (m > 0) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
@@ -562,7 +647,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         bucket_pass<G>(bufA, M::add(bufA, capB << 2), kkB, nwarps, m, L, sm.descT, sm.descB, lane, warp, accB,
                        ties);
       }
-      const unsigned long long sA = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64),
+      const unsigned long long sA = warp_sum_u64(accA),
                                sB = warp_sum_u64(accB),
                                sT = warp_sum_u64(((unsigned long long)g11part << 32) | ties),
                                sb = warp_sum_u64(((unsigned long long)g00part << 32) | bpart);
@@ -604,8 +689,8 @@ __global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
   const int n = p.n, kk = p.kk;
-  const int cap = (nwarps * kk) << 5;
-  Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk));
+  const int cap = (nwarps * kk) << 8;
+  Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk << 3));
   const typename M::ptr bufA = region_base<G>(sm, p), bufB = M::add(bufA, 2 * cap);
   for (int col = blockIdx.x; col < C; col += gridDim.x) {
     const ColStats CS = stats[col];
@@ -618,10 +703,9 @@ __global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams
     const uint32_t padA = (1u << CS.levels) - 1u;
     for (int q = tid; q < cap; q += T) M::st16(M::add(bufA, q << 1), (q < n) ? (uint32_t)rk[pm[q]] : padA);
     __syncthreads();
-    uint32_t acc2 = 0;
-    unsigned long long fix64 = 0;
-    count_pass<G>(bufA, bufB, kk, nwarps, CS.levels, sm.descT, lane, warp, acc2, fix64);
-    const unsigned long long s = warp_sum_u64((unsigned long long)(acc2 >> 1) + fix64);
+    unsigned long long accA = 0;
+    count_pass<G>(bufA, bufB, kk, nwarps, CS.levels, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, accA);
+    const unsigned long long s = warp_sum_u64(accA);
     if (lane == 0) sm.red[warp] = s;
     __syncthreads();
     if (tid == 0) {
@@ -874,30 +958,73 @@ int measure_smem_bandwidth(double* gbps32, double* gbps128) {
   return 0;
 }
 
-// Launch shape for vectors of length n: warps per CTA, chunks per warp, bytes of the ping-pong
-// region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied list), and
-// whether the region fits shared memory or has to live in the global scratch.
+// 8-key runs per thread such that W warps cover n keys: the smallest odd count (bank-conflict-free
+// 128-bit loads), unless that pushes the padded length past the 65536 slots the packed 16-bit
+// slot indices of pass A can address; then the smallest count, or 0 if W cannot cover n at all.
+static int odd_runs(int64_t n, int W) {
+  int kk = (int)((n + 256LL * W - 1) / (256LL * W));
+  if (kk < 1) kk = 1;
+  if (256LL * W * (kk | 1) <= 65536) return kk | 1;
+  return 256LL * W * kk <= 65536 ? kk : 0;
+}
+
+// warps per CTA of the per-column constant kernel: 16..32, least padding (the constant does not
+// depend on the launch shape)
+static int const_warps(int64_t n) {
+  int W = 32;
+  long long best = -1;
+  for (int w = 32; w >= 16; --w) {
+    const long long cap = 256LL * w * odd_runs(n, w);
+    if (cap > 0 && (best < 0 || cap < best)) { best = cap; W = w; }
+  }
+  return W;
+}
+
+// Launch shape for vectors of length n: warps per CTA, 8-key runs per thread (odd), bytes of the
+// ping-pong region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied
+// list), and whether the region fits shared memory or has to live in the global scratch.
 TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm) {
   TiledShape sh;
-  const int nchunks = (int)((n + 31) / 32);
-  int W = n <= 3072 ? 2 : n <= 8192 ? 4 : n <= 12288 ? 8 : n <= 24576 ? 16 : 32;  // tuned on B200, see profiles/
+  const int mchunks = (int)((max_tied + 31) / 32);
+  auto region_of = [&](int w) {
+    const int cap = w * odd_runs(n, w) * 256;
+    const int capB = w * ((mchunks + w - 1) / w) * 32;
+    return (std::max(2 * 2 * cap, 2 * 4 * capB) + 15) & ~15;
+  };
+  auto smem_of = [&](int w) {
+    return tiled_smem_bytes(region_of(w), (int)wstride, fmask_words(w, odd_runs(n, w) << 3));
+  };
+  // W: padded length (odd run count) x per-level fixed cost (two barriers and two scans cost
+  // about two runs per thread) x a latency-hiding factor for fewer than 32 resident warps per
+  // SM.  Fitted to the B200 sweeps in profiles/.  Shapes that do not fit shared memory run 32
+  // warps on the global scratch.
+  int W = 32;
+  double best = 1e300;
+  for (int w = 1; w <= 32; ++w) {
+    const int kk = odd_runs(n, w);
+    if (kk == 0) continue;
+    const size_t smem = smem_of(w);
+    if (smem > 227 * 1024) continue;
+    const int ctas = (int)std::min<size_t>(std::min(32, 2048 / (32 * w)), (228 * 1024) / (smem + 1024));
+    const double rw = std::min(32.0, (double)w * std::max(1, ctas));
+    const double cost = 256.0 * w * kk * (1.0 + 2.0 / kk) * std::pow(32.0 / rw, 0.4);
+    if (cost < best) { best = cost; W = w; }
+  }
   if (const char* e = getenv("ICIKT_WARPS")) {
     const int v = atoi(e);
-    if (v >= 1 && v <= 32) W = v;
+    if (v >= 1 && v <= 32 && odd_runs(n, v) > 0) W = v;
   }
+  if (getenv("ICIKT_FORCE_GMEM")) W = 32;
   sh.warps = W;
-  sh.kk = 2 * ((nchunks + 2 * W - 1) / (2 * W));  // even: the kernels handle two chunks per step
-  const int cap = W * sh.kk * 32;
-  const int mchunks = (int)((max_tied + 31) / 32);
-  const int kkB = (mchunks + W - 1) / W;
-  const int capB = W * kkB * 32;
-  sh.region_bytes = (std::max(2 * 2 * cap, 2 * 4 * capB) + 15) & ~15;
-  {  // the per-column constant kernel always runs 32 warps: its pass-A buffers must fit a scratch slot too
-    const int kk32 = 2 * ((nchunks + 63) / 64);
-    sh.const_region_bytes = (2 * 2 * (32 * kk32 * 32) + 15) & ~15;
+  sh.kk = odd_runs(n, W);
+  sh.region_bytes = region_of(W);
+  {  // the per-column constant kernel has its own shape: its pass-A buffers must fit a scratch slot too
+    const int Wc = const_warps(n);
+    sh.const_region_bytes = (2 * 2 * (Wc * odd_runs(n, Wc) * 256) + 15) & ~15;
+    sh.const_gmem = tiled_smem_bytes(sh.const_region_bytes, (int)wstride, fmask_words(Wc, odd_runs(n, Wc) << 3)) > 227 * 1024 ||
+                    getenv("ICIKT_FORCE_GMEM") != nullptr;
   }
-  const size_t smem = tiled_smem_bytes(sh.region_bytes, (int)wstride, fmask_words(W, sh.kk));
-  sh.gmem = smem > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr;
+  sh.gmem = smem_of(W) > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr;
   sh.max_ctas = n_sm * std::max(1, 2048 / (32 * W));
   return sh;
 }
@@ -946,7 +1073,7 @@ int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, 
   if (best < 1) return -1;
   long long grid = (long long)n_sm * best;
   if (grid > p.n_units) grid = p.n_units;
-  if (G && grid > sh.max_ctas) grid = sh.max_ctas;
+  if (G && grid > sh.scratch_ctas) grid = sh.scratch_ctas;
   if (grid < 1) grid = 1;
   if (cls == 2) return launch_tiled_variant<1024, 2, G>(p, threads, grid, smem, stream);
   if (cls == 1) return launch_tiled_variant<512, 3, G>(p, threads, grid, smem, stream);
@@ -960,34 +1087,31 @@ int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cud
   TiledParams p = make_params(pl);
   p.kk = sh.kk;
   p.scratch = pl.scratch;
-  p.scratch_stride = sh.region_bytes;
-  const int fw = fmask_words(sh.warps, sh.kk);
+  p.scratch_stride = sh.scratch_stride;
+  const int fw = fmask_words(sh.warps, sh.kk << 3);
   if (sh.gmem) {
-    if (!pl.scratch) return -2;
+    if (!pl.scratch || sh.region_bytes > sh.scratch_stride) return -2;
     return launch_tiled_g<true>(p, sh, tiled_smem_bytes(0, p.wstride, fw), n_sm, stream);
   }
   return launch_tiled_g<false>(p, sh, tiled_smem_bytes(sh.region_bytes, p.wstride, fw), n_sm, stream);
 }
 
 int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream) {
-  // the constant does not depend on the tied lists nor on the launch shape: 32 warps per column
-  TiledShape cs = sh;
   PairLaunch pl{};
   pl.tab = &tab;
   TiledParams p = make_params(pl);
-  const int nchunks = (int)((tab.n + 31) / 32);
-  const int W = 32;
-  p.kk = 2 * ((nchunks + 2 * W - 1) / (2 * W));
-  const int cap = W * p.kk * 32;
+  const int W = const_warps(tab.n);
+  p.kk = odd_runs(tab.n, W);
+  const int cap = W * p.kk * 256;
   const int region = (2 * 2 * cap + 15) & ~15;
-  const int fw = fmask_words(W, p.kk);
-  const bool g = tiled_smem_bytes(region, p.wstride, fw) > 227 * 1024 || (sh.gmem && getenv("ICIKT_FORCE_GMEM"));
+  const int fw = fmask_words(W, p.kk << 3);
+  const bool g = tiled_smem_bytes(region, p.wstride, fw) > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr;
   long long grid = tab.C;
   if (g) {
-    if (!scratch || sh.region_bytes < region) return -2;  // the plan sizes the slot as max(region, const region)
+    if (!scratch || sh.scratch_stride < region) return -2;  // the plan sizes the slot as max(region, const region)
     p.scratch = scratch;
-    p.scratch_stride = sh.region_bytes;
-    grid = std::min<long long>(grid, cs.max_ctas);
+    p.scratch_stride = sh.scratch_stride;
+    grid = std::min<long long>(grid, sh.scratch_ctas);
     const size_t smem = tiled_smem_bytes(0, p.wstride, fw);
     if (cudaFuncSetAttribute(column_const_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     column_const_kernel<true><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)tab.C);

@@ -11,6 +11,7 @@ for l in sys.stdin:
 ")
   echo "$1 W=$2 R=$3 $r" | tee -a $out
 }
-for W in 2 4 8 16; do for R in 0 2; do run config2 $W $R; done; done
-for W in 1 2 4; do for R in 0 2; do run config5 $W $R; done; done
-run target 16 0; run target 16 1; run target 32 0; run target 32 2; run target 8 0; run target 8 2
+for W in "" 2 3 4 5 7; do run config2 "$W" ""; done
+for W in "" 1 2 3; do run config5 "$W" ""; done
+for W in "" 9 12 16 27; do run target "$W" ""; done
+run target 16 0; run target 16 1; run target 16 2
