@@ -291,6 +291,11 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.grpstart, nw));
   PCK(dmalloc(&t.stats, (size_t)C));
   PCK(dmalloc(&t.max_tied, 1));
+  // padding words of the bit arrays (beyond n32/32) are never written by the kernels
+  PCK(cudaMemsetAsync(t.nabits, 0, sizeof(uint32_t) * nw, p->stream));
+  PCK(cudaMemsetAsync(t.firstbits, 0, sizeof(uint32_t) * nw, p->stream));
+  PCK(cudaMemsetAsync(t.grpstart, 0, sizeof(uint32_t) * nw, p->stream));
+  PCK(cudaMemsetAsync(t.max_tied, 0, sizeof(int32_t), p->stream));
   PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_max_tied), sizeof(int32_t)));
   p->shape = tiled_shape(n, 0, t.wstride, p->n_sm);
   PCK(dmalloc(&p->wk.keys_in, ne));

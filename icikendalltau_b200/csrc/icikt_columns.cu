@@ -11,7 +11,11 @@
 //   column_rank_kernel  compare_self + cumsum (:15-31, :250-251) -> dense ranks; tie-group
 //                       sizes -> count_rank_tie sums (:103-118) in exact int64; the bit masks
 //                       and the tied-row list (rows + dense group index) the pair kernel needs.
+#include <cub/block/block_merge_sort.cuh>
 #include <cub/device/device_segmented_sort.cuh>
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "icikt_internal.h"
 
@@ -84,6 +88,193 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* buf) {
   for (int w = 0; w < RANK_THREADS / 32; ++w) t += buf[w];
   __syncthreads();
   return t;
+}
+
+// Short columns (n <= 8192): the WHOLE per-column preprocessing in one kernel, one CTA per
+// column, every sorted position held in registers (thread t owns positions t*ITEMS ..).
+//   missing marking + order-preserving keys   (build_keys_kernel)
+//   sort                                      (cub::BlockMergeSort in shared memory)
+//   dense ranks, tie sums, first-group mask, tied-row list, statistics   (column_rank_kernel)
+// Replaces six launches (~150 us for 100 columns of 5 000 rows, two thirds of it in
+// cub::DeviceSegmentedSort) where the per-column work is a visible share of the whole job.
+// Each phase is one pass over the registers plus one block scan.
+constexpr int SORT_THREADS = RANK_THREADS;
+struct KeyLess {
+  __device__ __forceinline__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
+};
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS)
+    column_fused_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
+                        const double* __restrict__ global_na, int n_global_na, int na_inf,
+                        uint16_t* __restrict__ perm, uint16_t* __restrict__ rank, uint16_t* __restrict__ trow,
+                        uint16_t* __restrict__ trun, uint32_t* __restrict__ nabits,
+                        uint32_t* __restrict__ firstbits, ColStats* __restrict__ stats,
+                        int32_t* __restrict__ max_tied) {
+  using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
+  constexpr int CAP = SORT_THREADS * ITEMS;
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  __shared__ int warp_sums[32];
+  __shared__ long long llbuf[32];
+  __shared__ unsigned long long mnkey;
+  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
+  const int col = blockIdx.x, tid = threadIdx.x;
+  unsigned long long keys[ITEMS];
+  uint16_t vals[ITEMS];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {  // striped: a warp reads 32 consecutive rows
+    const int r = i * SORT_THREADS + tid;
+    bool miss = false;
+    unsigned long long k = ~0ull;  // padding sorts last; no value maps to all-ones (NaN is missing)
+    if (r < n) {
+      const double v = data[(size_t)col * ld + r];
+      miss = (v != v) || (na_inf && isinf(v));
+      for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
+      k = miss ? 0ull : order_key(v);
+    }
+    keys[i] = k;
+    vals[i] = (uint16_t)r;
+    const uint32_t m = __ballot_sync(FULL, miss);
+    if ((tid & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
+  }
+  Sort(temp).Sort(keys, vals, KeyLess());
+  __syncthreads();  // the sort's shared memory is reused below
+  unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(sort_smem);           // [SORT_THREADS]
+  uint16_t* gpos = reinterpret_cast<uint16_t*>(sort_smem + 8 * SORT_THREADS);                // [CAP + 2]
+  uint32_t* bits = reinterpret_cast<uint32_t*>(sort_smem + 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15));  // [CAP/32]
+  const int base = tid * ITEMS;  // blocked arrangement after the sort
+  uint16_t* pm = perm + (size_t)col * nstride;
+  uint16_t* rk = rank + (size_t)col * nstride;
+  const int nwords = (n + 31) >> 5;
+
+  int a_loc = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    if (base + i < n) pm[base + i] = vals[i];
+    a_loc += (keys[i] == 0ull);
+  }
+  lastkey[tid] = keys[ITEMS - 1];
+  int a;
+  block_scan_excl(a_loc, warp_sums, a);  // missing rows sort first (key 0)
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i)
+    if (base + i == a) mnkey = keys[i];
+  for (int w = tid; w < nwords; w += SORT_THREADS) bits[w] = 0;
+  __syncthreads();
+  // NA substitute = min - 0.1 (src/kendallc.cpp:214-219); if that does not move the minimum in
+  // fp64 the missing rows tie with it
+  bool absorb = false;
+  if (a > 0 && a < n) {
+    const double mn = key_value(mnkey);
+    absorb = (__dsub_rn(mn, 0.1) == mn);
+  }
+  // group starts (compare_self, :15-31) and dense ranks
+  unsigned long long prev = tid > 0 ? lastkey[tid - 1] : 0ull;
+  uint32_t fmask = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const int t = base + i;
+    const bool f = t < n && (t == 0 || (keys[i] != prev && !(t == a && absorb)));
+    prev = keys[i];
+    fmask |= (uint32_t)f << i;
+  }
+  int K;
+  const int excl = block_scan_excl(__popc(fmask), warp_sums, K);
+  {
+    int r = excl - 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int t = base + i;
+      if ((fmask >> i) & 1u) gpos[++r] = (uint16_t)t;
+      if (t < n) rk[vals[i]] = (uint16_t)r;
+    }
+  }
+  if (tid == 0) gpos[K] = (uint16_t)n;  // n <= 8192 here
+  __syncthreads();
+  // tie sums over group sizes (count_rank_tie, :103-118), exact int64
+  long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
+  for (int g = tid; g < K; g += SORT_THREADS) {
+    const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
+    if (g == 0 && a > 0) continue;  // the NA group is kept apart for the local perspective
+    s2 += t * (t - 1);
+    s3 += t * (t - 1) * (t - 2);
+    s5 += t * (t - 1) * (2 * t + 5);
+    if (g > 0 && t > 1) ntied += t;
+  }
+  s2 = block_sum_ll(s2, llbuf);
+  s3 = block_sum_ll(s3, llbuf);
+  s5 = block_sum_ll(s5, llbuf);
+  ntied = block_sum_ll(ntied, llbuf);
+  const int g0size = (K > 0) ? (int)gpos[1] : 0;
+  const int first_run = g0size > 1 ? g0size : 0;
+  // membership mask of the first group; rows of the other tied groups with their dense group index
+  uint32_t tmask = 0, gmask = 0;
+  {
+    int r = excl - 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int t = base + i;
+      if ((fmask >> i) & 1u) ++r;
+      if (t < first_run) atomicOr(&bits[vals[i] >> 5], 1u << (vals[i] & 31));
+      if (t < n && t >= g0size) {
+        const bool tied = ((int)gpos[r + 1] - (int)gpos[r]) > 1;
+        tmask |= (uint32_t)tied << i;
+        gmask |= (uint32_t)(tied && (int)gpos[r] == t) << i;
+      }
+    }
+  }
+  int tot2;
+  const int excl2 = block_scan_excl(__popc(tmask) | (__popc(gmask) << 16), warp_sums, tot2);
+  {
+    int pos = excl2 & 0xffff, gcount = excl2 >> 16;
+    uint16_t* tr = trow + (size_t)col * nstride;
+    uint16_t* tg = trun + (size_t)col * nstride;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      if ((gmask >> i) & 1u) ++gcount;
+      if ((tmask >> i) & 1u) {
+        tr[pos] = vals[i];
+        tg[pos] = (uint16_t)(gcount - 1);
+        ++pos;
+      }
+    }
+  }
+  __syncthreads();  // bits complete
+  for (int w = tid; w < nwords; w += SORT_THREADS) firstbits[(size_t)col * wstride + w] = bits[w];
+  if (tid == 0) {
+    ColStats s;
+    s.n_na = a;
+    s.first_run = first_run;
+    s.n_tied = (int)ntied;
+    s.n_groups = K;
+    int L = 1;
+    while ((1 << L) < K) ++L;
+    s.levels = L;
+    s.g0extra = (a > 0) ? g0size - a : 0;
+    s.flags = absorb ? 1 : 0;
+    s.n_tgroups = tot2 >> 16;
+    s.s2o = s2;
+    s.s3o = s3;
+    s.s5o = s5;
+    s.cconst = 0;
+    stats[col] = s;
+    atomicMax(max_tied, (int)ntied);
+  }
+}
+
+template <int ITEMS>
+int launch_column_fused(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na, int na_inf,
+                        ColumnTables& tab, cudaStream_t stream) {
+  using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
+  constexpr int CAP = SORT_THREADS * ITEMS;
+  const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * (CAP / 32);
+  const size_t smem = std::max(sizeof(typename Sort::TempStorage), post);
+  auto kern = column_fused_kernel<ITEMS>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
+                                                        d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
+                                                        tab.trow, tab.trun, tab.nabits, tab.firstbits, tab.stats,
+                                                        tab.max_tied);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 __global__ void __launch_bounds__(RANK_THREADS)
@@ -238,11 +429,22 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   const int n = (int)tab.n, C = (int)tab.C;
   const int nstride = (int)tab.nstride, wstride = (int)tab.wstride;
   int launches = 0;
-  if (cudaMemsetAsync(tab.nabits, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
-  if (cudaMemsetAsync(tab.grpstart, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
-  if (cudaMemsetAsync(tab.firstbits, 0, sizeof(uint32_t) * (size_t)wstride * C, stream) != cudaSuccess) return -1;
+  // the bit arrays are written in full (words below n32/32) by the kernels below; the padding
+  // words up to wstride were zeroed once when the plan was created
+  const int items = (n + SORT_THREADS - 1) / SORT_THREADS;
   if (cudaMemsetAsync(tab.max_tied, 0, sizeof(int32_t), stream) != cudaSuccess) return -1;
-  {
+  if (items <= 16 && !getenv("ICIKT_NO_FUSED_COLUMNS")) {
+    int l;
+    if (items <= 2) l = launch_column_fused<2>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    else if (items <= 4) l = launch_column_fused<4>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    else if (items <= 6) l = launch_column_fused<6>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    else if (items <= 8) l = launch_column_fused<8>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    else if (items <= 10) l = launch_column_fused<10>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    else if (items <= 12) l = launch_column_fused<12>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    else l = launch_column_fused<16>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+    if (l < 0) return -1;
+    launches += l;
+  } else {
     seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, C, nstride, n);
     ++launches;
     const int n32 = (n + 31) & ~31;
@@ -251,20 +453,20 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
                                                 na_inf, wk.keys_in, wk.vals_in, tab.nabits);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
+    size_t bytes = wk.cub_bytes;
+    if (cub::DeviceSegmentedSort::SortPairs(wk.cub_temp, bytes, (const unsigned long long*)wk.keys_in,
+                                            wk.keys_out, (const uint16_t*)wk.vals_in, tab.perm,
+                                            (long long)nstride * C, (long long)C,
+                                            (const long long*)wk.seg_begin, (const long long*)wk.seg_end,
+                                            stream) != cudaSuccess)
+      return -1;
+    launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
+    column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
+                                                       tab.trow, tab.trun, tab.firstbits, tab.grpstart,
+                                                       wk.gpos, tab.stats, tab.max_tied);
+    ++launches;
+    if (cudaGetLastError() != cudaSuccess) return -1;
   }
-  size_t bytes = wk.cub_bytes;
-  if (cub::DeviceSegmentedSort::SortPairs(wk.cub_temp, bytes, (const unsigned long long*)wk.keys_in,
-                                          wk.keys_out, (const uint16_t*)wk.vals_in, tab.perm,
-                                          (long long)nstride * C, (long long)C,
-                                          (const long long*)wk.seg_begin, (const long long*)wk.seg_end,
-                                          stream) != cudaSuccess)
-    return -1;
-  launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
-  column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
-                                                     tab.trow, tab.trun, tab.firstbits, tab.grpstart,
-                                                     wk.gpos, tab.stats, tab.max_tied);
-  ++launches;
-  if (cudaGetLastError() != cudaSuccess) return -1;
   const int cl = launch_column_consts(tab, sh, scratch, stream);
   if (cl < 0) return -1;
   return launches + cl;
