@@ -59,8 +59,11 @@ struct icikt_plan {
   ColumnTables tab;
   ColumnWork wk;
   bool columns_done = false;
-  TiledShape shape;            // launch shape of the tiled kernels
-  int32_t* h_max_tied = nullptr;  // pinned
+  // launch shapes of the pair kernel: `shape` for columns whose tied-row lists fit beside the
+  // pass-A buffers (the common case), `shape_heavy` for anything up to every row tied.  Both are
+  // enqueued; the device-side max over the columns picks the one that runs (no host round trip).
+  TiledShape shape, shape_heavy;
+  int tied_split = 0x7fffffff;  // max_tied <= tied_split runs `shape`
   unsigned char* d_scratch = nullptr;  // global-memory variant of the pair kernel
   size_t scratch_bytes = 0;
 
@@ -68,7 +71,13 @@ struct icikt_plan {
   PairUnit* d_units = nullptr;
   int32_t* d_pj = nullptr;
   PairRaw* d_raw = nullptr;
+  // results, packed in one allocation so that one copy brings them to the host:
+  // [tau P][pvalue P][taumax P][completeness P] doubles, [max taumax bits] u64, [status P] int32
+  unsigned char* d_res = nullptr;
+  unsigned char* h_res = nullptr;  // pinned staging copy (small and medium result sets only)
+  size_t res_bytes = 0;
   double *d_tau = nullptr, *d_p = nullptr, *d_tm = nullptr, *d_comp = nullptr;
+  unsigned long long* d_maxbits = nullptr;
   int32_t* d_status = nullptr;
   int64_t* d_counts = nullptr;
   unsigned long long* d_scalars = nullptr;  // [0] unit counter, [1] max taumax bits
@@ -95,7 +104,6 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->tab.grpstart);
   cudaFree(p->tab.stats);
   cudaFree(p->tab.max_tied);
-  if (p->h_max_tied) cudaFreeHost(p->h_max_tied);
   cudaFree(p->wk.keys_in);
   cudaFree(p->wk.keys_out);
   cudaFree(p->wk.vals_in);
@@ -106,11 +114,8 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->d_units);
   cudaFree(p->d_pj);
   cudaFree(p->d_raw);
-  cudaFree(p->d_tau);
-  cudaFree(p->d_p);
-  cudaFree(p->d_tm);
-  cudaFree(p->d_comp);
-  cudaFree(p->d_status);
+  cudaFree(p->d_res);
+  if (p->h_res) cudaFreeHost(p->h_res);
   cudaFree(p->d_counts);
   cudaFree(p->d_scalars);
   cudaFree(p->d_naive);
@@ -296,7 +301,6 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(cudaMemsetAsync(t.firstbits, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.grpstart, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.max_tied, 0, sizeof(int32_t), p->stream));
-  PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_max_tied), sizeof(int32_t)));
   p->shape = tiled_shape(n, 0, t.wstride, p->n_sm);
   PCK(dmalloc(&p->wk.keys_in, ne));
   PCK(dmalloc(&p->wk.keys_out, ne));
@@ -317,13 +321,17 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
     PCK(cudaMemcpyAsync(p->d_pj, pj, sizeof(int32_t) * np, cudaMemcpyHostToDevice, p->stream));
   }
   PCK(dmalloc(&p->d_raw, np));
-  PCK(dmalloc(&p->d_tau, np));
-  PCK(dmalloc(&p->d_p, np));
-  PCK(dmalloc(&p->d_tm, np));
-  PCK(dmalloc(&p->d_comp, np));
-  PCK(dmalloc(&p->d_status, np));
+  p->res_bytes = np * (4 * sizeof(double) + sizeof(int32_t)) + sizeof(unsigned long long);
+  PCK(cudaMalloc(reinterpret_cast<void**>(&p->d_res), p->res_bytes));
+  p->d_tau = reinterpret_cast<double*>(p->d_res);
+  p->d_p = p->d_tau + np;
+  p->d_tm = p->d_p + np;
+  p->d_comp = p->d_tm + np;
+  p->d_maxbits = reinterpret_cast<unsigned long long*>(p->d_comp + np);
+  p->d_status = reinterpret_cast<int32_t*>(p->d_maxbits + 1);
+  if (p->res_bytes <= (64u << 20)) PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_res), p->res_bytes));
   if (p->want_counts) PCK(dmalloc(&p->d_counts, np * ICIKT_NCOUNTS));
-  PCK(dmalloc(&p->d_scalars, 2));
+  PCK(dmalloc(&p->d_scalars, 2));  // [0] unit counter
   if (o.kernel == ICIKT_KERNEL_NAIVE) {
     p->naive_threads = std::min<int64_t>((int64_t)p->units.size(), (int64_t)p->n_sm * 256);
     p->naive_threads = std::max<int64_t>(p->naive_threads, 1);
@@ -380,28 +388,28 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   CK(cudaEventRecord(p->ev[2], p->stream));
   // worst-case shape (every row tied) decides whether the global scratch may be needed at all
   p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm);
-  const TiledShape worst = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
+  p->shape_heavy = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
+  const TiledShape& worst = p->shape_heavy;
   const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
   const int slot_ctas = std::max(worst.max_ctas, p->n_sm * 2);
   if ((worst.gmem || worst.const_gmem) && !p->d_scratch) {
     p->scratch_bytes = (size_t)slot_ctas * (size_t)slot_bytes;
     CK(cudaMalloc(reinterpret_cast<void**>(&p->d_scratch), p->scratch_bytes));
   }
-  p->shape.scratch_stride = p->d_scratch ? slot_bytes : 0;
-  p->shape.scratch_ctas = p->d_scratch ? slot_ctas : 0;
+  p->shape.scratch_stride = p->shape_heavy.scratch_stride = p->d_scratch ? slot_bytes : 0;
+  p->shape.scratch_ctas = p->shape_heavy.scratch_ctas = p->d_scratch ? slot_ctas : 0;
+  if (p->shape.gmem || (p->shape.warps == p->shape_heavy.warps && p->shape.region_bytes == p->shape_heavy.region_bytes)) {
+    p->shape = p->shape_heavy;  // one shape serves every column
+    p->tied_split = 0x7fffffff;
+  } else {
+    p->tied_split = tiled_tied_capacity(p->shape);
+  }
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
                                p->d_scratch, p->stream);
   if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
   CK(cudaEventRecord(p->ev[3], p->stream));
-  // the pair kernel's shared-memory region is sized for the longest tied list
-  CK(cudaMemcpyAsync(p->h_max_tied, p->tab.max_tied, sizeof(int32_t), cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaStreamSynchronize(p->stream));  // also: lit[] lives on this stack frame
-  {
-    TiledShape sh = tiled_shape(p->n, *p->h_max_tied, p->tab.wstride, p->n_sm);
-    sh.scratch_stride = p->d_scratch ? slot_bytes : 0;
-    sh.scratch_ctas = p->d_scratch ? slot_ctas : 0;
-    p->shape = sh;
-  }
+  // no synchronisation: `lit` is pageable host memory, so the copy above was staged before
+  // cudaMemcpyAsync returned
   p->tm.n_launches = l;
   p->columns_done = true;
   return ICIKT_OK;
@@ -411,6 +419,7 @@ int icikt_plan_pairs(icikt_plan* p) {
   if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
   CK(cudaSetDevice(p->device));
   CK(cudaMemsetAsync(p->d_scalars, 0, 2 * sizeof(unsigned long long), p->stream));
+  CK(cudaMemsetAsync(p->d_maxbits, 0, sizeof(unsigned long long), p->stream));
   CK(cudaEventRecord(p->ev[4], p->stream));
   if (p->P <= 0) CK(cudaEventRecord(p->ev[8], p->stream));
   PairLaunch pl;
@@ -426,8 +435,13 @@ int icikt_plan_pairs(icikt_plan* p) {
     int l;
     if (p->opts.kernel == ICIKT_KERNEL_NAIVE)
       l = launch_pairs_naive(pl, p->P, p->d_naive, p->naive_threads, p->stream);
-    else
-      l = launch_pairs_tiled(pl, p->shape, p->n_sm, p->stream);
+    else {
+      l = launch_pairs_tiled(pl, p->shape, p->n_sm, p->tied_split, -1, p->stream);
+      if (l > 0 && p->tied_split != 0x7fffffff) {
+        const int l2 = launch_pairs_tiled(pl, p->shape_heavy, p->n_sm, 0x7fffffff, p->tied_split, p->stream);
+        l = l2 < 0 ? l2 : l + l2;
+      }
+    }
     if (l == -2)
       return fail(ICIKT_ERR_TOO_LONG, "the tied-value lists of this matrix do not fit the pair kernel's "
                                       "shared memory (long vectors with heavy ties)");
@@ -449,7 +463,7 @@ int icikt_plan_pairs(icikt_plan* p) {
     el.completeness = p->d_comp;
     el.status = p->d_status;
     el.counts = p->d_counts;
-    el.max_taumax_bits = p->d_scalars + 1;
+    el.max_taumax_bits = p->d_maxbits;
     l = launch_epilogue(el, p->stream);
     if (l < 0) return cuda_fail(cudaGetLastError(), "epilogue kernel");
     launches += l;
@@ -473,18 +487,36 @@ int icikt_plan_download(icikt_plan* p, double* raw, double* pvalue, double* taum
   CK(cudaSetDevice(p->device));
   const size_t np = (size_t)p->P;
   CK(cudaEventRecord(p->ev[6], p->stream));
-  if (np) {
-    if (raw) CK(cudaMemcpyAsync(raw, p->d_tau, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-    if (pvalue) CK(cudaMemcpyAsync(pvalue, p->d_p, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-    if (taumax) CK(cudaMemcpyAsync(taumax, p->d_tm, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-    if (completeness) CK(cudaMemcpyAsync(completeness, p->d_comp, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-    if (status) CK(cudaMemcpyAsync(status, p->d_status, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, p->stream));
-    if (counts) CK(cudaMemcpyAsync(counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS, cudaMemcpyDeviceToHost, p->stream));
-  }
   unsigned long long bits = 0;
-  CK(cudaMemcpyAsync(&bits, p->d_scalars + 1, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaEventRecord(p->ev[7], p->stream));
-  CK(cudaStreamSynchronize(p->stream));
+  if (p->h_res) {
+    // one device-to-host copy into pinned memory, then plain host copies into the caller's arrays
+    CK(cudaMemcpyAsync(p->h_res, p->d_res, p->res_bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (counts && np) CK(cudaMemcpyAsync(counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaEventRecord(p->ev[7], p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const size_t npad = std::max<size_t>(np, 1);
+    const double* h = reinterpret_cast<const double*>(p->h_res);
+    if (np) {
+      if (raw) std::memcpy(raw, h, sizeof(double) * np);
+      if (pvalue) std::memcpy(pvalue, h + npad, sizeof(double) * np);
+      if (taumax) std::memcpy(taumax, h + 2 * npad, sizeof(double) * np);
+      if (completeness) std::memcpy(completeness, h + 3 * npad, sizeof(double) * np);
+      if (status) std::memcpy(status, p->h_res + 4 * npad * sizeof(double) + sizeof(unsigned long long), sizeof(int32_t) * np);
+    }
+    std::memcpy(&bits, h + 4 * npad, sizeof(bits));
+  } else {
+    if (np) {
+      if (raw) CK(cudaMemcpyAsync(raw, p->d_tau, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+      if (pvalue) CK(cudaMemcpyAsync(pvalue, p->d_p, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+      if (taumax) CK(cudaMemcpyAsync(taumax, p->d_tm, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+      if (completeness) CK(cudaMemcpyAsync(completeness, p->d_comp, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
+      if (status) CK(cudaMemcpyAsync(status, p->d_status, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, p->stream));
+      if (counts) CK(cudaMemcpyAsync(counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS, cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaMemcpyAsync(&bits, p->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaEventRecord(p->ev[7], p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  }
   if (max_taumax) {
     double v;
     std::memcpy(&v, &bits, sizeof(v));

@@ -86,7 +86,11 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
 int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream);
 
 // K2 (tiled) and K2-naive; both fill raw[P].
-int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream);
+// runs only if tied_gt < max_tied (device value written by K1) <= tied_le; unit_counter must be zero
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int tied_le, int tied_gt,
+                       cudaStream_t stream);
+// longest tied-row list (rows) the shape's shared-memory region can take in pass B
+int tiled_tied_capacity(const TiledShape& sh);
 int launch_pairs_naive(const PairLaunch& pl, int64_t P, uint32_t* d_scratch, int64_t n_threads,
                        cudaStream_t stream);
 size_t naive_scratch_bytes(int64_t n, int64_t n_threads);

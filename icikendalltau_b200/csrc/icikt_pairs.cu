@@ -449,6 +449,11 @@ struct TiledParams {
   long long n_units;
   int n, n32, nstride, wstride;
   int kk;  // pass A: 8-key runs per thread (odd); a warp covers 8*kk 32-element chunks
+  // the launch runs only if  tied_gt < *max_tied <= tied_le  (longest tied-row list over the
+  // columns, written by K1): lets the host enqueue the shape for light ties and the shape for
+  // heavy ties back to back without reading the value back
+  const int32_t* max_tied;
+  int tied_le, tied_gt;
 };
 
 // Shared-memory layout of one CTA (all offsets multiples of 16 bytes)
@@ -506,6 +511,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
+  {
+    const int mt = *p.max_tied;
+    if (mt > p.tied_le || mt <= p.tied_gt) return;
+  }
   const int n = p.n;
   const int nwords = p.n32 >> 5;
   const int kk = p.kk;       // 8-key runs per thread in pass A
@@ -936,12 +945,21 @@ TiledParams make_params(const PairLaunch& pl) {
   p.scratch = nullptr;
   p.scratch_stride = 0;
   p.kk = 0;
+  p.max_tied = t.max_tied;
+  p.tied_le = 0x7fffffff;
+  p.tied_gt = -1;
   return p;
 }
 
 }  // namespace
 
 int64_t tiled_max_n() { return 65535; }
+
+int tiled_tied_capacity(const TiledShape& sh) {
+  // pass B ping-pongs two u32 buffers of W * kkB * 32 keys inside the region
+  const int per = sh.warps * 32;
+  return (sh.region_bytes / 8) / per * per;
+}
 
 int measure_smem_bandwidth(double* gbps32, double* gbps128) {
   int dev = 0, n_sm = 0;
@@ -1082,9 +1100,11 @@ int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, 
 
 }  // namespace
 
-int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, cudaStream_t stream) {
-  if (cudaMemsetAsync(pl.unit_counter, 0, sizeof(unsigned long long), stream) != cudaSuccess) return -1;
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int tied_le, int tied_gt,
+                       cudaStream_t stream) {
   TiledParams p = make_params(pl);
+  p.tied_le = tied_le;
+  p.tied_gt = tied_gt;
   p.kk = sh.kk;
   p.scratch = pl.scratch;
   p.scratch_stride = sh.scratch_stride;
