@@ -115,6 +115,10 @@ struct Mem<false> {
         : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base)
         : "memory");
   }
+  static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ ptr from_shared(const void* q) { return smem_addr(q); }
   static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(p), "h"((unsigned short)v) : "memory");
   }
@@ -148,6 +152,9 @@ struct Mem<true> {
     if (ph) S += 1;
     if (!pl) acc2 += qs >> 16;
   }
+  static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) { atomicAdd(reinterpret_cast<uint32_t*>(p), v); }
+  // generic addressing reaches shared memory too
+  static __device__ __forceinline__ ptr from_shared(const void* q) { return (ptr) const_cast<void*>(q); }
   static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
     *reinterpret_cast<unsigned short*>(p) = (unsigned short)v;
   }
@@ -363,67 +370,111 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
   }
 }
 
-// Ordered stream compaction: writes the y-ranks of the rows of x's first tie group into
-// buf[0, f) in ascending y order by sweeping y's sorted order (permY) and keeping the rows whose
-// bit is set in x's membership mask.  Two rows per lane (one 32-bit load of permY).  Sweep 1
-// counts the kept rows per warp segment and parks the ballot masks in `fmask`; sweep 2 scatters.
-// The group is then free of inversions.  kk must be even; permY is readable up to nstride.
-// `rank_tbl` is y's dense-rank table (u16 per row) in the same memory space as `buf`.
+// First x tie group (the missing rows): writes the y-ranks of its f rows into buf[0, f) in
+// ascending order, so that the group contributes no inversions, and returns (summed over the
+// threads) its joint ties with y, sum over y ranks of C(count, 2).  The sorted sequence is fully
+// described by a histogram over the K ranks of y, so nothing is moved:
+//   1. hist[rank_y[row]]++ for the f rows (perm_x[0..f) are exactly the group's rows), 16-bit
+//      counters packed two per word, shared-memory atomics;
+//   2. every thread folds a contiguous range of counters, one block scan gives its output slot;
+//   3. it writes `count` copies of each of its ranks; ranks with a long run (the rows missing in
+//      both columns, heavy ties) are parked in a short list and written by the whole CTA.
+// The histogram lives at the top of `buf` (which the gather fills afterwards), above the f output
+// slots; if the K counters do not fit there the ranks are processed in several rounds, and if
+// not even 32 fit, in a 16-word spare in shared memory.  Cost ~ 8 f + 7 K instead of ~ 38 n
+// for an ordered compaction of y's sorted order through x's membership mask.
 template <bool G>
-__device__ __forceinline__ void emit_first_group(typename Mem<G>::ptr buf, const int n, const int kk,
-                                                 const int nwarps,
-                                                 const uint16_t* __restrict__ permY_g,
-                                                 typename Mem<G>::ptr rank_tbl,
-                                                 const uint32_t* __restrict__ fbX,
-                                                 uint32_t* __restrict__ fmask, uint32_t* descT,
-                                                 const int lane, const int warp) {
+__device__ __forceinline__ uint32_t emit_first_group(typename Mem<G>::ptr buf, const int cap, const int f,
+                                                     const int K, const uint16_t* __restrict__ permX,
+                                                     typename Mem<G>::ptr rank_tbl,
+                                                     uint32_t* __restrict__ mini, uint32_t* __restrict__ list,
+                                                     const int list_cap, uint32_t* descT, uint32_t* list_n,
+                                                     const int nwarps) {
   typedef Mem<G> M;
-  const int kk2 = kk >> 1;
-  const int c0 = warp * kk;  // first 32-chunk of my segment; double chunk c covers chunks c0+2c, c0+2c+1
-  const uint32_t lt = lanemask_lt();
-  const uint32_t* permY2 = reinterpret_cast<const uint32_t*>(permY_g);
-  const int nvalid2 = (n + 1) >> 1;  // 32-bit words of permY holding at least one valid row
-  uint32_t T = 0;
-#pragma unroll 2
-  for (int c = 0; c < kk2; ++c) {
-    const int widx = ((c0 + 2 * c) << 4) + lane;  // word index: rows 2*widx, 2*widx+1
-    bool memL = false, memH = false;
-    if (widx < nvalid2) {
-      const uint32_t rr = __ldg(permY2 + widx);
-      const uint32_t r0 = rr & 0xffffu, r1 = rr >> 16;
-      memL = (__funnelshift_r(fbX[r0 >> 5], 0u, r0) & 1u) != 0u;  // shift amount is taken mod 32
-      memH = (2 * widx + 1 < n) && ((__funnelshift_r(fbX[r1 >> 5], 0u, r1) & 1u) != 0u);
-    }
-    const uint32_t fL = __ballot_sync(FULL, memL), fH = __ballot_sync(FULL, memH);
-    if (lane == 0) {
-      fmask[c0 + 2 * c] = fL;
-      fmask[c0 + 2 * c + 1] = fH;
-    }
-    T += __popc(fL) + __popc(fH);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  int hw = (cap - ((f + 1) & ~1)) >> 1;            // counter words available above the output slots
+  typename M::ptr hist = M::add(buf, 2 * cap - 4 * hw);
+  if (hw < 16) {
+    hw = 16;
+    hist = M::from_shared(mini);
   }
-  if (lane == 0) descT[warp] = T;
-  __syncthreads();
-  const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
-  uint32_t incl = v;
+  const int kw = (K + 1) >> 1;                     // counter words needed
+  if (hw > kw) hw = kw;
+  const int wpt = (hw + T - 1) / T;                // words per thread
+  uint32_t ties = 0, done = 0;                     // done: output slots filled by earlier rounds
+  for (int k0 = 0; k0 < K; k0 += 2 * hw) {
+    for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
+    if (tid == 0) *list_n = 0u;
+    __syncthreads();
+    {  // 1. histogram of the group's y ranks inside [k0, k0 + 2 hw)
+      const uint4* px8 = reinterpret_cast<const uint4*>(permX);
+      const uint32_t span = (uint32_t)(2 * hw);
+      for (int q8 = tid; q8 < ((f + 7) >> 3); q8 += T) {
+        const uint4 pv = __ldg(px8 + q8);  // perm is readable up to nstride (multiple of 64)
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(FULL, incl, d);
-    if (lane >= d) incl += t;
-  }
-  uint32_t P = __shfl_sync(FULL, incl - v, warp);
-#pragma unroll 2
-  for (int c = 0; c < kk2; ++c) {
-    const uint32_t fL = fmask[c0 + 2 * c], fH = fmask[c0 + 2 * c + 1];
-    const bool memL = (fL >> lane) & 1u, memH = (fH >> lane) & 1u;
-    if (memL || memH) {
-      const uint32_t rr = __ldg(permY2 + (((c0 + 2 * c) << 4) + lane));
-      const uint32_t pL = P + __popc(fL & lt) + __popc(fH & lt);
-      if (memL) M::st16(M::add(buf, (int32_t)(pL << 1)), M::ld16(M::add(rank_tbl, (int32_t)((rr & 0xffffu) << 1))));
-      if (memH)
-        M::st16(M::add(buf, (int32_t)((pL + (memL ? 1u : 0u)) << 1)), M::ld16(M::add(rank_tbl, (int32_t)((rr >> 16) << 1))));
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t row = (j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xffffu);
+          if ((q8 << 3) + j < f) {
+            const uint32_t r = M::ld16(M::add(rank_tbl, (int32_t)(row << 1))) - (uint32_t)k0;
+            if (r < span) M::red_add32(M::add(hist, (int32_t)((r >> 1) << 2)), (r & 1u) ? 0x10000u : 1u);
+          }
+        }
+      }
     }
-    P += __popc(fL) + __popc(fH);
+    __syncthreads();
+    // 2. rows per thread range, block scan
+    const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
+    uint32_t mine = 0;
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t c = M::ld32(M::add(hist, w << 2));
+      mine += (c & 0xffffu) + (c >> 16);
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) descT[warp] = incl;
+    __syncthreads();
+    const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+    const uint32_t total = __reduce_add_sync(FULL, v);
+    uint32_t pos = done + __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
+    // 3. write the runs
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t cw = M::ld32(M::add(hist, w << 2));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
+        const uint32_t r = (uint32_t)k0 + 2u * (uint32_t)w + (uint32_t)h;
+        if (c == 1u) {
+          M::st16(M::add(buf, (int32_t)(pos << 1)), r);
+        } else if (c > 1u) {
+          ties += (c * (c - 1u)) >> 1;
+          uint32_t slot = 0xffffffffu;
+          if (c >= 48u) slot = atomicAdd(list_n, 1u);
+          if (slot < (uint32_t)list_cap) {
+            list[3 * slot + 0] = r;
+            list[3 * slot + 1] = pos;
+            list[3 * slot + 2] = c;
+          } else {
+            for (uint32_t j = 0; j < c; ++j) M::st16(M::add(buf, (int32_t)((pos + j) << 1)), r);
+          }
+        }
+        pos += c;
+      }
+    }
+    done += total;
+    __syncthreads();
+    const uint32_t nl = min(*list_n, (uint32_t)list_cap);
+    for (uint32_t e = 0; e < nl; ++e) {
+      const uint32_t r = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
+      for (uint32_t j = tid; j < c; j += T) M::st16(M::add(buf, (int32_t)((off + j) << 1)), r);
+    }
+    __syncthreads();  // the list and the counters are reused by the next round / overwritten by the gather
   }
+  return ties;
 }
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -463,8 +514,8 @@ struct Carve {
   unsigned char* region_ptr;  // ping-pong region (shared-memory variant)
   uint32_t region;            // its shared-window address
   uint32_t* nabY;
-  uint32_t* fbX;
-  uint32_t* fmask;
+  uint32_t* mini;   // [16] spare histogram words + [1] list length of the first-group emission
+  uint32_t* fmask;  // the emission's list of long runs
   uint32_t* descT;
   int32_t* descB;
   __device__ Carve(unsigned char* p, int wstride, int fwords) {
@@ -478,8 +529,8 @@ struct Carve {
     p += 4 * 32;
     nabY = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)wstride;
-    fbX = reinterpret_cast<uint32_t*>(p);
-    p += 4 * (size_t)wstride;
+    mini = reinterpret_cast<uint32_t*>(p);
+    p += 4 * 32;
     fmask = reinterpret_cast<uint32_t*>(p);
     p += 4 * (size_t)fwords;
     region_ptr = p;
@@ -489,7 +540,7 @@ struct Carve {
 
 __host__ __device__ inline int fmask_words(int warps, int kk) { return (warps * kk + 3) & ~3; }
 inline size_t tiled_smem_bytes(int region_bytes, int wstride, int fwords) {
-  return 8 * 32 * 4 + 16 + 256 + 8 * (size_t)wstride + 4 * (size_t)fwords + (size_t)region_bytes;
+  return 8 * 32 * 4 + 16 + 256 + 4 * (size_t)wstride + 128 + 4 * (size_t)fwords + (size_t)region_bytes;
 }
 
 template <bool G>
@@ -522,9 +573,6 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   const int cap = (nwarps * kkc) << 5;
   Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kkc));
   const typename M::ptr bufA = region_base<G>(sm, p), bufB16 = M::add(bufA, 2 * cap);
-  // tie counters: second half of the region while it is otherwise unused
-  uint32_t* const cnt = G ? reinterpret_cast<uint32_t*>(p.scratch + (size_t)blockIdx.x * (size_t)p.scratch_stride + 2 * (size_t)cap)
-                          : reinterpret_cast<uint32_t*>(sm.region_ptr + 2 * (size_t)cap);
 
   for (;;) {
     if (tid == 0) *sm.unit_slot = (long long)atomicAdd(p.unit_counter, 1ull);
@@ -538,9 +586,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const uint32_t* nb = p.nabits + (size_t)ycol * p.wstride;
       for (int i = tid; i < nwords; i += T) sm.nabY[i] = nb[i];
     }
-    const uint16_t* permY_g = p.perm + (size_t)ycol * p.nstride;
     const uint16_t* rankY_g = p.rank + (size_t)ycol * p.nstride;
-    const uint32_t* fbYg = p.firstbits + (size_t)ycol * p.wstride;
     const uint32_t* g0Yg = ((YS.flags & 1) ? p.firstbits : p.nabits) + (size_t)ycol * p.wstride;
     // y's dense-rank table: staged into the second ping-pong buffer (shared variant) or read in place
     const typename M::ptr rank_tbl = G ? (typename M::ptr)(size_t)rankY_g : bufB16;
@@ -556,15 +602,13 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const uint32_t* fbXg = p.firstbits + (size_t)xcol * p.wstride;
       const uint32_t* nbXg = p.nabits + (size_t)xcol * p.wstride;
       const bool absorbed = ((XS.flags | YS.flags) & 1) != 0;
-      // joint-missing rows (b), joint lowest group (g00, differs from b only if a column's
-      // missing rows tie with its minimum), and first-group(x) x first-group(y) rows (g11)
-      uint32_t bpart = 0, g00part = 0, g11part = 0;
+      // joint-missing rows (b) and joint lowest group (g00, differs from b only if a column's
+      // missing rows tie with its minimum)
+      uint32_t bpart = 0, g00part = 0;
       for (int i = tid; i < nwords; i += T) {
-        const uint32_t fb = fbXg[i], nb = nbXg[i];
-        sm.fbX[i] = fb;
+        const uint32_t nb = nbXg[i];
         bpart += __popc(nb & sm.nabY[i]);
-        g11part += __popc(fb & fbYg[i]);
-        if (absorbed) g00part += __popc(((XS.flags & 1) ? fb : nb) & g0Yg[i]);
+        if (absorbed) g00part += __popc(((XS.flags & 1) ? fbXg[i] : nb) & g0Yg[i]);
       }
       if (YS.n_groups < 2 || XS.n_groups < 2) {
         // a constant or all-missing column: K3 reports NA; only the joint-missing count is kept
@@ -586,20 +630,6 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       }
       const int f = XS.first_run;
       uint32_t ties = 0;
-      __syncthreads();  // fbX is complete
-      if (f > 0 && YS.n_tied > 0) {
-        // joint ties of x's first group with the tied (non-first) groups of y: one counter per
-        // tied y group; every member row adds the number of members seen before it
-        const uint16_t* trowY = p.trow + (size_t)ycol * p.nstride;
-        const uint16_t* trunY = p.trun + (size_t)ycol * p.nstride;
-        for (int i = tid; i < YS.n_tgroups; i += T) cnt[i] = 0;
-        __syncthreads();
-        for (int t = tid; t < YS.n_tied; t += T) {
-          const uint32_t row = trowY[t];
-          if ((sm.fbX[row >> 5] >> (row & 31)) & 1u) ties += atomicAdd(&cnt[trunY[t]], 1u);
-        }
-        __syncthreads();
-      }
       if (!G) {  // dense ranks of y go to the second ping-pong buffer until pass A starts
         const uint4* src = reinterpret_cast<const uint4*>(rankY_g);
         for (int i = tid; i < (p.nstride >> 3); i += T) {
@@ -608,6 +638,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         }
         __syncthreads();
       }
+      // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
+      if (f > 0)
+        ties = emit_first_group<G>(bufA, cap, f, YS.n_groups, permX, rank_tbl, sm.mini, sm.fmask,
+                                   fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16, nwarps);
       {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
         const uint4* px8 = reinterpret_cast<const uint4*>(permX);
         for (int q8 = (f >> 3) + tid; q8 < (cap >> 3); q8 += T) {
@@ -638,7 +672,6 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
           }
         }
       }
-      if (f > 0) emit_first_group<G>(bufA, n, kkc, nwarps, permY_g, rank_tbl, sm.fbX, sm.fmask, sm.descT, lane, warp);
       __syncthreads();
       uint32_t accB = 0;
       unsigned long long accA = 0;
@@ -658,7 +691,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       }
       const unsigned long long sA = warp_sum_u64(accA),
                                sB = warp_sum_u64(accB),
-                               sT = warp_sum_u64(((unsigned long long)g11part << 32) | ties),
+                               sT = warp_sum_u64((unsigned long long)ties),
                                sb = warp_sum_u64(((unsigned long long)g00part << 32) | bpart);
       if (lane == 0) {
         sm.red[warp * 4 + 0] = sA;
@@ -675,10 +708,9 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
           t2 += sm.red[w * 4 + 2];
           bb += sm.red[w * 4 + 3];
         }
-        const long long g11 = (long long)(t2 >> 32);  // rows in the first group of both columns
         PairRaw r;
         r.dis = (long long)(a - YS.cconst - b2);
-        r.ntie = (long long)(t2 & 0xffffffffull) + ((f > 0 && YS.first_run > 0) ? g11 * (g11 - 1) / 2 : 0);
+        r.ntie = (long long)t2;
         r.b = (long long)(bb & 0xffffffffull);
         r.g00 = absorbed ? (long long)(bb >> 32) : r.b;
         p.raw[slot] = r;

@@ -456,3 +456,30 @@ def test_config4_shape_counts_with_heavy_ties():
     x, persp = synth.make("config4", C=8)
     got = ik.run_pairs(x, (np.nan, np.inf, 0.0), perspective=persp, want_counts=True)
     assert_parity(got, oracle_pairs(x, global_na=(np.nan, np.inf, 0.0), perspective=persp), "config4")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,fracs,ties", [(3000, (0.85, 0.0, 0.4, 0.97), False), (256, (255 / 256, 0.0, 0.5), False),
+                                          (5000, (0.7, 0.1, 0.0), True), (20000, (0.9, 0.02, 0.3), True)])
+def test_uneven_missingness_first_group_emission(n, fracs, ties):
+    """Columns with very different missing fractions: the rank histogram of x's first group does not
+    fit beside its output slots and is processed in several rounds (or in the spare words); with ties
+    in y long runs go through the cooperative list.  Both orders of every pair are exercised."""
+    rng = np.random.default_rng(n)
+    base = rng.normal(size=n)
+    cols = []
+    for fr in fracs:
+        v = base + 0.5 * rng.normal(size=n)
+        if ties:
+            v = np.round(v * 1.5)
+        k = int(round(fr * n))
+        if k:
+            v[np.argsort(v)[:k]] = np.nan
+        cols.append(v)
+    x = np.asfortranarray(np.column_stack(cols))
+    C = x.shape[1]
+    pi = np.array([i for i in range(C) for j in range(C) if i != j], dtype=np.int32)
+    pj = np.array([j for i in range(C) for j in range(C) if i != j], dtype=np.int32)
+    for persp in ("global", "local"):
+        got = ik.run_pairs(x, (), pi=pi, pj=pj, perspective=persp, want_counts=True)
+        assert_parity(got, oracle_pairs(x, pi=pi, pj=pj, perspective=persp), f"uneven NA n={n} {persp}")
