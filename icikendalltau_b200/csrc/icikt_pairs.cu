@@ -62,6 +62,12 @@ __device__ __forceinline__ uint32_t below_top(uint32_t bits) {
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+// Constants handed over as kernel parameters so that the assembler keeps multiplications by
+// them as IMAD / IMAD.HI (FMA pipe) instead of strength-reducing them to integer-ALU shifts/adds.
+struct PipeConst {
+  uint32_t one, two, c64k;
+};
+
 template <bool G>
 struct Mem;
 template <>
@@ -84,12 +90,26 @@ struct Mem<false> {
   // position of p for the inversion accumulator: any value that differs from the byte offset
   // inside the buffer by a per-level constant (here the shared-window address itself)
   static __device__ __forceinline__ uint32_t off(ptr p, ptr) { return p; }
+  // a + b on the FMA pipe (IMAD with a multiplier the assembler cannot fold): the integer ALU
+  // pipe is the binding one in pass A, both pipes issue one warp instruction per two cycles
+  static __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+  }
+  // high 16-bit key of a word on the FMA pipe (IMAD.HI by 65536)
+  static __device__ __forceinline__ uint32_t hi16(uint32_t w, uint32_t c64k) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(w), "r"(c64k));
+    return d;
+  }
   // one key of pass A's scatter sweep (two bits per level, see count_pass): Q01/Q23 hold the
   // next free slot (element index, 16 bits each) of digit classes 0|1 and 2|3, S the number of
-  // keys seen so far whose high bit is set.  14 instructions per key.
+  // keys seen so far whose high bit is set.  `two` is a register holding 2 that the assembler
+  // cannot fold, so the slot address is an IMAD and not an LEA.  14 instructions per key.
   static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
-                                               uint32_t key, ptr base) {
+                                               uint32_t key, ptr base, uint32_t two) {
     asm volatile(
         "{\n\t"
         ".reg .pred ph, pl;\n\t"
@@ -101,7 +121,7 @@ struct Mem<false> {
         "selp.b32 qs, %1, %0, ph;\n\t"
         "selp.b32 sel, 0x4432, 0x4410, pl;\n\t"
         "prmt.b32 idx, qs, 0, sel;\n\t"
-        "mad.lo.u32 ad, idx, 2, %9;\n\t"
+        "mad.lo.u32 ad, idx, %10, %9;\n\t"
         "st.shared.u16 [ad], %8;\n\t"
         "selp.b32 inc, 0x10000, 1, pl;\n\t"
         "shr.u32 up, qs, 16;\n\t"
@@ -112,8 +132,31 @@ struct Mem<false> {
         "@!pl add.u32 %4, %4, up;\n\t"
         "}"
         : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
-        : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base), "r"(two)
         : "memory");
+  }
+  // the same without the store: the last level only has to count
+  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred ph, pl;\n\t"
+        ".reg .b32 t, qs, inc, up;\n\t"
+        "and.b32 t, %5, %7;\n\t"
+        "setp.ne.u32 ph, t, 0;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 pl, t, 0;\n\t"
+        "selp.b32 qs, %1, %0, ph;\n\t"
+        "selp.b32 inc, 0x10000, 1, pl;\n\t"
+        "shr.u32 up, qs, 16;\n\t"
+        "@ph add.u32 %1, %1, inc;\n\t"
+        "@!ph add.u32 %0, %0, inc;\n\t"
+        "@!ph add.u32 %3, %3, %2;\n\t"
+        "@ph add.u32 %2, %2, 1;\n\t"
+        "@!pl add.u32 %4, %4, up;\n\t"
+        "}"
+        : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi));
   }
   static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
@@ -140,13 +183,24 @@ struct Mem<true> {
     a = v.x; b = v.y; c = v.z; d = v.w;
   }
   static __device__ __forceinline__ uint32_t off(ptr p, ptr base) { return (uint32_t)(p - base); }
+  static __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t) { return a + b; }
+  static __device__ __forceinline__ uint32_t hi16(uint32_t w, uint32_t) { return w >> 16; }
   static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
-                                               uint32_t key, ptr base) {
+                                               uint32_t key, ptr base, uint32_t) {
     const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
     const uint32_t qs = ph ? Q23 : Q01;
     const uint32_t idx = pl ? (qs >> 16) : (qs & 0xffffu);
     *reinterpret_cast<unsigned short*>(base + 2 * (size_t)idx) = (unsigned short)key;
+    const uint32_t inc = pl ? 0x10000u : 1u;
+    if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
+    if (ph) S += 1;
+    if (!pl) acc2 += qs >> 16;
+  }
+  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi) {
+    const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
+    const uint32_t qs = ph ? Q23 : Q01;
     const uint32_t inc = pl ? 0x10000u : 1u;
     if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
     if (ph) S += 1;
@@ -297,7 +351,8 @@ __device__ __forceinline__ void bucket_pass(typename Mem<G>::ptr a, typename Mem
 template <bool G>
 __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
                                            const int nwarps, const int L, uint32_t* descA, uint32_t* descB,
-                                           const int lane, const int warp, unsigned long long& acc64) {
+                                           const int lane, const int warp, const PipeConst pc,
+                                           unsigned long long& acc64) {
   typedef Mem<G> M;
   const uint32_t tid = ((uint32_t)warp << 5) + (uint32_t)lane;
   const uint32_t R = (uint32_t)kk << 3;                // keys per thread range
@@ -314,9 +369,9 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t lo = (w[j] >> s) & 0x00010001u, hi = (w[j] >> (s + 1)) & 0x00010001u;
-        cl += lo;
-        ch += hi;
-        cb += lo & hi;
+        cl = M::fadd(cl, lo, pc.one);
+        ch = M::fadd(ch, hi, pc.one);
+        cb = M::fadd(cb, lo & hi, pc.one);
       }
     }
     const uint32_t n3 = (cb & 0xffffu) + (cb >> 16);
@@ -349,14 +404,27 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
     uint32_t S = e2 + e3, acc = 0, acc2 = 0;
     uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
     asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));  // keep the bit tests single LOP3s
+    if (s > 0) {
 #pragma unroll 1
-    for (int c = 0; c < kk; ++c) {
-      uint32_t w[4];
-      M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+      for (int c = 0; c < kk; ++c) {
+        uint32_t w[4];
+        M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        M::step4(Q01, Q23, S, acc, acc2, w[j], bLl, bHl, w[j], b);
-        M::step4(Q01, Q23, S, acc, acc2, w[j], bLh, bHh, w[j] >> 16, b);
+        for (int j = 0; j < 4; ++j) {
+          M::step4(Q01, Q23, S, acc, acc2, w[j], bLl, bHl, w[j], b, pc.two);
+          M::step4(Q01, Q23, S, acc, acc2, w[j], bLh, bHh, M::hi16(w[j], pc.c64k), b, pc.two);
+        }
+      }
+    } else {  // the sorted sequence itself is not needed: the last level only counts
+#pragma unroll 1
+      for (int c = 0; c < kk; ++c) {
+        uint32_t w[4];
+        M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          M::step4c(Q01, Q23, S, acc, acc2, w[j], bLl, bHl);
+          M::step4c(Q01, Q23, S, acc, acc2, w[j], bLh, bHh);
+        }
       }
     }
     // acc2 summed absolute slot indices: take out the class bases (class 1 starts at N0, class 3
@@ -505,6 +573,7 @@ struct TiledParams {
   // heavy ties back to back without reading the value back
   const int32_t* max_tied;
   int tied_le, tied_gt;
+  PipeConst pc;
 };
 
 // Shared-memory layout of one CTA (all offsets multiples of 16 bytes)
@@ -675,7 +744,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       __syncthreads();
       uint32_t accB = 0;
       unsigned long long accA = 0;
-      count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, accA);
+      count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
       const int m = XS.n_tied;
       if (m > 0) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
@@ -745,7 +814,7 @@ __global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams
     for (int q = tid; q < cap; q += T) M::st16(M::add(bufA, q << 1), (q < n) ? (uint32_t)rk[pm[q]] : padA);
     __syncthreads();
     unsigned long long accA = 0;
-    count_pass<G>(bufA, bufB, kk, nwarps, CS.levels, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, accA);
+    count_pass<G>(bufA, bufB, kk, nwarps, CS.levels, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
     const unsigned long long s = warp_sum_u64(accA);
     if (lane == 0) sm.red[warp] = s;
     __syncthreads();
@@ -980,6 +1049,9 @@ TiledParams make_params(const PairLaunch& pl) {
   p.max_tied = t.max_tied;
   p.tied_le = 0x7fffffff;
   p.tied_gt = -1;
+  p.pc.one = 1u;
+  p.pc.two = 2u;
+  p.pc.c64k = 65536u;
   return p;
 }
 
