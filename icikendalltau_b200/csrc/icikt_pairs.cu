@@ -474,21 +474,29 @@ __device__ __forceinline__ uint32_t emit_first_group(typename Mem<G>::ptr buf, c
     for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
     if (tid == 0) *list_n = 0u;
     __syncthreads();
-    {  // 1. histogram of the group's y ranks inside [k0, k0 + 2 hw)
+    {  // 1. histogram of the group's y ranks inside [k0, k0 + 2 hw).  Rank 0 of the first round
+       // (the rows missing in both columns, by far the fullest counter) is counted per warp by
+       // ballot instead of same-address atomics.
       const uint4* px8 = reinterpret_cast<const uint4*>(permX);
       const uint32_t span = (uint32_t)(2 * hw);
-      for (int q8 = tid; q8 < ((f + 7) >> 3); q8 += T) {
-        const uint4 pv = __ldg(px8 + q8);  // perm is readable up to nstride (multiple of 64)
+      const int lim8 = (f + 7) >> 3;
+      uint32_t zeros = 0;
+      for (int q8w = tid & ~31; q8w < lim8; q8w += T) {  // warp-uniform trip count
+        const int q8 = q8w + lane;
+        uint4 pv = make_uint4(0u, 0u, 0u, 0u);
+        if (q8 < lim8) pv = __ldg(px8 + q8);  // perm is readable up to nstride (multiple of 64)
         const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t row = (j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xffffu);
-          if ((q8 << 3) + j < f) {
-            const uint32_t r = M::ld16(M::add(rank_tbl, (int32_t)(row << 1))) - (uint32_t)k0;
-            if (r < span) M::red_add32(M::add(hist, (int32_t)((r >> 1) << 2)), (r & 1u) ? 0x10000u : 1u);
-          }
+          uint32_t r = 0xffffffffu;
+          if ((q8 << 3) + j < f) r = M::ld16(M::add(rank_tbl, (int32_t)(row << 1))) - (uint32_t)k0;
+          const bool z = (r == 0u);
+          zeros += __popc(__ballot_sync(FULL, z));
+          if (r < span && !z) M::red_add32(M::add(hist, (int32_t)((r >> 1) << 2)), (r & 1u) ? 0x10000u : 1u);
         }
       }
+      if (lane == 0 && zeros) M::red_add32(hist, zeros);
     }
     __syncthreads();
     // 2. rows per thread range, block scan
