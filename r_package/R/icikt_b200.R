@@ -234,3 +234,23 @@ pairwise_completeness = function(data_matrix, global_na = c(NA, Inf, 0), include
   .Call(C_icikt_release)
   library.dynam.unload("ICIKendallTauB200", libpath)
 }
+
+# Result formats either side of the path (reference: R/reshaping.R:16-68), same names and columns.
+cor_matrix_2_long_df = function(in_matrix) {
+  if (is.null(rownames(in_matrix)) || is.null(colnames(in_matrix))) stop("`in_matrix` needs row and column names")
+  data.frame(s1 = rep(rownames(in_matrix), times = ncol(in_matrix)),
+             s2 = rep(colnames(in_matrix), each = nrow(in_matrix)),
+             cor = as.vector(in_matrix), stringsAsFactors = FALSE)
+}
+
+long_df_2_cor_matrix = function(long_df, is_square = TRUE) {
+  if (!all(c("s1", "s2", "cor") %in% names(long_df))) {
+    stop("The data.frame must contain the names 's1', 's2', and 'cor'.")
+  }
+  s1 = as.character(long_df[["s1"]]); s2 = as.character(long_df[["s2"]])
+  if (is_square) { rows = cols = sort(unique(c(s1, s2))) } else { rows = sort(unique(s1)); cols = sort(unique(s2)) }
+  out = matrix(NA_real_, length(rows), length(cols), dimnames = list(rows, cols))
+  out[cbind(s1, s2)] = long_df[["cor"]]
+  if (is_square && nrow(long_df) != length(out)) out[cbind(s2, s1)] = long_df[["cor"]]
+  out
+}

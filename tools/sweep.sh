@@ -11,7 +11,9 @@ for l in sys.stdin:
 ")
   echo "$1 W=$2 R=$3 $r" | tee -a $out
 }
-for W in "" 2 3 4 5 7; do run config2 "$W" ""; done
+for W in "" 2 3 4 5 6 7 10; do run config2 "$W" ""; done
+run config2 4 0; run config2 4 1; run config2 4 2; run config2 3 0
 for W in "" 1 2 3; do run config5 "$W" ""; done
-for W in "" 9 12 16 27; do run target "$W" ""; done
+run config5 1 0; run config5 1 1; run config5 1 2
+for W in "" 9 12 16 20 27; do run target "$W" ""; done
 run target 16 0; run target 16 1; run target 16 2
