@@ -17,7 +17,7 @@ OK = 0
 ERR_NO_DEVICE, ERR_BAD_ARG, ERR_TOO_LONG, ERR_CUDA, ERR_ALLOC = -1, -2, -3, -4, -5
 NCOUNTS = 7
 KERNEL_TILED, KERNEL_NAIVE = 0, 1
-PERSPECTIVE = {"global": 0, "local": 1}
+PERSPECTIVE = {"global": 0, "local": 1, "complete": 2}
 ALTERNATIVE = {"two.sided": 0, "less": 1, "greater": 2}
 
 # every symbol include/icikt_b200.h declares (checked by tests/test_abi_cpu.py)

@@ -309,22 +309,24 @@ def kt_fast(x, y=None, use="everything", alternative="two.sided", continuity=Fal
     if do:
         kw = dict(perspective="local", alternative="two.sided", continuity=False, device=device)
         if na_method == "pairwise.complete.obs" and np.isnan(data).any():
-            # Pairs with a missing row in either column are filtered per pair (:323-331) and run as
-            # two-column problems; all other pairs go out in one batched call.
-            col_na = np.isnan(data).any(axis=0)
-            clean = ~(col_na[pi] | col_na[pj])
-            if clean.any():
-                r = _lib.run_pairs(data, (), pi=pi[clean], pj=pj[clean], **kw)
-                _warn_status(r["status"])
-                tau[clean], pv[clean] = r["raw"], r["pvalue"]
-            for k in np.nonzero(~clean)[0]:
+            # Rows with a missing value in either column are dropped per pair (:323-331).  The pair
+            # kernel does that on the device (complete-observations mode); only pairs it flags as
+            # unsupported (a column whose missing rows tie with its minimum in fp64) are filtered
+            # here and run as two-column problems.
+            r = _lib.run_pairs(data, (), include_diag=True, **dict(kw, perspective="complete"))
+            tau, pv = r["raw"].copy(), r["pvalue"].copy()
+            redo = np.nonzero(r["status"] == 9)[0]
+            r["status"][redo] = 0
+            _warn_status(r["status"])
+            for k in redo:
                 good = ~np.isnan(data[:, pi[k]]) & ~np.isnan(data[:, pj[k]])
+                tau[k] = pv[k] = np.nan
                 if good.sum() == 0:
                     continue
                 sub = np.column_stack([data[good, pi[k]], data[good, pj[k]]])
-                r = _lib.run_pairs(sub, (), pi=[0], pj=[1], **kw)
-                _warn_status(r["status"])
-                tau[k], pv[k] = r["raw"][0], r["pvalue"][0]
+                r2 = _lib.run_pairs(sub, (), pi=[0], pj=[1], **kw)
+                _warn_status(r2["status"])
+                tau[k], pv[k] = r2["raw"][0], r2["pvalue"][0]
         else:
             r = _lib.run_pairs(data, (), include_diag=True, **kw)
             _warn_status(r["status"])

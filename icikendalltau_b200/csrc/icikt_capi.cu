@@ -71,6 +71,7 @@ struct icikt_plan {
   PairUnit* d_units = nullptr;
   int32_t* d_pj = nullptr;
   PairRaw* d_raw = nullptr;
+  PairComplete* d_pw = nullptr;  // complete-observations mode
   // results, packed in one allocation so that one copy brings them to the host:
   // [tau P][pvalue P][taumax P][completeness P] doubles, [max taumax bits] u64, [status P] int32
   unsigned char* d_res = nullptr;
@@ -102,6 +103,7 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->tab.nabits);
   cudaFree(p->tab.firstbits);
   cudaFree(p->tab.grpstart);
+  cudaFree(p->tab.gstart);
   cudaFree(p->tab.stats);
   cudaFree(p->tab.max_tied);
   cudaFree(p->wk.keys_in);
@@ -114,6 +116,7 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->d_units);
   cudaFree(p->d_pj);
   cudaFree(p->d_raw);
+  cudaFree(p->d_pw);
   cudaFree(p->d_res);
   if (p->h_res) cudaFreeHost(p->h_res);
   cudaFree(p->d_counts);
@@ -294,6 +297,8 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.nabits, nw));
   PCK(dmalloc(&t.firstbits, nw));
   PCK(dmalloc(&t.grpstart, nw));
+  t.gstride = t.nstride + 64;
+  PCK(dmalloc(&t.gstart, (size_t)t.gstride * C));
   PCK(dmalloc(&t.stats, (size_t)C));
   PCK(dmalloc(&t.max_tied, 1));
   // padding words of the bit arrays (beyond n32/32) are never written by the kernels
@@ -321,6 +326,7 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
     PCK(cudaMemcpyAsync(p->d_pj, pj, sizeof(int32_t) * np, cudaMemcpyHostToDevice, p->stream));
   }
   PCK(dmalloc(&p->d_raw, np));
+  if (o.perspective == ICIKT_PERSPECTIVE_COMPLETE) PCK(dmalloc(&p->d_pw, np));
   p->res_bytes = np * (4 * sizeof(double) + sizeof(int32_t)) + sizeof(unsigned long long);
   PCK(cudaMalloc(reinterpret_cast<void**>(&p->d_res), p->res_bytes));
   p->d_tau = reinterpret_cast<double*>(p->d_res);
@@ -428,11 +434,14 @@ int icikt_plan_pairs(icikt_plan* p) {
   pl.n_units = (int64_t)p->units.size();
   pl.pj_list = p->d_pj;
   pl.raw = p->d_raw;
+  pl.pw = (p->opts.perspective == ICIKT_PERSPECTIVE_COMPLETE) ? p->d_pw : nullptr;
   pl.unit_counter = p->d_scalars;
   pl.scratch = p->d_scratch;
   int launches = 0;
   if (p->P > 0) {
     int l;
+    if (pl.pw && p->opts.kernel == ICIKT_KERNEL_NAIVE)
+      return fail(ICIKT_ERR_BAD_ARG, "the complete-observations mode needs the tiled kernel");
     if (p->opts.kernel == ICIKT_KERNEL_NAIVE)
       l = launch_pairs_naive(pl, p->P, p->d_naive, p->naive_threads, p->stream);
     else {
@@ -454,6 +463,7 @@ int icikt_plan_pairs(icikt_plan* p) {
     el.n_units = pl.n_units;
     el.pj_list = p->d_pj;
     el.raw = p->d_raw;
+    el.pw = pl.pw;
     el.perspective = p->opts.perspective;
     el.alternative = p->opts.alternative;
     el.continuity = p->opts.continuity;
@@ -581,7 +591,8 @@ static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const 
   icikt_plan* p = nullptr;
   const bool cacheable = (pi == nullptr);
   int rc = ICIKT_OK;
-  if (cacheable && cache_matches(g_cached, n, C, o)) {
+  if (cacheable && cache_matches(g_cached, n, C, o) &&
+      (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || g_cached->d_pw)) {
     p = g_cached;
     p->opts.perspective = o.perspective;
     p->opts.alternative = o.alternative;

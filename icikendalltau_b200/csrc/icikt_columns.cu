@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         const double* __restrict__ global_na, int n_global_na, int na_inf,
                         uint16_t* __restrict__ perm, uint16_t* __restrict__ rank, uint16_t* __restrict__ trow,
                         uint16_t* __restrict__ trun, uint32_t* __restrict__ nabits,
-                        uint32_t* __restrict__ firstbits, ColStats* __restrict__ stats,
-                        int32_t* __restrict__ max_tied) {
+                        uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
+                        ColStats* __restrict__ stats, int32_t* __restrict__ max_tied) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
   }
   if (tid == 0) gpos[K] = (uint16_t)n;  // n <= 8192 here
   __syncthreads();
+  for (int g = tid; g <= K; g += SORT_THREADS) gstart[(size_t)col * gstride + g] = gpos[g];
   // tie sums over group sizes (count_rank_tie, :103-118), exact int64
   long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
   for (int g = tid; g < K; g += SORT_THREADS) {
@@ -272,8 +273,8 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
-                                                        tab.trow, tab.trun, tab.nabits, tab.firstbits, tab.stats,
-                                                        tab.max_tied);
+                                                        tab.trow, tab.trun, tab.nabits, tab.firstbits, tab.gstart,
+                                                        (int)tab.gstride, tab.stats, tab.max_tied);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -282,8 +283,8 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        uint16_t* __restrict__ perm, uint16_t* __restrict__ rank,
                        uint16_t* __restrict__ trow, uint16_t* __restrict__ trun,
                        uint32_t* __restrict__ firstbits, uint32_t* __restrict__ grpstart,
-                       uint32_t* __restrict__ gpos_all, ColStats* __restrict__ stats,
-                       int32_t* __restrict__ max_tied) {
+                       uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
+                       ColStats* __restrict__ stats, int32_t* __restrict__ max_tied) {
   __shared__ int warp_sums[32];
   __shared__ long long llbuf[32];
   __shared__ uint32_t bits[2048];
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
   const int K = carry;
   if (tid == 0) gpos[K] = (uint32_t)n;
   __syncthreads();
+  for (int g = tid; g <= K; g += RANK_THREADS) gstart_tab[(size_t)col * gstride + g] = (uint16_t)gpos[g];  // n <= 65535
 
   // tie sums over group sizes (count_rank_tie, src/kendallc.cpp:103-118), exact int64
   long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
@@ -463,7 +465,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                        tab.trow, tab.trun, tab.firstbits, tab.grpstart,
-                                                       wk.gpos, tab.stats, tab.max_tied);
+                                                       wk.gpos, tab.gstart, (int)tab.gstride, tab.stats, tab.max_tied);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
   }

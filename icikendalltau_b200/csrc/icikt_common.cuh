@@ -116,48 +116,23 @@ ICIKT_HD double pnorm_std(double x, bool lower_tail) {
 
 ICIKT_HD double qnan() { return nan(""); }
 
-// One pair's results from the integer counts.
-//   n        : vector length (features)
-//   X, Y     : per-column statistics of the two columns
-//   dis      : #{(p,q): x_p < x_q and y_p > y_q}            (kendall_discordant, :70-100)
-//   ntie_g   : sum over joint (x,y) tie groups g(g-1)/2 on all n rows (:261-267)
-//   b        : rows missing in both columns
-//   g00      : rows in the lowest tie group of both columns (== b unless a column's missing
-//              rows tie with its minimum, SURVEY.md 8a row 3)
-ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int64_t dis,
-                            int64_t ntie_g, int64_t b, int64_t g00, int perspective,
-                            int alternative, int continuity, PairOut& o) {
-  const double NA = qnan();
-  o.tau = o.pvalue = o.taumax = o.completeness = NA;
-  o.xtie = o.ytie = o.tot = o.ntie = 0;
-  o.status = 0;
-  const int64_t bb = (perspective == 1) ? b : 0;  // local drops the joint-missing rows (:180-185)
-  const int64_t np = n - bb;
-  o.n_entry = np;
-  const int64_t a = X.n_na, c = Y.n_na;
-  if (a == n || c == n) { o.status = 1; return; }  // :190-199 (a-bb == n-bb  <=>  a == n)
-  if (np < 2) { o.status = 2; return; }            // :224-231
-  // group 0 after removing the joint-missing rows
-  const int64_t t0x = (a > 0) ? (a - bb) + X.g0extra : 0;
-  const int64_t t0y = (c > 0) ? (c - bb) + Y.g0extra : 0;
-  const int64_t kx = (int64_t)X.n_groups - (a > 0 ? 1 : 0) + (t0x > 0 ? 1 : 0);
-  const int64_t ky = (int64_t)Y.n_groups - (c > 0 ? 1 : 0) + (t0y > 0 ? 1 : 0);
-  if (kx == 1 || ky == 1) { o.status = 3; return; }  // :234-244
+// tau, tau_max and the variance-based p-value from the exact integer counts of one pair
+// (src/kendallc.cpp:280-335).  s2/s3/s5 are the column's sums of t(t-1), t(t-1)(t-2), t(t-1)(2t+5)
+// over its tie groups on the np rows that enter.  Sets status 4 and returns false if every pair
+// of rows is tied in x or in y (:291-298).
+ICIKT_HD bool tau_from_counts(int64_t np, int64_t xs2, int64_t xs3, int64_t xs5, int64_t ys2, int64_t ys3,
+                              int64_t ys5, int64_t ntie, int64_t dis, int alternative, int continuity,
+                              PairOut& o) {
   // count_rank_tie, :103-118 (sums are exact int64 here; the reference's are int32)
-  const int64_t xtie = (X.s2o + t0x * (t0x - 1)) / 2;
-  const int64_t ytie = (Y.s2o + t0y * (t0y - 1)) / 2;
-  const double x0 = (double)((X.s3o + t0x * (t0x - 1) * (t0x - 2)) / 2);
-  const double y0 = (double)((Y.s3o + t0y * (t0y - 1) * (t0y - 2)) / 2);
-  const double x1 = (double)(X.s5o + t0x * (t0x - 1) * (2 * t0x + 5));
-  const double y1 = (double)(Y.s5o + t0y * (t0y - 1) * (2 * t0y + 5));
-  // the joint group (lowest x group, lowest y group) shrinks from g00 to g00 - bb rows
-  const int64_t ntie = ntie_g - g00 * (g00 - 1) / 2 + (g00 - bb) * (g00 - bb - 1) / 2;
+  const int64_t xtie = xs2 / 2, ytie = ys2 / 2;
+  const double x0 = (double)(xs3 / 2), y0 = (double)(ys3 / 2);
+  const double x1 = (double)xs5, y1 = (double)ys5;
   o.ntie = ntie;
   const int64_t tot = np * (np - 1) / 2;  // :280
   o.xtie = xtie;
   o.ytie = ytie;
   o.tot = tot;
-  if (xtie == tot || ytie == tot) { o.status = 4; return; }  // :291-298
+  if (xtie == tot || ytie == tot) { o.status = 4; return false; }  // :291-298
   // :300-308
   const double dxt = (double)xtie, dyt = (double)ytie;
   const double den = sqrt(((double)tot - dxt) * ((double)tot - dyt));
@@ -189,10 +164,77 @@ ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int
   o.tau = tau;
   o.pvalue = pv;
   o.taumax = tau_max;
+  return true;
+}
+
+// One pair's results from the integer counts.
+//   n        : vector length (features)
+//   X, Y     : per-column statistics of the two columns
+//   dis      : #{(p,q): x_p < x_q and y_p > y_q}            (kendall_discordant, :70-100)
+//   ntie_g   : sum over joint (x,y) tie groups g(g-1)/2 on all n rows (:261-267)
+//   b        : rows missing in both columns
+//   g00      : rows in the lowest tie group of both columns (== b unless a column's missing
+//              rows tie with its minimum, SURVEY.md 8a row 3)
+ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int64_t dis,
+                            int64_t ntie_g, int64_t b, int64_t g00, int perspective,
+                            int alternative, int continuity, PairOut& o) {
+  const double NA = qnan();
+  o.tau = o.pvalue = o.taumax = o.completeness = NA;
+  o.xtie = o.ytie = o.tot = o.ntie = 0;
+  o.status = 0;
+  const int64_t bb = (perspective == 1) ? b : 0;  // local drops the joint-missing rows (:180-185)
+  const int64_t np = n - bb;
+  o.n_entry = np;
+  const int64_t a = X.n_na, c = Y.n_na;
+  if (a == n || c == n) { o.status = 1; return; }  // :190-199 (a-bb == n-bb  <=>  a == n)
+  if (np < 2) { o.status = 2; return; }            // :224-231
+  // group 0 after removing the joint-missing rows
+  const int64_t t0x = (a > 0) ? (a - bb) + X.g0extra : 0;
+  const int64_t t0y = (c > 0) ? (c - bb) + Y.g0extra : 0;
+  const int64_t kx = (int64_t)X.n_groups - (a > 0 ? 1 : 0) + (t0x > 0 ? 1 : 0);
+  const int64_t ky = (int64_t)Y.n_groups - (c > 0 ? 1 : 0) + (t0y > 0 ? 1 : 0);
+  if (kx == 1 || ky == 1) { o.status = 3; return; }  // :234-244
+  // the joint group (lowest x group, lowest y group) shrinks from g00 to g00 - bb rows
+  const int64_t ntie = ntie_g - g00 * (g00 - 1) / 2 + (g00 - bb) * (g00 - bb - 1) / 2;
+  if (!tau_from_counts(np, X.s2o + t0x * (t0x - 1), X.s3o + t0x * (t0x - 1) * (t0x - 2),
+                       X.s5o + t0x * (t0x - 1) * (2 * t0x + 5), Y.s2o + t0y * (t0y - 1),
+                       Y.s3o + t0y * (t0y - 1) * (t0y - 2), Y.s5o + t0y * (t0y - 1) * (2 * t0y + 5), ntie,
+                       dis, alternative, continuity, o))
+    return;
   // :205-212  completeness = 1 - card(NA_x or NA_y) / length, evaluated as one correctly
   // rounded quotient (the reference uses x87 long double and rounds once at the end)
   const int64_t miss = a + c - b - bb;
   o.completeness = (double)(np - miss) / (double)np;
+}
+
+// Counts of one pair restricted to the rows present in BOTH columns (kt_fast with
+// use = "pairwise.complete.obs": kt_split drops the rows missing in either column and calls
+// ici_kt on what is left, R/kendalltau.R:323-341).  Produced by the pair kernel in its
+// complete-observations mode from the global counts, two rank histograms and the group-start
+// tables; x/y are the kernel's streamed / staged column (tau is symmetric in them).
+struct PairComplete {
+  int64_t n_rows;           // rows present in both columns
+  int64_t dis, ntie;        // discordant pairs / joint ties among those rows
+  int64_t xs2, xs3, xs5;    // tie sums of x on those rows
+  int64_t ys2, ys3, ys5;
+  int32_t kx, ky;           // distinct values of x / y on those rows
+  int32_t unsupported, pad;  // 1: a column's missing rows tie with its minimum (host path needed)
+};
+
+ICIKT_HD void pair_epilogue_complete(const PairComplete& c, int alternative, int continuity, PairOut& o) {
+  const double NA = qnan();
+  o.tau = o.pvalue = o.taumax = o.completeness = NA;
+  o.xtie = o.ytie = o.tot = o.ntie = 0;
+  o.status = 0;
+  o.n_entry = c.n_rows;
+  if (c.unsupported) { o.status = 9; return; }
+  if (c.n_rows == 0) { o.status = 1; return; }  // kt_split leaves NA without calling ici_kt
+  if (c.n_rows < 2) { o.status = 2; return; }   // :224-231
+  if (c.kx == 1 || c.ky == 1) { o.status = 3; return; }  // :234-244
+  if (!tau_from_counts(c.n_rows, c.xs2, c.xs3, c.xs5, c.ys2, c.ys3, c.ys5, c.ntie, c.dis, alternative,
+                       continuity, o))
+    return;
+  o.completeness = 1.0;  // no missing value is left in the two vectors (:205-212)
 }
 
 }  // namespace icikt

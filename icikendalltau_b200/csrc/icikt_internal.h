@@ -21,7 +21,9 @@ struct ColumnTables {
   uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1)
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
-  uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group
+  uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group (long-column path only)
+  uint16_t* gstart = nullptr;     // [C][gstride] sorted position where the group of dense rank r starts; [K] = n
+  int64_t gstride = 0;            // nstride + 64
   ColStats* stats = nullptr;      // [C]
   int32_t* max_tied = nullptr;    // [1] max over columns of ColStats::n_tied
 };
@@ -60,6 +62,7 @@ struct PairLaunch {
   int64_t n_units;
   const int32_t* pj_list;  // device, may be null
   PairRaw* raw;            // device [P]
+  PairComplete* pw = nullptr;  // device [P], complete-observations mode only
   unsigned long long* unit_counter;  // device, zeroed by the launcher
   unsigned char* scratch = nullptr;  // device, global-memory variant only: max_ctas * region_bytes
 };
@@ -102,6 +105,7 @@ struct EpilogueLaunch {
   int64_t n_units;
   const int32_t* pj_list;
   const PairRaw* raw;
+  const PairComplete* pw = nullptr;
   int perspective, alternative, continuity;
   double* tau;
   double* pvalue;

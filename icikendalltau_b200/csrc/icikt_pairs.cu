@@ -438,29 +438,47 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
   }
 }
 
-// First x tie group (the missing rows): writes the y-ranks of its f rows into buf[0, f) in
-// ascending order, so that the group contributes no inversions, and returns (summed over the
-// threads) its joint ties with y, sum over y ranks of C(count, 2).  The sorted sequence is fully
-// described by a histogram over the K ranks of y, so nothing is moved:
-//   1. hist[rank_y[row]]++ for the f rows (perm_x[0..f) are exactly the group's rows), 16-bit
-//      counters packed two per word, shared-memory atomics;
-//   2. every thread folds a contiguous range of counters, one block scan gives its output slot;
-//   3. it writes `count` copies of each of its ranks; ranks with a long run (the rows missing in
-//      both columns, heavy ties) are parked in a short list and written by the whole CTA.
-// The histogram lives at the top of `buf` (which the gather fills afterwards), above the f output
-// slots; if the K counters do not fit there the ranks are processed in several rounds, and if
-// not even 32 fit, in a 16-word spare in shared memory.  Cost ~ 8 f + 7 K instead of ~ 38 n
-// for an ordered compaction of y's sorted order through x's membership mask.
-template <bool G>
-__device__ __forceinline__ uint32_t emit_first_group(typename Mem<G>::ptr buf, const int cap, const int f,
-                                                     const int K, const uint16_t* __restrict__ permX,
-                                                     typename Mem<G>::ptr rank_tbl,
-                                                     uint32_t* __restrict__ mini, uint32_t* __restrict__ list,
-                                                     const int list_cap, uint32_t* descT, uint32_t* list_n,
-                                                     const int nwarps) {
+// Per-thread sums of the complete-observations mode for one side of a pair (see group_hist).
+struct PwSide {
+  unsigned long long S = 0;   // sum over the group's rows of (present rows of the other column below it)
+  unsigned long long T = 0;   // ties of the group's present rows in the other column, sum C(count, 2)
+  unsigned long long s2 = 0, s3 = 0, s5 = 0;  // tie sums of the other column without the group's rows
+  uint32_t k = 0;             // distinct values of the other column left without the group's rows
+};
+
+// Rank histogram of a group of rows (x's first tie group -- in particular its missing rows) over
+// the dense ranks of another column.
+//   EMIT: writes the ranks of the `nrows` rows into buf[0, nrows) in ascending order, so that the
+//   group contributes no inversions, and returns (summed over the threads) its joint ties with the
+//   other column, sum over ranks of C(count, 2).  The sorted sequence is fully described by the
+//   histogram, so nothing is moved:
+//     1. hist[rank[row]]++ for the rows, 16-bit counters packed two per word, shared-memory atomics
+//        (rank 0 -- the rows missing in both columns, by far the fullest counter -- by ballot);
+//     2. every thread folds a contiguous range of counters, one block scan gives its output slot;
+//     3. it writes `count` copies of each of its ranks; ranks with a long run are parked in a short
+//        list and written by the whole CTA.
+//   The histogram lives at the top of `buf` (which the gather fills afterwards), above the `keep`
+//   slots at the bottom that must survive; if the K counters do not fit there the ranks are
+//   processed in several rounds, and if not even 32 fit, in a 16-word spare in shared memory.
+//   Cost ~ 8 nrows + 7 K instead of ~ 38 n for an ordered compaction of the other column's sorted
+//   order through the group's membership mask.
+//   PW (complete-observations mode, kt_fast use = "pairwise.complete.obs"): the same sweep over
+//   the counters also yields, from the other column's group-start table, everything needed to
+//   take the group's rows out of the pair: see PwSide.  `a_tbl` = missing rows of the other column.
+//   GT: the rank table is read from global memory instead of the staged copy.
+template <bool G, bool EMIT, bool PW, bool GT>
+__device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const int cap, const int keep,
+                                               const int nrows, const int K,
+                                               const uint16_t* __restrict__ rows,
+                                               typename Mem<G>::ptr rank_tbl,
+                                               const uint16_t* __restrict__ rank_g,
+                                               uint32_t* __restrict__ mini, uint32_t* __restrict__ list,
+                                               const int list_cap, uint32_t* descT, uint32_t* list_n,
+                                               const int nwarps, const uint16_t* __restrict__ gstart,
+                                               const int a_tbl, PwSide& pw) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
-  int hw = (cap - ((f + 1) & ~1)) >> 1;            // counter words available above the output slots
+  int hw = (cap - ((keep + 1) & ~1)) >> 1;         // counter words available above the kept slots
   typename M::ptr hist = M::add(buf, 2 * cap - 4 * hw);
   if (hw < 16) {
     hw = 16;
@@ -469,28 +487,28 @@ __device__ __forceinline__ uint32_t emit_first_group(typename Mem<G>::ptr buf, c
   const int kw = (K + 1) >> 1;                     // counter words needed
   if (hw > kw) hw = kw;
   const int wpt = (hw + T - 1) / T;                // words per thread
+  const uint32_t r0 = a_tbl > 0 ? 1u : 0u;         // first rank of the other column that is a value
   uint32_t ties = 0, done = 0;                     // done: output slots filled by earlier rounds
   for (int k0 = 0; k0 < K; k0 += 2 * hw) {
     for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
     if (tid == 0) *list_n = 0u;
     __syncthreads();
-    {  // 1. histogram of the group's y ranks inside [k0, k0 + 2 hw).  Rank 0 of the first round
-       // (the rows missing in both columns, by far the fullest counter) is counted per warp by
-       // ballot instead of same-address atomics.
-      const uint4* px8 = reinterpret_cast<const uint4*>(permX);
+    {  // 1. histogram of the rows' ranks inside [k0, k0 + 2 hw)
+      const uint4* px8 = reinterpret_cast<const uint4*>(rows);
       const uint32_t span = (uint32_t)(2 * hw);
-      const int lim8 = (f + 7) >> 3;
+      const int lim8 = (nrows + 7) >> 3;
       uint32_t zeros = 0;
       for (int q8w = tid & ~31; q8w < lim8; q8w += T) {  // warp-uniform trip count
         const int q8 = q8w + lane;
         uint4 pv = make_uint4(0u, 0u, 0u, 0u);
         if (q8 < lim8) pv = __ldg(px8 + q8);  // perm is readable up to nstride (multiple of 64)
-        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+        const uint32_t pwd[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t row = (j & 1) ? (pw[j >> 1] >> 16) : (pw[j >> 1] & 0xffffu);
+          const uint32_t row = (j & 1) ? (pwd[j >> 1] >> 16) : (pwd[j >> 1] & 0xffffu);
           uint32_t r = 0xffffffffu;
-          if ((q8 << 3) + j < f) r = M::ld16(M::add(rank_tbl, (int32_t)(row << 1))) - (uint32_t)k0;
+          if ((q8 << 3) + j < nrows)
+            r = (GT ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)))) - (uint32_t)k0;
           const bool z = (r == 0u);
           zeros += __popc(__ballot_sync(FULL, z));
           if (r < span && !z) M::red_add32(M::add(hist, (int32_t)((r >> 1) << 2)), (r & 1u) ? 0x10000u : 1u);
@@ -501,54 +519,73 @@ __device__ __forceinline__ uint32_t emit_first_group(typename Mem<G>::ptr buf, c
     __syncthreads();
     // 2. rows per thread range, block scan
     const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
-    uint32_t mine = 0;
-    for (int w = w0; w < w1; ++w) {
-      const uint32_t c = M::ld32(M::add(hist, w << 2));
-      mine += (c & 0xffffu) + (c >> 16);
-    }
-    uint32_t incl = mine;
+    uint32_t pos = 0, total = 0;
+    if (EMIT) {
+      uint32_t mine = 0;
+      for (int w = w0; w < w1; ++w) {
+        const uint32_t c = M::ld32(M::add(hist, w << 2));
+        mine += (c & 0xffffu) + (c >> 16);
+      }
+      uint32_t incl = mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl += t;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) descT[warp] = incl;
+      __syncthreads();
+      const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+      total = __reduce_add_sync(FULL, v);
+      pos = done + __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
     }
-    if (lane == 31) descT[warp] = incl;
-    __syncthreads();
-    const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
-    const uint32_t total = __reduce_add_sync(FULL, v);
-    uint32_t pos = done + __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
-    // 3. write the runs
+    // 3. write the runs / sum up
     for (int w = w0; w < w1; ++w) {
       const uint32_t cw = M::ld32(M::add(hist, w << 2));
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
         const uint32_t r = (uint32_t)k0 + 2u * (uint32_t)w + (uint32_t)h;
-        if (c == 1u) {
-          M::st16(M::add(buf, (int32_t)(pos << 1)), r);
-        } else if (c > 1u) {
-          ties += (c * (c - 1u)) >> 1;
-          uint32_t slot = 0xffffffffu;
-          if (c >= 48u) slot = atomicAdd(list_n, 1u);
-          if (slot < (uint32_t)list_cap) {
-            list[3 * slot + 0] = r;
-            list[3 * slot + 1] = pos;
-            list[3 * slot + 2] = c;
-          } else {
-            for (uint32_t j = 0; j < c; ++j) M::st16(M::add(buf, (int32_t)((pos + j) << 1)), r);
+        if (PW && r >= r0 && r < (uint32_t)K) {
+          const unsigned long long gs = gstart[r], sz = (unsigned long long)gstart[r + 1] - gs;
+          const unsigned long long t = sz - c;  // rows of this value left without the group's rows
+          pw.S += (unsigned long long)c * (gs - (unsigned long long)a_tbl);
+          pw.T += ((unsigned long long)c * (c - (c ? 1u : 0u))) >> 1;
+          pw.k += (t > 0);
+          if (t > 1) {
+            pw.s2 += t * (t - 1);
+            pw.s3 += t * (t - 1) * (t - 2);
+            pw.s5 += t * (t - 1) * (2 * t + 5);
           }
         }
-        pos += c;
+        if (EMIT) {
+          if (c == 1u) {
+            M::st16(M::add(buf, (int32_t)(pos << 1)), r);
+          } else if (c > 1u) {
+            ties += (c * (c - 1u)) >> 1;
+            uint32_t slot = 0xffffffffu;
+            if (c >= 48u) slot = atomicAdd(list_n, 1u);
+            if (slot < (uint32_t)list_cap) {
+              list[3 * slot + 0] = r;
+              list[3 * slot + 1] = pos;
+              list[3 * slot + 2] = c;
+            } else {
+              for (uint32_t j = 0; j < c; ++j) M::st16(M::add(buf, (int32_t)((pos + j) << 1)), r);
+            }
+          }
+          pos += c;
+        }
       }
     }
     done += total;
     __syncthreads();
-    const uint32_t nl = min(*list_n, (uint32_t)list_cap);
-    for (uint32_t e = 0; e < nl; ++e) {
-      const uint32_t r = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
-      for (uint32_t j = tid; j < c; j += T) M::st16(M::add(buf, (int32_t)((off + j) << 1)), r);
+    if (EMIT) {
+      const uint32_t nl = min(*list_n, (uint32_t)list_cap);
+      for (uint32_t e = 0; e < nl; ++e) {
+        const uint32_t r = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
+        for (uint32_t j = tid; j < c; j += T) M::st16(M::add(buf, (int32_t)((off + j) << 1)), r);
+      }
+      __syncthreads();  // the list and the counters are reused by the next round / overwritten by the gather
     }
-    __syncthreads();  // the list and the counters are reused by the next round / overwritten by the gather
   }
   return ties;
 }
@@ -570,6 +607,9 @@ struct TiledParams {
   const PairUnit* units;
   const int32_t* pj_list;
   PairRaw* raw;
+  PairComplete* pw;              // complete-observations mode: per-pair counts on the shared rows
+  const uint16_t* gstart;        // [C][gstride] group-start table (complete-observations mode)
+  int gstride;
   unsigned long long* unit_counter;
   unsigned char* scratch;        // global-memory variant: per-CTA ping-pong region
   long long scratch_stride;      // bytes per CTA
@@ -633,7 +673,36 @@ __device__ __forceinline__ unsigned char* region_base<true>(const Carve&, const 
 
 // MAXT/MINB only steer the register allocation (occupancy classes); G selects where the
 // ping-pong buffers live (shared memory, or an L2-resident global scratch for long vectors).
-template <int MAXT, int MINB, bool G>
+// sums four per-thread values over the CTA; the totals are valid in thread 0
+__device__ __forceinline__ void block_sum4(unsigned long long* red, int nwarps, unsigned long long& a,
+                                           unsigned long long& b, unsigned long long& c, unsigned long long& d) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  a = warp_sum_u64(a);
+  b = warp_sum_u64(b);
+  c = warp_sum_u64(c);
+  d = warp_sum_u64(d);
+  __syncthreads();
+  if (lane == 0) {
+    red[warp * 4 + 0] = a;
+    red[warp * 4 + 1] = b;
+    red[warp * 4 + 2] = c;
+    red[warp * 4 + 3] = d;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    a = b = c = d = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      a += red[w * 4 + 0];
+      b += red[w * 4 + 1];
+      c += red[w * 4 + 2];
+      d += red[w * 4 + 3];
+    }
+  }
+}
+
+// PW: complete-observations mode (kt_fast use = "pairwise.complete.obs"): besides the global
+// counts the kernel takes the rows missing in either column out of the pair, see PairComplete.
+template <int MAXT, int MINB, bool G, bool PW>
 __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledParams p) {
   typedef Mem<G> M;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -701,11 +770,20 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
           r.b = (long long)bb;
           r.g00 = (long long)bb;
           p.raw[slot] = r;
+          if (PW) {  // a column without two distinct values: 0 rows -> NA, 1 row -> too short, else single value
+            PairComplete c{};
+            c.n_rows = (long long)n - XS.n_na - YS.n_na + (long long)bb;
+            c.kx = c.ky = 1;
+            c.unsupported = absorbed ? 1 : 0;
+            p.pw[slot] = c;
+          }
         }
         __syncthreads();
         continue;
       }
-      const int f = XS.first_run;
+      // complete-observations mode: the missing rows of x are taken out even if there is only one
+      const int f = (PW && XS.n_na > 0) ? XS.n_na : XS.first_run;
+      PwSide pwy, pwx;  // y without x's missing rows / x without y's missing rows
       uint32_t ties = 0;
       if (!G) {  // dense ranks of y go to the second ping-pong buffer until pass A starts
         const uint4* src = reinterpret_cast<const uint4*>(rankY_g);
@@ -716,9 +794,21 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         __syncthreads();
       }
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
-      if (f > 0)
-        ties = emit_first_group<G>(bufA, cap, f, YS.n_groups, permX, rank_tbl, sm.mini, sm.fmask,
-                                   fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16, nwarps);
+      if (f > 0) {
+        if (PW && XS.n_na > 0)
+          ties = group_hist<G, true, true, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
+                                                  sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
+                                                  nwarps, p.gstart + (size_t)ycol * p.gstride, YS.n_na, pwy);
+        else
+          ties = group_hist<G, true, false, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
+                                                   sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
+                                                   nwarps, nullptr, 0, pwy);
+      }
+      if (PW && YS.n_na > 0)  // the missing rows of y over the ranks of x (read from global memory)
+        group_hist<G, false, true, true>(bufA, cap, f, YS.n_na, XS.n_groups, p.perm + (size_t)ycol * p.nstride,
+                                         rank_tbl, p.rank + (size_t)xcol * p.nstride, sm.mini, sm.fmask,
+                                         fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16, nwarps,
+                                         p.gstart + (size_t)xcol * p.gstride, XS.n_na, pwx);
       {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
         const uint4* px8 = reinterpret_cast<const uint4*>(permX);
         for (int q8 = (f >> 3) + tid; q8 < (cap >> 3); q8 += T) {
@@ -777,6 +867,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         sm.red[warp * 4 + 3] = sb;
       }
       __syncthreads();
+      long long g_dis = 0, g_ntie = 0, g_b = 0;
       if (tid == 0) {
         unsigned long long a = 0, b2 = 0, t2 = 0, bb = 0;
         for (int w = 0; w < nwarps; ++w) {
@@ -791,6 +882,46 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         r.b = (long long)(bb & 0xffffffffull);
         r.g00 = absorbed ? (long long)(bb >> 32) : r.b;
         p.raw[slot] = r;
+        g_dis = r.dis;
+        g_ntie = r.ntie;
+        g_b = r.b;
+      }
+      if (PW) {
+        unsigned long long kxy = ((unsigned long long)pwx.k << 32) | pwy.k, z0 = 0, z1 = 0;
+        block_sum4(sm.red, nwarps, pwy.S, pwy.T, pwx.S, pwx.T);
+        block_sum4(sm.red, nwarps, pwy.s2, pwy.s3, pwy.s5, kxy);
+        block_sum4(sm.red, nwarps, pwx.s2, pwx.s3, pwx.s5, z0);
+        (void)z1;
+        if (tid == 0) {
+          const long long ax = XS.n_na, ay = YS.n_na, b = g_b;
+          const long long xm = ax - b, ym = ay - b;  // missing in x only / in y only
+          const long long t1 = ax > 0 ? (long long)pwy.T : 0, t2 = ay > 0 ? (long long)pwx.T : 0;
+          // discordant pairs of the global count with a row missing in one column (NA below every
+          // value): x-missing row above a shared row in y, shared row below a y-missing row in x,
+          // x-missing row against y-missing row
+          const long long c1 = ax > 0 ? (long long)pwy.S - xm * (xm - 1) / 2 + t1 : 0;
+          const long long c2 = ay > 0 ? (long long)pwx.S - ym * (ym - 1) / 2 + t2 : 0;
+          PairComplete c{};
+          c.n_rows = (long long)n - ax - ay + b;
+          c.dis = g_dis - c1 - c2 - xm * ym;
+          c.ntie = g_ntie - b * (b - 1) / 2 - t1 - t2;
+          if (ay > 0) {
+            c.xs2 = (long long)pwx.s2; c.xs3 = (long long)pwx.s3; c.xs5 = (long long)pwx.s5;
+            c.kx = (int32_t)(kxy >> 32);
+          } else {
+            c.xs2 = XS.s2o; c.xs3 = XS.s3o; c.xs5 = XS.s5o;
+            c.kx = XS.n_groups - (ax > 0 ? 1 : 0);
+          }
+          if (ax > 0) {
+            c.ys2 = (long long)pwy.s2; c.ys3 = (long long)pwy.s3; c.ys5 = (long long)pwy.s5;
+            c.ky = (int32_t)(kxy & 0xffffffffull);
+          } else {
+            c.ys2 = YS.s2o; c.ys3 = YS.s3o; c.ys5 = YS.s5o;
+            c.ky = YS.n_groups - (ay > 0 ? 1 : 0);
+          }
+          c.unsupported = absorbed ? 1 : 0;
+          p.pw[slot] = c;
+        }
       }
       __syncthreads();
     }
@@ -917,6 +1048,7 @@ struct EpiParams {
   const PairUnit* units;
   const int32_t* pj_list;
   const PairRaw* raw;
+  const PairComplete* pw;  // complete-observations mode (else null)
   double* tau;
   double* pvalue;
   double* taumax;
@@ -939,11 +1071,21 @@ __global__ void __launch_bounds__(128) epilogue_kernel(const EpiParams p) {
     for (int k = lane; k < unit.count; k += 32) {
       const long long slot = unit.slot0 + k;
       const int xcol = unit.j_explicit ? p.pj_list[slot] : unit.j0 + k;
-      const PairRaw r = p.raw[slot];
+      PairRaw r = p.raw[slot];
       PairOut o;
-      // reference naming: x = first column of the pair (unit.col), y = the second
-      pair_epilogue(p.n, p.stats[unit.col], p.stats[xcol], r.dis, r.ntie, r.b, r.g00, p.perspective,
-                    p.alternative, p.continuity, o);
+      if (p.pw) {
+        // the kernel's x is the second column of the pair; the reference names the first one x
+        PairComplete c = p.pw[slot], d = c;
+        d.xs2 = c.ys2; d.xs3 = c.ys3; d.xs5 = c.ys5; d.kx = c.ky;
+        d.ys2 = c.xs2; d.ys3 = c.xs3; d.ys5 = c.xs5; d.ky = c.kx;
+        pair_epilogue_complete(d, p.alternative, p.continuity, o);
+        r.dis = c.dis;
+        r.b = 0;
+      } else {
+        // reference naming: x = first column of the pair (unit.col), y = the second
+        pair_epilogue(p.n, p.stats[unit.col], p.stats[xcol], r.dis, r.ntie, r.b, r.g00, p.perspective,
+                      p.alternative, p.continuity, o);
+      }
       p.tau[slot] = o.tau;
       if (p.pvalue) p.pvalue[slot] = o.pvalue;
       if (p.taumax) p.taumax[slot] = o.taumax;
@@ -1045,6 +1187,9 @@ TiledParams make_params(const PairLaunch& pl) {
   p.units = pl.units;
   p.pj_list = pl.pj_list;
   p.raw = pl.raw;
+  p.pw = pl.pw;
+  p.gstart = t.gstart;
+  p.gstride = (int)t.gstride;
   p.unit_counter = pl.unit_counter;
   p.n_units = pl.n_units;
   p.n = (int)t.n;
@@ -1161,9 +1306,9 @@ TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm) {
 
 namespace {
 
-template <int MAXT, int MINB, bool G>
+template <int MAXT, int MINB, bool G, bool PW = false>
 int tiled_occupancy(int threads, size_t smem) {
-  auto kern = pairs_tiled_kernel<MAXT, MINB, G>;
+  auto kern = pairs_tiled_kernel<MAXT, MINB, G, PW>;
   if (threads > MAXT) return 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
@@ -1177,9 +1322,9 @@ int tiled_occupancy(int threads, size_t smem) {
   return per_sm;
 }
 
-template <int MAXT, int MINB, bool G>
+template <int MAXT, int MINB, bool G, bool PW = false>
 int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size_t smem, cudaStream_t stream) {
-  pairs_tiled_kernel<MAXT, MINB, G><<<(unsigned)grid, threads, smem, stream>>>(p);
+  pairs_tiled_kernel<MAXT, MINB, G, PW><<<(unsigned)grid, threads, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1188,6 +1333,15 @@ int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size
 template <bool G>
 int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, cudaStream_t stream) {
   const int threads = 32 * sh.warps;
+  if (p.pw) {  // complete-observations mode: one register class
+    const int occ = tiled_occupancy<1024, 1, G, true>(threads, smem);
+    if (occ < 1) return -1;
+    long long grid = (long long)n_sm * occ;
+    if (grid > p.n_units) grid = p.n_units;
+    if (G && grid > sh.scratch_ctas) grid = sh.scratch_ctas;
+    if (grid < 1) grid = 1;
+    return launch_tiled_variant<1024, 1, G, true>(p, threads, grid, smem, stream);
+  }
   const int o64 = tiled_occupancy<1024, 1, G>(threads, smem);
   const int o40 = tiled_occupancy<512, 3, G>(threads, smem);
   const int o32 = tiled_occupancy<1024, 2, G>(threads, smem);
@@ -1274,6 +1428,7 @@ int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream) {
   p.units = el.units;
   p.pj_list = el.pj_list;
   p.raw = el.raw;
+  p.pw = el.pw;
   p.tau = el.tau;
   p.pvalue = el.pvalue;
   p.taumax = el.taumax;

@@ -56,9 +56,16 @@ extern "C" {
 #define ICIKT_STATUS_TOO_SHORT 2     /* :224-231  "The vectors only have a single value"     */
 #define ICIKT_STATUS_SINGLE_UNIQUE 3 /* :234-244  "... have only a single unique value"      */
 #define ICIKT_STATUS_ALL_TIED 4      /* :291-298  "Ties equal the total"                     */
+#define ICIKT_STATUS_UNSUPPORTED 9   /* complete-observations mode only, see ICIKT_PERSPECTIVE_COMPLETE */
 
 #define ICIKT_PERSPECTIVE_GLOBAL 0 /* any string other than "local", src/kendallc.cpp:180 */
 #define ICIKT_PERSPECTIVE_LOCAL 1
+/* Not an ICI perspective: plain Kendall-tau-b on the rows present in BOTH columns, what
+ * kt_fast(use = "pairwise.complete.obs") computes pair by pair (kt_split drops the rows missing
+ * in either column and calls ici_kt on the rest, R/kendalltau.R:323-341).  completeness is 1,
+ * counts are those of the shared rows; status 9 = a column's missing rows tie with its
+ * minimum in fp64 (|min| >= ~1e15), the caller has to filter that pair on the host.          */
+#define ICIKT_PERSPECTIVE_COMPLETE 2
 
 #define ICIKT_ALT_TWO_SIDED 0
 #define ICIKT_ALT_LESS 1

@@ -483,3 +483,65 @@ def test_uneven_missingness_first_group_emission(n, fracs, ties):
     for persp in ("global", "local"):
         got = ik.run_pairs(x, (), pi=pi, pj=pj, perspective=persp, want_counts=True)
         assert_parity(got, oracle_pairs(x, pi=pi, pj=pj, perspective=persp), f"uneven NA n={n} {persp}")
+
+
+def _oracle_complete(x, pi, pj):
+    """kt_split with use = 'pairwise.complete.obs' (R/kendalltau.R:323-341): drop the rows missing in
+    either column, then ici_kt on what is left."""
+    P = len(pi)
+    out = dict(raw=np.full(P, np.nan), pvalue=np.full(P, np.nan), taumax=np.full(P, np.nan),
+               status=np.zeros(P, dtype=np.int32), counts=np.zeros((P, 7), dtype=np.int64))
+    for k in range(P):
+        good = ~np.isnan(x[:, pi[k]]) & ~np.isnan(x[:, pj[k]])
+        if good.sum() == 0:
+            out["status"][k] = 1
+            continue
+        sub = np.asfortranarray(np.column_stack([x[good, pi[k]], x[good, pj[k]]]))
+        r = O.pair_loop(sub, np.array([0], np.int32), np.array([1], np.int32), perspective="local",
+                        want_counts=True)
+        out["status"][k] = r["status"][0]
+        for nm in ("raw", "pvalue", "taumax"):
+            out[nm][k] = r[nm][0]
+        out["counts"][k] = r["counts"][0]
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,C,na", [("normal", 300, 7, 0.2), ("ties", 1000, 6, 0.3), ("heavy", 2500, 5, 0.35),
+                                         ("mixed", 6000, 5, 0.25), ("normal", 33, 5, 0.5), ("ties", 20000, 3, 0.4)])
+def test_complete_observations_mode(kind, n, C, na):
+    """Device-side pairwise.complete.obs: every count on the shared rows is bit-exact against the
+    oracle run on the filtered vectors; includes (i,i) pairs, both orders and degenerate columns."""
+    x = gen(n, C, kind, na, seed=7 * n + C)
+    rng = np.random.default_rng(n)
+    x[rng.random(n) < 0.1, 1] = np.nan          # missingness that is not left-censoring
+    x = np.column_stack([x, np.full(n, np.nan), np.full(n, 2.5), np.where(np.arange(n) % 3 == 0, np.nan, 1.0)])
+    x[0, 2] = np.nan                             # a column with exactly one missing row
+    x = np.asfortranarray(x)
+    C = x.shape[1]
+    pi = np.array([i for i in range(C) for j in range(C)], dtype=np.int32)
+    pj = np.array([j for i in range(C) for j in range(C)], dtype=np.int32)
+    got = ik.run_pairs(x, (), pi=pi, pj=pj, perspective="complete", want_counts=True)
+    ref = _oracle_complete(x, pi, pj)
+    assert np.array_equal(got["status"], ref["status"])
+    ok = ref["status"] == 0
+    for k, nm in enumerate(COUNT_NAMES[:6]):
+        assert np.array_equal(got["counts"][ok, k], ref["counts"][ok, k]), nm
+    for nm, tol in (("raw", 1e-12), ("taumax", 1e-12), ("pvalue", 1e-9)):
+        a, b = got[nm], ref[nm]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), nm
+        m = ~np.isnan(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=tol, atol=0, err_msg=nm)
+    assert np.all(got["completeness"][ok] == 1.0)
+
+
+@pytest.mark.gpu
+def test_kt_fast_pairwise_uses_device_mode_and_matches_host_filtering():
+    x = gen(800, 9, "mixed", 0.3, seed=99)
+    names = [f"s{i}" for i in range(x.shape[1])]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fast = ik.kt_fast(x, use="pairwise.complete.obs", colnames=names)
+    ref = O.kt_fast(x, use="pairwise.complete.obs")
+    np.testing.assert_allclose(fast["tau"], ref["tau"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(fast["pvalue"], ref["pvalue"], rtol=1e-9, equal_nan=True)
