@@ -188,19 +188,20 @@ kt_fast = function(x, y = NULL, use = "everything", alternative = "two.sided", c
   if (do_it) {
     # kt_split calls ici_kt(tmp_x, tmp_y) with its defaults (:341): local, two.sided, no continuity
     if (na_method == "pairwise.complete.obs" && anyNA(data)) {
-      col_na = colSums(is.na(data)) > 0
-      clean = !(col_na[plan$i] | col_na[plan$j])
-      if (any(clean)) {
-        r = .Call(C_icikt_pair_list, data, double(0), plan$i[clean], plan$j[clean], "local", "two.sided",
-                  FALSE, FALSE, as.integer(device))
-        .warn_status(r$status); tau[clean] = r$raw; pvalue[clean] = r$pvalue
-      }
-      for (k in which(!clean)) {   # rows missing in either column are dropped per pair (:323-331)
+      # rows missing in either column are dropped per pair (:323-331) -- on the device
+      # (complete-observations mode); status 9 marks the pairs the device cannot take
+      # (a column whose missing rows tie with its minimum in fp64), those are filtered here
+      r = .Call(C_icikt_all_pairs, data, double(0), "complete", "two.sided", FALSE, TRUE, FALSE, as.integer(device))
+      tau = r$raw; pvalue = r$pvalue
+      redo = which(r$status == 9L)
+      .warn_status(r$status[r$status != 9L])
+      for (k in redo) {
         good = !is.na(data[, plan$i[k]]) & !is.na(data[, plan$j[k]])
+        tau[k] = NA_real_; pvalue[k] = NA_real_
         if (!any(good)) next
-        r = .Call(C_icikt_pair_list, cbind(data[good, plan$i[k]], data[good, plan$j[k]]), double(0), 1L, 2L,
-                  "local", "two.sided", FALSE, FALSE, as.integer(device))
-        .warn_status(r$status); tau[k] = r$raw; pvalue[k] = r$pvalue
+        r2 = .Call(C_icikt_pair_list, cbind(data[good, plan$i[k]], data[good, plan$j[k]]), double(0), 1L, 2L,
+                   "local", "two.sided", FALSE, FALSE, as.integer(device))
+        .warn_status(r2$status); tau[k] = r2$raw; pvalue[k] = r2$pvalue
       }
     } else {
       r = .Call(C_icikt_all_pairs, data, double(0), "local", "two.sided", FALSE, TRUE, FALSE, as.integer(device))

@@ -27,7 +27,9 @@ static void fill_opts(icikt_opts* o, SEXP perspective, SEXP alternative, SEXP co
   icikt_default_opts(o);
   const char* p = CHAR(STRING_ELT(perspective, 0));
   /* any string other than "local" behaves as global, src/kendallc.cpp:180 */
-  o->perspective = strcmp(p, "local") == 0 ? ICIKT_PERSPECTIVE_LOCAL : ICIKT_PERSPECTIVE_GLOBAL;
+  o->perspective = strcmp(p, "local") == 0 ? ICIKT_PERSPECTIVE_LOCAL
+                 : strcmp(p, "complete") == 0 ? ICIKT_PERSPECTIVE_COMPLETE /* kt_fast, pairwise.complete.obs */
+                                              : ICIKT_PERSPECTIVE_GLOBAL;
   const char* a = CHAR(STRING_ELT(alternative, 0));
   if (strcmp(a, "two.sided") == 0) o->alternative = ICIKT_ALT_TWO_SIDED;
   else if (strcmp(a, "less") == 0) o->alternative = ICIKT_ALT_LESS;
