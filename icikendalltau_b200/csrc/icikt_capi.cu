@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -43,6 +44,16 @@ int64_t row_start(int64_t i, int64_t C) { return i * (2 * C - i - 1) / 2; }
 
 }  // namespace
 
+// result sets up to stage_all() bytes: one pinned copy of everything; above: two pinned chunks of
+// stage_chunk() bytes (the environment overrides exist for the tests)
+static size_t env_bytes(const char* name, size_t dflt) {
+  const char* e = std::getenv(name);
+  const long long v = e ? std::atoll(e) : 0;
+  return v > 0 ? (size_t)v : dflt;
+}
+static size_t stage_all() { return env_bytes("ICIKT_STAGE_ALL", 96u << 20); }
+static size_t stage_chunk() { return env_bytes("ICIKT_STAGE_CHUNK", 32u << 20); }
+
 struct icikt_plan {
   int device = 0;
   int n_sm = 0;
@@ -76,6 +87,9 @@ struct icikt_plan {
   // [tau P][pvalue P][taumax P][completeness P] doubles, [max taumax bits] u64, [status P] int32
   unsigned char* d_res = nullptr;
   unsigned char* h_res = nullptr;  // pinned staging copy (small and medium result sets only)
+  unsigned char* h_stage[2] = {nullptr, nullptr};  // large result sets: two pinned chunks, copy-out pipelined
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_ev[2]{};
   size_t res_bytes = 0;
   double *d_tau = nullptr, *d_p = nullptr, *d_tm = nullptr, *d_comp = nullptr;
   unsigned long long* d_maxbits = nullptr;
@@ -119,6 +133,10 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->d_pw);
   cudaFree(p->d_res);
   if (p->h_res) cudaFreeHost(p->h_res);
+  for (int i = 0; i < 2; ++i) {
+    if (p->h_stage[i]) cudaFreeHost(p->h_stage[i]);
+    if (p->stage_ev[i]) cudaEventDestroy(p->stage_ev[i]);
+  }
   cudaFree(p->d_counts);
   cudaFree(p->d_scalars);
   cudaFree(p->d_naive);
@@ -203,6 +221,33 @@ int select_device(int device) {
   }
   if (device < 0 || device >= cnt) return fail(ICIKT_ERR_BAD_ARG, "device ordinal out of range");
   CK(cudaSetDevice(device));
+  return ICIKT_OK;
+}
+
+// Device -> pageable host memory through two pinned chunks: the copy of chunk k+1 runs while chunk k
+// is moved from the staging buffer into the caller's array (cudaMemcpyAsync straight into pageable
+// memory is staged by the driver at a fraction of the link rate).
+int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes) {
+  unsigned char* out = static_cast<unsigned char*>(dst);
+  const unsigned char* src = static_cast<const unsigned char*>(d_src);
+  size_t off[2] = {0, 0}, len[2] = {0, 0};
+  int k = 0;
+  for (size_t o = 0; o < bytes || len[0] || len[1]; ++k) {
+    const int cur = k & 1;
+    if (len[cur]) {  // the chunk issued two steps ago has landed in h_stage[cur]
+      CK(cudaEventSynchronize(p->stage_ev[cur]));
+      std::memcpy(out + off[cur], p->h_stage[cur], len[cur]);
+      len[cur] = 0;
+    }
+    if (o < bytes) {
+      const size_t l = std::min(p->stage_bytes, bytes - o);
+      CK(cudaMemcpyAsync(p->h_stage[cur], src + o, l, cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaEventRecord(p->stage_ev[cur], p->stream));
+      off[cur] = o;
+      len[cur] = l;
+      o += l;
+    }
+  }
   return ICIKT_OK;
 }
 
@@ -335,7 +380,15 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   p->d_comp = p->d_tm + np;
   p->d_maxbits = reinterpret_cast<unsigned long long*>(p->d_comp + np);
   p->d_status = reinterpret_cast<int32_t*>(p->d_maxbits + 1);
-  if (p->res_bytes <= (64u << 20)) PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_res), p->res_bytes));
+  if (p->res_bytes <= stage_all()) {
+    PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_res), p->res_bytes));
+  } else {
+    p->stage_bytes = stage_chunk();
+    for (int i = 0; i < 2; ++i) {
+      PCK(cudaMallocHost(reinterpret_cast<void**>(&p->h_stage[i]), p->stage_bytes));
+      PCK(cudaEventCreateWithFlags(&p->stage_ev[i], cudaEventDisableTiming));
+    }
+  }
   if (p->want_counts) PCK(dmalloc(&p->d_counts, np * ICIKT_NCOUNTS));
   PCK(dmalloc(&p->d_scalars, 2));  // [0] unit counter
   if (o.kernel == ICIKT_KERNEL_NAIVE) {
@@ -516,12 +569,14 @@ int icikt_plan_download(icikt_plan* p, double* raw, double* pvalue, double* taum
     std::memcpy(&bits, h + 4 * npad, sizeof(bits));
   } else {
     if (np) {
-      if (raw) CK(cudaMemcpyAsync(raw, p->d_tau, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-      if (pvalue) CK(cudaMemcpyAsync(pvalue, p->d_p, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-      if (taumax) CK(cudaMemcpyAsync(taumax, p->d_tm, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-      if (completeness) CK(cudaMemcpyAsync(completeness, p->d_comp, sizeof(double) * np, cudaMemcpyDeviceToHost, p->stream));
-      if (status) CK(cudaMemcpyAsync(status, p->d_status, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, p->stream));
-      if (counts) CK(cudaMemcpyAsync(counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS, cudaMemcpyDeviceToHost, p->stream));
+      int rc = ICIKT_OK;
+      if (raw) rc = staged_copy_out(p, raw, p->d_tau, sizeof(double) * np);
+      if (rc == ICIKT_OK && pvalue) rc = staged_copy_out(p, pvalue, p->d_p, sizeof(double) * np);
+      if (rc == ICIKT_OK && taumax) rc = staged_copy_out(p, taumax, p->d_tm, sizeof(double) * np);
+      if (rc == ICIKT_OK && completeness) rc = staged_copy_out(p, completeness, p->d_comp, sizeof(double) * np);
+      if (rc == ICIKT_OK && status) rc = staged_copy_out(p, status, p->d_status, sizeof(int32_t) * np);
+      if (rc == ICIKT_OK && counts) rc = staged_copy_out(p, counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS);
+      if (rc != ICIKT_OK) return rc;
     }
     CK(cudaMemcpyAsync(&bits, p->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaEventRecord(p->ev[7], p->stream));

@@ -545,3 +545,17 @@ def test_kt_fast_pairwise_uses_device_mode_and_matches_host_filtering():
     ref = O.kt_fast(x, use="pairwise.complete.obs")
     np.testing.assert_allclose(fast["tau"], ref["tau"], rtol=1e-12, equal_nan=True)
     np.testing.assert_allclose(fast["pvalue"], ref["pvalue"], rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_chunked_copy_out_of_large_result_sets(monkeypatch):
+    """Result sets above the one-shot staging limit leave the device through two pinned chunks;
+    forced here with tiny limits so that every array takes several chunks of uneven length."""
+    x = gen(400, 40, "mixed", 0.25, seed=5)
+    ref = oracle_pairs(x, perspective="global")
+    monkeypatch.setenv("ICIKT_STAGE_ALL", "1024")
+    monkeypatch.setenv("ICIKT_STAGE_CHUNK", "1000")
+    _lib.release_workspace()
+    got = ik.run_pairs(x, (), perspective="global", want_counts=True)
+    _lib.release_workspace()
+    assert_parity(got, ref, "chunked copy-out")

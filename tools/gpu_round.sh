@@ -1,7 +1,6 @@
 set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$? | tee -a gpurun_out/pytest_gpu.log
 tail -30 gpurun_out/pytest_gpu.log
-python bench.py --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/q_config2.json
-for wl in target; do
-python bench.py --workload $wl --steps 3 --warmup 3 --quick 2>/dev/null | tail -1 > gpurun_out/q_$wl.json
+for wl in config5 target; do
+python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/q_$wl.json
 done
