@@ -11,7 +11,7 @@ done
 python bench.py --kernel naive --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${tag}_naive_config2.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}_config2.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/ncu_launch.log 2>&1
 prof() { # name workload cols
-ncu --set full --clock-control none --import-source on -k regex:pairs_tiled --launch-skip 3 --launch-count 1 -f -o gpurun_out/prof_${tag}_k2_$1 python bench.py --workload $2 --cols $3 --steps 1 --warmup 3 --quick > gpurun_out/ncu_$1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pairs_tiled --launch-skip 6 --launch-count 1 -f -o gpurun_out/prof_${tag}_k2_$1 python bench.py --workload $2 --cols $3 --steps 1 --warmup 3 --quick > gpurun_out/ncu_$1.log 2>&1
 }
 prof config2 config2 100
 prof target target 300
