@@ -82,6 +82,9 @@ def load():
     L.icikt_all_pairs.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
                                   ctypes.c_int32, ctypes.POINTER(Opts)] + common_out
     L.icikt_all_pairs.restype = ctypes.c_int
+    L.icikt_all_pairs_multi.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
+                                        ctypes.c_int32, ctypes.POINTER(Opts), _ip, ctypes.c_int32] + common_out
+    L.icikt_all_pairs_multi.restype = ctypes.c_int
     L.icikt_pair_list.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
                                   ctypes.c_int32, _ip, _ip, ctypes.c_int64,
                                   ctypes.POINTER(Opts)] + common_out
@@ -153,11 +156,13 @@ def _ptr(a, t):
     return a.ctypes.data_as(t) if a is not None else None
 
 
-def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, **opt_kw):
+def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, devices=None, **opt_kw):
     """One-shot call through icikt_all_pairs / icikt_pair_list with host buffers.
 
     data: (n, C) array (copied to Fortran order if needed).  Returns a dict of NumPy arrays in
     pair order: raw, pvalue, taumax, completeness, status, [counts], max_taumax, timings.
+    devices: list of CUDA ordinals -> icikt_all_pairs_multi (all pairs only): every device takes a
+    contiguous slice of the pair order.
     """
     L = load()
     data = np.asfortranarray(data, dtype=np.float64)
@@ -179,7 +184,13 @@ def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, **opt_kw)
     mx = ctypes.c_double(float("nan"))
     t = Timings()
     g, gp, ng = _global_na_array(global_na)
-    if pi is None:
+    if pi is None and devices is not None:
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        rc = L.icikt_all_pairs_multi(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), _ptr(dev, _ip),
+                                     int(dev.size), _ptr(raw, _dp), _ptr(pv, _dp), _ptr(tm, _dp),
+                                     _ptr(comp, _dp), _ptr(status, _ip), _ptr(counts, _lp),
+                                     ctypes.byref(mx), ctypes.byref(t))
+    elif pi is None:
         rc = L.icikt_all_pairs(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), _ptr(raw, _dp),
                                _ptr(pv, _dp), _ptr(tm, _dp), _ptr(comp, _dp), _ptr(status, _ip),
                                _ptr(counts, _lp), ctypes.byref(mx), ctypes.byref(t))

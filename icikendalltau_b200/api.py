@@ -186,12 +186,14 @@ def _reshape(names, pi, pj, cols):
 
 def ici_kendalltau(data_matrix, global_na=(np.nan, np.inf, 0), perspective="global", scale_max=True,
                    diag_good=True, include_only=None, alternative="two.sided", continuity=False,
-                   check_timing=False, return_matrix=True, colnames=None, device=0):
+                   check_timing=False, return_matrix=True, colnames=None, device=0, n_gpus=1):
     """All-pairs ICI-Kendall-tau between the columns (samples) of a features x samples matrix.
 
     Returns a dict with `cor`, `raw`, `pvalue`, `taumax`, `completeness` (C x C matrices),
     `keep`, `run_time` and `names`; with return_matrix=False a long table `cor` (dict of columns
     s1, s2, raw, pvalue, taumax, completeness, cor) like the reference's data.frame.
+    n_gpus > 1 spreads the pair order over that many GPUs of the box (the role of the reference's
+    furrr workers), still in one library call.
     """
     data, names = _colnames_of(data_matrix, colnames, "data_matrix")
     n, C = data.shape
@@ -218,7 +220,9 @@ def ici_kendalltau(data_matrix, global_na=(np.nan, np.inf, 0), perspective="glob
 
     log.info("Running correlations ...")
     t1 = time.perf_counter()
-    if all_pairs:
+    if all_pairs and n_gpus > 1:  # one call, the pair order sliced over the GPUs inside the library
+        r = _lib.run_pairs(data, global_na, include_diag=not diag_good, devices=range(n_gpus), **kw)
+    elif all_pairs:
         r = _lib.run_pairs(data, global_na, include_diag=not diag_good, **kw)
     else:
         r = _lib.run_pairs(data, global_na, pi=pi, pj=pj, **kw)

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/icikt_b200.h"
@@ -715,6 +716,68 @@ int icikt_all_pairs(const double* data, int64_t n, int64_t C, int64_t ld, const 
                     double* max_taumax, icikt_timings* timings) {
   return one_shot(data, n, C, ld, global_na, n_global_na, nullptr, nullptr, 0, opts, raw, pvalue, taumax,
                   completeness, status, counts, max_taumax, timings);
+}
+
+int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                          int32_t n_global_na, const icikt_opts* opts, const int32_t* devices,
+                          int32_t n_devices, double* raw, double* pvalue, double* taumax,
+                          double* completeness, int32_t* status, int64_t* counts, double* max_taumax,
+                          icikt_timings* timings) {
+  if (!data || !raw) return fail(ICIKT_ERR_BAD_ARG, "data and raw must not be NULL");
+  if (n_devices < 1 || n_devices > 64) return fail(ICIKT_ERR_BAD_ARG, "n_devices must be 1..64");
+  if (n < 1 || C < 1) return fail(ICIKT_ERR_BAD_ARG, "n and C must be >= 1");
+  icikt_opts base;
+  if (opts) base = *opts; else icikt_default_opts(&base);
+  base.want_counts = counts ? 1 : 0;
+  const int64_t ptot = tri_pairs(C) + (base.include_diag ? C : 0);
+  struct Work {
+    int rc = ICIKT_OK;
+    std::string err;
+    double mx = std::nan("");
+    icikt_timings tm{};
+  };
+  std::vector<Work> work((size_t)n_devices);
+  std::vector<std::thread> threads;
+  for (int k = 0; k < n_devices; ++k) {
+    threads.emplace_back([&, k]() {
+      Work& w = work[(size_t)k];
+      icikt_opts o = base;
+      o.device = devices ? devices[k] : k;
+      o.pair_lo = ptot * k / n_devices;  // contiguous slices that differ by at most one pair
+      o.pair_hi = ptot * (k + 1) / n_devices;
+      const int64_t lo = o.pair_lo, cnt = o.pair_hi - o.pair_lo;
+      if (cnt <= 0) return;
+      icikt_plan* p = nullptr;
+      w.rc = icikt_plan_create(&p, n, C, nullptr, nullptr, 0, &o);
+      if (w.rc == ICIKT_OK) w.rc = icikt_plan_upload(p, data, ld);
+      if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns(p, global_na, n_global_na);
+      if (w.rc == ICIKT_OK) w.rc = icikt_plan_pairs(p);
+      if (w.rc == ICIKT_OK)
+        w.rc = icikt_plan_download(p, raw + lo, pvalue ? pvalue + lo : nullptr, taumax ? taumax + lo : nullptr,
+                                   completeness ? completeness + lo : nullptr, status ? status + lo : nullptr,
+                                   counts ? counts + lo * ICIKT_NCOUNTS : nullptr, &w.mx);
+      if (w.rc == ICIKT_OK) w.rc = icikt_plan_timings(p, &w.tm);
+      if (w.rc != ICIKT_OK) w.err = g_err;  // thread-local message of this worker
+      if (p) icikt_plan_destroy(p);
+    });
+  }
+  for (auto& t : threads) t.join();
+  double mx = std::nan("");
+  icikt_timings slowest{};
+  for (const Work& w : work) {
+    if (w.rc != ICIKT_OK) return fail(w.rc, w.err);
+    if (w.mx == w.mx && !(mx >= w.mx)) mx = w.mx;
+    if (w.tm.total_ms >= slowest.total_ms) {
+      const int launches = slowest.n_launches + w.tm.n_launches;
+      slowest = w.tm;
+      slowest.n_launches = launches;
+    } else {
+      slowest.n_launches += w.tm.n_launches;
+    }
+  }
+  if (max_taumax) *max_taumax = mx;
+  if (timings) *timings = slowest;
+  return ICIKT_OK;
 }
 
 int icikt_pair_list(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,

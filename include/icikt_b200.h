@@ -127,6 +127,18 @@ int icikt_all_pairs(const double* data, int64_t n, int64_t C, int64_t ld,
                     int32_t* status, int64_t* counts, double* max_taumax,
                     icikt_timings* timings);
 
+/* The same over several GPUs of one box in ONE call (what `computation$ncore` workers are to the
+ * reference, R/kendalltau.R:250-253): device k of devices[0..n_devices) preprocesses all columns
+ * and computes the k-th contiguous slice of the pair order straight into the caller's arrays;
+ * max_taumax is the maximum over the devices.  No collective is involved: pairs are independent
+ * (SURVEY.md 8e).  devices == NULL means ordinals 0..n_devices-1; opts->device, pair_lo and
+ * pair_hi are ignored.  timings (may be NULL) receives the slowest device's figures.            */
+int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld,
+                          const double* global_na, int32_t n_global_na, const icikt_opts* opts,
+                          const int32_t* devices, int32_t n_devices, double* raw, double* pvalue,
+                          double* taumax, double* completeness, int32_t* status, int64_t* counts,
+                          double* max_taumax, icikt_timings* timings);
+
 /* Same for an explicit pair list (include_only, ici_kt(x, y) with C = 2 and P = 1,
  * kt_fast incl. (i,i) pairs).  pi[k], pj[k] in [0, C).                               */
 int icikt_pair_list(const double* data, int64_t n, int64_t C, int64_t ld,

@@ -115,6 +115,8 @@ ici_kt = function(x, y, perspective = "local", alternative = "two.sided", contin
   res
 }
 
+# `device`: one CUDA ordinal, or a vector of ordinals -- the pair order is then sliced over those
+# GPUs inside the one library call (the role of the reference's furrr workers).
 ici_kendalltau = function(data_matrix, global_na = c(NA, Inf, 0), perspective = "global", scale_max = TRUE,
                           diag_good = TRUE, include_only = NULL, alternative = "two.sided",
                           continuity = FALSE, check_timing = FALSE, return_matrix = TRUE, device = 0L) {

@@ -76,8 +76,13 @@ SEXP C_icikt_all_pairs(SEXP data, SEXP global_na, SEXP perspective, SEXP alterna
   int* status;
   SEXP mxs;
   SEXP res = make_result(P, &raw, &pv, &tm, &comp, &status, &mxs);
-  const int rc = icikt_all_pairs(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), &o, raw, pv,
-                                 tm, comp, status, NULL, &mx, NULL);
+  /* `device`: one ordinal, or several -> the pair order is sliced over those GPUs inside the call */
+  const int rc = (isInteger(device) && XLENGTH(device) > 1)
+                     ? icikt_all_pairs_multi(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), &o,
+                                             INTEGER(device), (int32_t)XLENGTH(device), raw, pv, tm, comp, status,
+                                             NULL, &mx, NULL)
+                     : icikt_all_pairs(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), &o, raw,
+                                       pv, tm, comp, status, NULL, &mx, NULL);
   if (rc != ICIKT_OK) {
     UNPROTECT(1);
     error("libicikt_b200 (%d): %s", rc, icikt_last_error());

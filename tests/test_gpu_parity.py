@@ -559,3 +559,20 @@ def test_chunked_copy_out_of_large_result_sets(monkeypatch):
     got = ik.run_pairs(x, (), perspective="global", want_counts=True)
     _lib.release_workspace()
     assert_parity(got, ref, "chunked copy-out")
+
+
+@pytest.mark.gpu
+def test_multi_gpu_call_matches_single_gpu():
+    """icikt_all_pairs_multi: the pair order sliced over the devices inside one call gives the very
+    bytes of the single-device call (with one GPU the two slices simply run on the same device)."""
+    ndev = _lib.load().icikt_device_count()
+    x = gen(700, 23, "mixed", 0.25, seed=77)
+    one = ik.run_pairs(x, (), perspective="local", include_diag=True, want_counts=True)
+    devices = [0, 1 % ndev, 0] if ndev > 1 else [0, 0, 0]
+    many = ik.run_pairs(x, (), perspective="local", include_diag=True, want_counts=True, devices=devices)
+    for k in ("raw", "pvalue", "taumax", "completeness", "status", "counts"):
+        np.testing.assert_array_equal(one[k], many[k], err_msg=k)
+    assert one["max_taumax"] == many["max_taumax"]
+    res = ik.ici_kendalltau(x, global_na=(np.nan,), colnames=[f"s{i}" for i in range(23)], n_gpus=min(2, max(ndev, 1)))
+    ref = ik.ici_kendalltau(x, global_na=(np.nan,), colnames=[f"s{i}" for i in range(23)])
+    np.testing.assert_array_equal(res["cor"], ref["cor"])
