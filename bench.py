@@ -84,11 +84,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_shape(name, n_gpus, scaling, cols=0):
+def workload_shape(name, n_gpus, scaling, cols=0, rows=0):
     from icikendalltau_b200 import synth
     n, C, q, persp, kind = synth.WORKLOADS[name]
     if cols:
         C = cols
+    if rows:
+        n = rows
     if scaling == "weak" and n_gpus > 1:
         # pairs ~ C^2/2: keep pairs per GPU constant
         C = int(round(math.sqrt(n_gpus * C * (C - 1) + 0.25) + 0.5))
@@ -120,7 +122,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from icikendalltau_b200 import synth
-    n, C, persp = workload_shape(args.workload, args.gpus, args.scaling, args.cols)
+    n, C, persp = workload_shape(args.workload, args.gpus, args.scaling, args.cols, args.rows)
     x, _ = synth.make(args.workload, n=n, C=C)
     cores = os.cpu_count() or 1
     P = C * (C - 1) // 2
@@ -162,6 +164,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", default="tiled", choices=["tiled", "naive"])
     ap.add_argument("--cols", type=int, default=0, help="override the number of samples (profiling runs only)")
+    ap.add_argument("--rows", type=int, default=0, help="override the number of features (profiling runs only)")
     ap.add_argument("--quick", action="store_true", help="skip the e2e and CPU legs (tuning sweeps)")
     args = ap.parse_args()
 
@@ -200,7 +203,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    n, C, persp = workload_shape(args.workload, n_gpus, args.scaling, args.cols)
+    n, C, persp = workload_shape(args.workload, n_gpus, args.scaling, args.cols, args.rows)
     x, _ = synth.make(args.workload, n=n, C=C)  # same seed on every rank
     P_total = C * (C - 1) // 2
     lo, hi = sharding.pair_range(P_total, rank, world)

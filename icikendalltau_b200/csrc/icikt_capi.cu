@@ -119,6 +119,7 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->tab.firstbits);
   cudaFree(p->tab.grpstart);
   cudaFree(p->tab.gstart);
+  cudaFree(p->tab.lgrp);
   cudaFree(p->tab.stats);
   cudaFree(p->tab.max_tied);
   cudaFree(p->wk.keys_in);
@@ -345,6 +346,7 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.grpstart, nw));
   t.gstride = t.nstride + 64;
   PCK(dmalloc(&t.gstart, (size_t)t.gstride * C));
+  PCK(dmalloc(&t.lgrp, (size_t)kLargeStride * C));
   PCK(dmalloc(&t.stats, (size_t)C));
   PCK(dmalloc(&t.max_tied, 1));
   // padding words of the bit arrays (beyond n32/32) are never written by the kernels

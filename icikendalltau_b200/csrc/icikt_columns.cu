@@ -109,15 +109,18 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         uint16_t* __restrict__ perm, uint16_t* __restrict__ rank, uint16_t* __restrict__ trow,
                         uint16_t* __restrict__ trun, uint32_t* __restrict__ nabits,
                         uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
-                        ColStats* __restrict__ stats, int32_t* __restrict__ max_tied) {
+                        uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
+                        int32_t* __restrict__ max_tied) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
   __shared__ int warp_sums[32];
   __shared__ long long llbuf[32];
   __shared__ unsigned long long mnkey;
+  __shared__ int n_large;
   typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
   const int col = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) n_large = 0;
   unsigned long long keys[ITEMS];
   uint16_t vals[ITEMS];
 #pragma unroll
@@ -195,11 +198,16 @@ __global__ void __launch_bounds__(SORT_THREADS)
   long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
   for (int g = tid; g < K; g += SORT_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
+    if (g > 0 && t >= kLargeTie) {  // large tie group: also listed by (start position, size)
+      const int k = atomicAdd(&n_large, 1);
+      lgrp[(size_t)col * kLargeStride + 2 * k] = gpos[g];
+      lgrp[(size_t)col * kLargeStride + 2 * k + 1] = (uint16_t)t;
+    }
+    if (g > 0 && t > 1) ntied += t;
     if (g == 0 && a > 0) continue;  // the NA group is kept apart for the local perspective
     s2 += t * (t - 1);
     s3 += t * (t - 1) * (t - 2);
     s5 += t * (t - 1) * (2 * t + 5);
-    if (g > 0 && t > 1) ntied += t;
   }
   s2 = block_sum_ll(s2, llbuf);
   s3 = block_sum_ll(s3, llbuf);
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
   const int g0size = (K > 0) ? (int)gpos[1] : 0;
   const int first_run = g0size > 1 ? g0size : 0;
   // membership mask of the first group; rows of the other tied groups with their dense group index
-  uint32_t tmask = 0, gmask = 0;
+  uint32_t tmask = 0, gmask = 0, lmask = 0;
   {
     int r = excl - 1;
 #pragma unroll
@@ -217,8 +225,10 @@ __global__ void __launch_bounds__(SORT_THREADS)
       if ((fmask >> i) & 1u) ++r;
       if (t < first_run) atomicOr(&bits[vals[i] >> 5], 1u << (vals[i] & 31));
       if (t < n && t >= g0size) {
-        const bool tied = ((int)gpos[r + 1] - (int)gpos[r]) > 1;
+        const int sz = (int)gpos[r + 1] - (int)gpos[r];
+        const bool tied = sz > 1;
         tmask |= (uint32_t)tied << i;
+        lmask |= (uint32_t)(sz >= kLargeTie) << i;
         gmask |= (uint32_t)(tied && (int)gpos[r] == t) << i;
       }
     }
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
       if ((gmask >> i) & 1u) ++gcount;
       if ((tmask >> i) & 1u) {
         tr[pos] = vals[i];
-        tg[pos] = (uint16_t)(gcount - 1);
+        tg[pos] = (uint16_t)((gcount - 1) | (((lmask >> i) & 1u) ? kLargeFlag : 0u));
         ++pos;
       }
     }
@@ -251,14 +261,14 @@ __global__ void __launch_bounds__(SORT_THREADS)
     while ((1 << L) < K) ++L;
     s.levels = L;
     s.g0extra = (a > 0) ? g0size - a : 0;
-    s.flags = absorb ? 1 : 0;
+    s.flags = (absorb ? 1 : 0) | (n_large << 8);
     s.n_tgroups = tot2 >> 16;
     s.s2o = s2;
     s.s3o = s3;
     s.s5o = s5;
     s.cconst = 0;
     stats[col] = s;
-    atomicMax(max_tied, (int)ntied);
+    atomicMax(max_tied, n_large > 0 ? 0x40000000 : (int)ntied);  // large groups need the heavy shape
   }
 }
 
@@ -274,7 +284,7 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
                                                         tab.trow, tab.trun, tab.nabits, tab.firstbits, tab.gstart,
-                                                        (int)tab.gstride, tab.stats, tab.max_tied);
+                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -284,7 +294,9 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        uint16_t* __restrict__ trow, uint16_t* __restrict__ trun,
                        uint32_t* __restrict__ firstbits, uint32_t* __restrict__ grpstart,
                        uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
-                       ColStats* __restrict__ stats, int32_t* __restrict__ max_tied) {
+                       uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
+                       int32_t* __restrict__ max_tied) {
+  __shared__ int n_large;
   __shared__ int warp_sums[32];
   __shared__ long long llbuf[32];
   __shared__ uint32_t bits[2048];
@@ -298,6 +310,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
   uint32_t* gpos = gpos_all + (size_t)col * (nstride + 64);
   const int n32 = (n + 31) & ~31;
   const int nwords = n32 >> 5;
+  if (tid == 0) n_large = 0;
 
   // missing rows sort first (key 0)
   long long a_ll = 0;
@@ -337,11 +350,16 @@ __global__ void __launch_bounds__(RANK_THREADS)
   long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
   for (int g = tid; g < K; g += RANK_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
+    if (g > 0 && t >= kLargeTie) {  // large tie group: also listed by (start position, size)
+      const int k = atomicAdd(&n_large, 1);
+      lgrp[(size_t)col * kLargeStride + 2 * k] = (uint16_t)gpos[g];
+      lgrp[(size_t)col * kLargeStride + 2 * k + 1] = (uint16_t)t;
+    }
+    if (g > 0 && t > 1) ntied += t;
     if (g == 0 && a > 0) continue;  // the NA group is kept apart for the local perspective
     s2 += t * (t - 1);
     s3 += t * (t - 1) * (t - 2);
     s5 += t * (t - 1) * (2 * t + 5);
-    if (g > 0 && t > 1) ntied += t;
   }
   s2 = block_sum_ll(s2, llbuf);
   s3 = block_sum_ll(s3, llbuf);
@@ -365,12 +383,14 @@ __global__ void __launch_bounds__(RANK_THREADS)
   int gcarry = 0;
   for (int t0 = 0; t0 < n32; t0 += RANK_THREADS) {
     const int t = t0 + tid;
-    int flag = 0, r = 0, gstart = 0;
+    int flag = 0, r = 0, gstart = 0, large = 0;
     uint16_t row = 0;
     if (t < n && t >= g0size) {
       row = pm[t];
       r = rk[row];
-      flag = (gpos[r + 1] - gpos[r]) > 1;
+      const uint32_t sz = gpos[r + 1] - gpos[r];
+      flag = sz > 1;
+      large = sz >= (uint32_t)kLargeTie;
       gstart = flag && (gpos[r] == (uint32_t)t);
     }
     int total, gtotal;
@@ -378,7 +398,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
     const int gincl = block_scan_excl(gstart, warp_sums, gtotal) + gstart;
     if (flag) {
       tr[carry + excl] = row;
-      tg[carry + excl] = (uint16_t)(gcarry + gincl - 1);
+      tg[carry + excl] = (uint16_t)((gcarry + gincl - 1) | (large ? kLargeFlag : 0u));
     }
     carry += total;
     gcarry += gtotal;
@@ -394,14 +414,14 @@ __global__ void __launch_bounds__(RANK_THREADS)
     while ((1 << L) < K) ++L;
     s.levels = L;
     s.g0extra = (a > 0) ? g0size - a : 0;
-    s.flags = absorb ? 1 : 0;
+    s.flags = (absorb ? 1 : 0) | (n_large << 8);
     s.n_tgroups = gcarry;
     s.s2o = s2;
     s.s3o = s3;
     s.s5o = s5;
     s.cconst = 0;
     stats[col] = s;
-    atomicMax(max_tied, (int)ntied);
+    atomicMax(max_tied, n_large > 0 ? 0x40000000 : (int)ntied);
   }
 }
 
@@ -465,7 +485,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                        tab.trow, tab.trun, tab.firstbits, tab.grpstart,
-                                                       wk.gpos, tab.gstart, (int)tab.gstride, tab.stats, tab.max_tied);
+                                                       wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
   }

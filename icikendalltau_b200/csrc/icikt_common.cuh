@@ -29,13 +29,21 @@ struct ColStats {
   int32_t n_groups;   // K: number of groups (distinct values, NA group included)
   int32_t levels;     // L = max(1, ceil(log2 K)): bits of a dense rank
   int32_t g0extra;    // non-missing rows merged into the NA group
-  int32_t flags;      // bit 0: the missing rows tie with the minimum
+  int32_t flags;      // bit 0: the missing rows tie with the minimum; bits 8..: number of large tie groups
   int32_t n_tgroups;  // number of tie groups of size > 1 other than the first group
   int64_t s2o;        // sum t(t-1)        over groups other than the NA group
   int64_t s3o;        // sum t(t-1)(t-2)
   int64_t s5o;        // sum t(t-1)(2t+5)
   uint64_t cconst;    // pass-A correction constant (see icikt_pairs.cu)
 };
+
+// Tie groups (other than the first) of at least this many rows are "large": the pair kernel
+// writes them into the sequence already sorted by the other column (rank histogram, like the
+// first group); the rows of the smaller groups are compared directly inside their group.  In the
+// tied-row list the rows of large groups carry kLargeFlag in their group index.
+constexpr int kLargeTie = 64;
+constexpr int kLargeStride = 2048;  // u16 per column in the large-group table: (start, size) x 1024
+constexpr unsigned kLargeFlag = 0x8000u;
 
 struct PairOut {
   double tau, pvalue, taumax, completeness;

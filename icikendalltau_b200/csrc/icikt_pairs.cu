@@ -590,6 +590,139 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
   return ties;
 }
 
+// Small tie groups of x (fewer than kLargeTie rows, other than the first): the inversions and the
+// joint ties inside each group by direct comparison.  `keys` receives (group index << 16 | y rank)
+// of all m tied rows of x in x order (rows of large groups carry kLargeFlag and are skipped); every
+// thread takes a row and walks forward to the end of its group -- the lanes of a warp read
+// consecutive words.  At most kLargeTie/2 comparisons per row, one for the usual isolated tie.
+template <bool G>
+__device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, const int m,
+                                                    const uint16_t* __restrict__ trow,
+                                                    const uint16_t* __restrict__ trun,
+                                                    typename Mem<G>::ptr rank_tbl, uint32_t& inv, uint32_t& ties) {
+  typedef Mem<G> M;
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int t = tid; t < m; t += T)
+    M::st32(M::add(keys, t << 2), ((uint32_t)trun[t] << 16) | M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)trow[t] << 1))));
+  __syncthreads();
+  for (int k = tid; k < m; k += T) {
+    const uint32_t mine = M::ld32(M::add(keys, k << 2));
+    if (mine & (kLargeFlag << 16)) continue;
+    for (int j = k + 1; j < m; ++j) {
+      const uint32_t other = M::ld32(M::add(keys, j << 2));
+      if ((other ^ mine) >= 0x10000u) break;  // next group
+      inv += (other < mine);
+      ties += (other == mine);
+    }
+  }
+  __syncthreads();
+}
+
+// Large tie groups of x (other than the first): their rows' y-ranks, already gathered into the
+// sequence in x order, are rewritten in ascending order group by group, so that the groups
+// contribute no inversions to pass A and their rows need not go through the bucketed pass B.
+// Same histogram technique as group_hist, several groups per round: bin = (group in batch) * K + rank,
+// as many groups per batch as the counter area holds.  Returns (summed over the threads) the joint
+// ties inside those groups.  `pre` is a shared array of 256 words; `lg` the column's (start, size) table.
+template <bool G>
+__device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
+                                                        const int hist_words, const uint16_t* __restrict__ permX,
+                                                        typename Mem<G>::ptr rank_tbl, const int K,
+                                                        const uint16_t* __restrict__ lg, const int nlg,
+                                                        uint32_t* __restrict__ pre, uint32_t* __restrict__ list,
+                                                        const int list_cap, uint32_t* descT, uint32_t* list_n,
+                                                        const int nwarps) {
+  typedef Mem<G> M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  const int gb_max = max(1, min(255, (2 * hist_words) / K));  // groups per batch (pre[] holds 256 words)
+  uint32_t ties = 0;
+  for (int g0 = 0; g0 < nlg; g0 += gb_max) {
+    const int nb = min(gb_max, nlg - g0);
+    const int bins = nb * K, hw = (bins + 1) >> 1, wpt = (hw + T - 1) / T;
+    if (tid == 0) {
+      uint32_t acc = 0;
+      for (int j = 0; j < nb; ++j) {
+        pre[j] = acc;
+        acc += lg[2 * (g0 + j) + 1];
+      }
+      pre[nb] = acc;
+      *list_n = 0u;
+    }
+    for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {  // 1. histogram; rows of one bin met by several lanes are added once
+      const int s0 = lg[2 * (g0 + j)], t = lg[2 * (g0 + j) + 1];
+      for (int qw = tid & ~31; qw < t; qw += T) {  // warp-uniform trip count
+        const int q = qw + lane;
+        uint32_t bin = 0x80000000u | (uint32_t)lane;  // idle lanes: a key of their own
+        if (q < t) bin = (uint32_t)(j * K) + M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)permX[s0 + q] << 1)));
+        const uint32_t peers = __match_any_sync(FULL, bin);
+        if (q < t && (peers & ((1u << lane) - 1u)) == 0u)
+          M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), (uint32_t)__popc(peers) << ((bin & 1u) * 16u));
+      }
+    }
+    __syncthreads();
+    // 2. rows per thread range of counters, block scan
+    const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
+    uint32_t mine = 0;
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t c = M::ld32(M::add(hist, w << 2));
+      mine += (c & 0xffffu) + (c >> 16);
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) descT[warp] = incl;
+    __syncthreads();
+    const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+    uint32_t pos = __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
+    // 3. write the runs: rank r of group j goes to start_j + (rows of the batch before it) - (rows of earlier groups)
+    int b = 2 * w0;
+    int j = b / K, r = b - j * K;
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t cw = M::ld32(M::add(hist, w << 2));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
+        if (b < bins && c != 0u) {
+          const uint32_t dst = (uint32_t)lg[2 * (g0 + j)] + (pos - pre[j]);
+          if (c == 1u) {
+            M::st16(M::add(buf, (int32_t)(dst << 1)), (uint32_t)r);
+          } else {
+            ties += (c * (c - 1u)) >> 1;
+            uint32_t slot = 0xffffffffu;
+            if (c >= 48u) slot = atomicAdd(list_n, 1u);
+            if (slot < (uint32_t)list_cap) {
+              list[3 * slot + 0] = (uint32_t)r;
+              list[3 * slot + 1] = dst;
+              list[3 * slot + 2] = c;
+            } else {
+              for (uint32_t k = 0; k < c; ++k) M::st16(M::add(buf, (int32_t)((dst + k) << 1)), (uint32_t)r);
+            }
+          }
+          pos += c;
+        }
+        ++b;
+        if (++r == K) {
+          r = 0;
+          ++j;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t nl = min(*list_n, (uint32_t)list_cap);
+    for (uint32_t e = 0; e < nl; ++e) {
+      const uint32_t r2 = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
+      for (uint32_t k = tid; k < c; k += T) M::st16(M::add(buf, (int32_t)((off + k) << 1)), r2);
+    }
+    __syncthreads();
+  }
+  return ties;
+}
+
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
@@ -610,6 +743,8 @@ struct TiledParams {
   PairComplete* pw;              // complete-observations mode: per-pair counts on the shared rows
   const uint16_t* gstart;        // [C][gstride] group-start table (complete-observations mode)
   int gstride;
+  const uint16_t* lgrp;          // [C][kLargeStride] large tie groups: (start position, size)
+  int region_bytes;              // ping-pong region of this launch: 4*cap (light ties) or 8*cap
   unsigned long long* unit_counter;
   unsigned char* scratch;        // global-memory variant: per-CTA ping-pong region
   long long scratch_stride;      // bytes per CTA
@@ -793,14 +928,25 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         }
         __syncthreads();
       }
+      // Tied x groups other than the first: small ones are compared directly (before anything is
+      // written into the sequence buffer), large ones are sorted by y in place after the gather.
+      // If the large groups' rank counters would cost more than pass B (very many distinct y
+      // values x very many large groups), pass B does all tied rows after pass A instead.
+      const int m = XS.n_tied, nlg = XS.flags >> 8;
+      const bool heavy_region = p.region_bytes >= 8 * cap;
+      const bool by_pass_b = nlg > 0 && (!heavy_region || (long long)nlg * YS.n_groups > 16LL * cap);
+      uint32_t accB = 0;
+      if (m > 0 && !by_pass_b)
+        small_groups_direct<G>(heavy_region ? M::add(bufA, 4 * cap) : bufA, m, p.trow + (size_t)xcol * p.nstride,
+                               p.trun + (size_t)xcol * p.nstride, rank_tbl, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
       if (f > 0) {
         if (PW && XS.n_na > 0)
-          ties = group_hist<G, true, true, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
+          ties += group_hist<G, true, true, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
                                                   sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
                                                   nwarps, p.gstart + (size_t)ycol * p.gstride, YS.n_na, pwy);
         else
-          ties = group_hist<G, true, false, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
+          ties += group_hist<G, true, false, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
                                                    sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
                                                    nwarps, nullptr, 0, pwy);
       }
@@ -840,11 +986,17 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         }
       }
       __syncthreads();
-      uint32_t accB = 0;
+      if (nlg > 0 && !by_pass_b) {
+        // large tie groups of x: sorted by y in place (the counters live in the upper half of the
+        // heavy region)
+        ties += large_groups_sorted<G>(bufA, M::add(bufA, 4 * cap), cap, permX, rank_tbl, YS.n_groups,
+                                       p.lgrp + (size_t)xcol * kLargeStride, nlg,
+                                       reinterpret_cast<uint32_t*>(sm.red), sm.fmask, fmask_words(nwarps, kkc) / 3,
+                                       sm.descT, sm.mini + 16, nwarps);
+      }
       unsigned long long accA = 0;
       count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
-      const int m = XS.n_tied;
-      if (m > 0) {
+      if (m > 0 && by_pass_b) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
         const int capB = (nwarps * kkB) << 5;
         const uint16_t* trow = p.trow + (size_t)xcol * p.nstride;
@@ -1190,6 +1342,8 @@ TiledParams make_params(const PairLaunch& pl) {
   p.pw = pl.pw;
   p.gstart = t.gstart;
   p.gstride = (int)t.gstride;
+  p.lgrp = t.lgrp;
+  p.region_bytes = 0;
   p.unit_counter = pl.unit_counter;
   p.n_units = pl.n_units;
   p.n = (int)t.n;
@@ -1264,7 +1418,9 @@ TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm) {
   auto region_of = [&](int w) {
     const int cap = w * odd_runs(n, w) * 256;
     const int capB = w * ((mchunks + w - 1) / w) * 32;
-    return (std::max(2 * 2 * cap, 2 * 4 * capB) + 15) & ~15;
+    // pass A: two u16 buffers; heavy shapes: + as much again for the tied rows' keys, the rank
+    // counters of the large tie groups, or pass B's two u32 buffers
+    return (std::max((mchunks > 0 ? 8 : 4) * cap, 2 * 4 * capB) + 15) & ~15;
   };
   auto smem_of = [&](int w) {
     return tiled_smem_bytes(region_of(w), (int)wstride, fmask_words(w, odd_runs(n, w) << 3));
@@ -1328,8 +1484,8 @@ int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-// Three register classes of the same code (64 / 40 / 32 registers per thread): take the one
-// that keeps the most threads resident for this shared-memory footprint, the roomier on ties.
+// Three register classes of the same code (64 / 40 / 32 registers per thread): take the roomiest
+// one unless a tighter class keeps clearly more threads resident for this shared-memory footprint.
 template <bool G>
 int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, cudaStream_t stream) {
   const int threads = 32 * sh.warps;
@@ -1345,9 +1501,10 @@ int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, 
   const int o64 = tiled_occupancy<1024, 1, G>(threads, smem);
   const int o40 = tiled_occupancy<512, 3, G>(threads, smem);
   const int o32 = tiled_occupancy<1024, 2, G>(threads, smem);
+  // the tighter classes spill: they have to buy at least a quarter more resident CTAs
   int cls = 0, best = o64;
-  if (o40 > best) { cls = 1; best = o40; }
-  if (o32 > best) { cls = 2; best = o32; }
+  if (4 * o40 >= 5 * best) { cls = 1; best = o40; }
+  if (4 * o32 >= 5 * best) { cls = 2; best = o32; }
   if (const char* e = getenv("ICIKT_REGCLASS")) {
     const int v = atoi(e);
     if (v == 0 && o64 > 0) { cls = 0; best = o64; }
@@ -1372,6 +1529,7 @@ int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int
   p.tied_le = tied_le;
   p.tied_gt = tied_gt;
   p.kk = sh.kk;
+  p.region_bytes = sh.region_bytes;
   p.scratch = pl.scratch;
   p.scratch_stride = sh.scratch_stride;
   const int fw = fmask_words(sh.warps, sh.kk << 3);

@@ -1,15 +1,10 @@
 set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$? | tee -a gpurun_out/pytest_gpu.log
 tail -30 gpurun_out/pytest_gpu.log
-python - <<'PY' > gpurun_out/multi_call.log 2>&1
-import time, numpy as np
-import icikendalltau_b200 as ik
-from icikendalltau_b200 import synth, _lib
-nd = _lib.load().icikt_device_count()
-x, _ = synth.make("target", C=1200)
-for devs in ([0], list(range(nd))):
-    ik.run_pairs(x, (), devices=devs)
-    t0 = time.perf_counter(); r = ik.run_pairs(x, (), devices=devs); dt = time.perf_counter() - t0
-    print("devices", devs, "pairs", r["raw"].size, "seconds %.3f" % dt, "pairs/s %.4g" % (r["raw"].size / dt), r["timings"])
-PY
-cat gpurun_out/multi_call.log
+python tools/gpu_diag.py > gpurun_out/diag.log 2>&1; tail -2 gpurun_out/diag.log
+for r in 5000 20000 40000; do
+python bench.py --workload config4 --rows $r --cols 300 --steps 3 --warmup 3 --quick 2>/dev/null | tail -1 > gpurun_out/q_counts_$r.json
+done
+python bench.py --workload config4 --steps 2 --warmup 3 --quick 2>/dev/null | tail -1 > gpurun_out/q_counts_60000.json
+python bench.py --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/q_config2.json
+python bench.py --workload target --steps 3 --warmup 3 --quick 2>/dev/null | tail -1 > gpurun_out/q_target.json
