@@ -11,13 +11,14 @@ import numpy as np
 
 WORKLOADS = {
     # name: (n_features, n_samples, censor quantile, perspective, kind)
+    "config1": (6887, 96, 0.0, "global", "yeast"),  # the bundled data set, zeros missing (tests/golden)
     "config2": (5000, 100, 0.20, "global", "lognormal"),
     "config3": (20000, 1000, 0.25, "local", "lognormal"),
     "config4": (60000, 200, 0.0, "global", "counts"),
     "config5": (2000, 5000, 0.20, "global", "lognormal"),
     "target": (20000, 2000, 0.25, "global", "lognormal"),
 }
-SEEDS = {"config2": 1002, "config3": 1003, "config4": 1004, "config5": 1005, "target": 1006}
+SEEDS = {"config1": 1001, "config2": 1002, "config3": 1003, "config4": 1004, "config5": 1005, "target": 1006}
 
 
 def left_censored(n, C, q, seed):
@@ -53,6 +54,14 @@ def make(name, n=None, C=None, seed=None):
     n0, C0, q, persp, kind = WORKLOADS[name]
     n, C = n or n0, C or C0
     seed = SEEDS[name] if seed is None else seed
+    if kind == "yeast":
+        # BASELINE config 1: the reference's bundled yeast RNA-seq counts (6 887 x 96), zeros -> missing
+        # as ici_kendalltau's default global_na does; fixture made by tests/golden/make_golden.py
+        import os
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        x = np.array(np.load(os.path.join(here, "tests", "golden", "yeast_missing.npz"))["data"], dtype=np.float64)
+        x[x == 0] = np.nan
+        return np.asfortranarray(x[:n, :C]), persp
     if kind == "counts":
         return count_matrix(n, C, seed, min_present=min(14000, max(2, n // 4))), persp
     return left_censored(n, C, q, seed), persp
