@@ -71,11 +71,10 @@ struct icikt_plan {
   ColumnTables tab;
   ColumnWork wk;
   bool columns_done = false;
-  // launch shapes of the pair kernel: `shape` for columns whose tied-row lists fit beside the
-  // pass-A buffers (the common case), `shape_heavy` for anything up to every row tied.  Both are
-  // enqueued; the device-side max over the columns picks the one that runs (no host round trip).
-  TiledShape shape, shape_heavy;
-  int tied_split = 0x7fffffff;  // max_tied <= tied_split runs `shape`
+  // launch shapes of the pair kernel, one per tier (see tiled_shape): no large tie groups /
+  // large tie groups sorted in place / pass B.  All are enqueued; the device-side maxima over the
+  // columns pick the one that runs (no host round trip).
+  TiledShape shape, shape_mid, shape_heavy;
   unsigned char* d_scratch = nullptr;  // global-memory variant of the pair kernel
   size_t scratch_bytes = 0;
 
@@ -115,6 +114,7 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->tab.rank);
   cudaFree(p->tab.trow);
   cudaFree(p->tab.trun);
+  cudaFree(p->tab.tend);
   cudaFree(p->tab.nabits);
   cudaFree(p->tab.firstbits);
   cudaFree(p->tab.grpstart);
@@ -341,6 +341,7 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.rank, ne));
   PCK(dmalloc(&t.trow, ne));
   PCK(dmalloc(&t.trun, ne));
+  PCK(dmalloc(&t.tend, ne));
   PCK(dmalloc(&t.nabits, nw));
   PCK(dmalloc(&t.firstbits, nw));
   PCK(dmalloc(&t.grpstart, nw));
@@ -348,12 +349,12 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.gstart, (size_t)t.gstride * C));
   PCK(dmalloc(&t.lgrp, (size_t)kLargeStride * C));
   PCK(dmalloc(&t.stats, (size_t)C));
-  PCK(dmalloc(&t.max_tied, 1));
+  PCK(dmalloc(&t.max_tied, 4));
   // padding words of the bit arrays (beyond n32/32) are never written by the kernels
   PCK(cudaMemsetAsync(t.nabits, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.firstbits, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.grpstart, 0, sizeof(uint32_t) * nw, p->stream));
-  PCK(cudaMemsetAsync(t.max_tied, 0, sizeof(int32_t), p->stream));
+  PCK(cudaMemsetAsync(t.max_tied, 0, 4 * sizeof(int32_t), p->stream));
   p->shape = tiled_shape(n, 0, t.wstride, p->n_sm);
   PCK(dmalloc(&p->wk.keys_in, ne));
   PCK(dmalloc(&p->wk.keys_out, ne));
@@ -448,23 +449,20 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   }
   if (nlit) CK(cudaMemcpyAsync(p->d_global_na, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, p->stream));
   CK(cudaEventRecord(p->ev[2], p->stream));
-  // worst-case shape (every row tied) decides whether the global scratch may be needed at all
+  // the largest tier decides whether the global scratch may be needed at all
   p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm);
-  p->shape_heavy = tiled_shape(p->n, p->n, p->tab.wstride, p->n_sm);
+  p->shape_mid = tiled_shape(p->n, 1, p->tab.wstride, p->n_sm);
+  p->shape_heavy = tiled_shape(p->n, 2, p->tab.wstride, p->n_sm);
   const TiledShape& worst = p->shape_heavy;
   const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
-  const int slot_ctas = std::max(worst.max_ctas, p->n_sm * 2);
+  const int slot_ctas = std::max(std::max(worst.max_ctas, p->shape.max_ctas), std::max(p->shape_mid.max_ctas, p->n_sm * 2));
   if ((worst.gmem || worst.const_gmem) && !p->d_scratch) {
     p->scratch_bytes = (size_t)slot_ctas * (size_t)slot_bytes;
     CK(cudaMalloc(reinterpret_cast<void**>(&p->d_scratch), p->scratch_bytes));
   }
-  p->shape.scratch_stride = p->shape_heavy.scratch_stride = p->d_scratch ? slot_bytes : 0;
-  p->shape.scratch_ctas = p->shape_heavy.scratch_ctas = p->d_scratch ? slot_ctas : 0;
-  if (p->shape.gmem || (p->shape.warps == p->shape_heavy.warps && p->shape.region_bytes == p->shape_heavy.region_bytes)) {
-    p->shape = p->shape_heavy;  // one shape serves every column
-    p->tied_split = 0x7fffffff;
-  } else {
-    p->tied_split = tiled_tied_capacity(p->shape);
+  for (TiledShape* sh : {&p->shape, &p->shape_mid, &p->shape_heavy}) {
+    sh->scratch_stride = p->d_scratch ? slot_bytes : 0;
+    sh->scratch_ctas = p->d_scratch ? slot_ctas : 0;
   }
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
                                p->d_scratch, p->stream);
@@ -501,10 +499,14 @@ int icikt_plan_pairs(icikt_plan* p) {
     if (p->opts.kernel == ICIKT_KERNEL_NAIVE)
       l = launch_pairs_naive(pl, p->P, p->d_naive, p->naive_threads, p->stream);
     else {
-      l = launch_pairs_tiled(pl, p->shape, p->n_sm, p->tied_split, -1, p->stream);
-      if (l > 0 && p->tied_split != 0x7fffffff) {
-        const int l2 = launch_pairs_tiled(pl, p->shape_heavy, p->n_sm, 0x7fffffff, p->tied_split, p->stream);
+      l = launch_pairs_tiled(pl, p->shape, p->n_sm, 0, p->stream);
+      if (l > 0) {
+        const int l2 = launch_pairs_tiled(pl, p->shape_mid, p->n_sm, 1, p->stream);
         l = l2 < 0 ? l2 : l + l2;
+      }
+      if (l > 0) {
+        const int l3 = launch_pairs_tiled(pl, p->shape_heavy, p->n_sm, 2, p->stream);
+        l = l3 < 0 ? l3 : l + l3;
       }
     }
     if (l == -2)

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
     column_fused_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
                         const double* __restrict__ global_na, int n_global_na, int na_inf,
                         uint16_t* __restrict__ perm, uint16_t* __restrict__ rank, uint16_t* __restrict__ trow,
-                        uint16_t* __restrict__ trun, uint32_t* __restrict__ nabits,
+                        uint16_t* __restrict__ trun, uint16_t* __restrict__ tend, uint32_t* __restrict__ nabits,
                         uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
                         uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
                         int32_t* __restrict__ max_tied) {
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
   const int first_run = g0size > 1 ? g0size : 0;
   // membership mask of the first group; rows of the other tied groups with their dense group index
   uint32_t tmask = 0, gmask = 0, lmask = 0;
+  int after[ITEMS];  // rows of the item's group from the item to the group's end (tied items only)
   {
     int r = excl - 1;
 #pragma unroll
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const bool tied = sz > 1;
         tmask |= (uint32_t)tied << i;
         lmask |= (uint32_t)(sz >= kLargeTie) << i;
+        after[i] = (int)gpos[r + 1] - t;
         gmask |= (uint32_t)(tied && (int)gpos[r] == t) << i;
       }
     }
@@ -239,12 +241,15 @@ __global__ void __launch_bounds__(SORT_THREADS)
     int pos = excl2 & 0xffff, gcount = excl2 >> 16;
     uint16_t* tr = trow + (size_t)col * nstride;
     uint16_t* tg = trun + (size_t)col * nstride;
+    uint16_t* te = tend + (size_t)col * nstride;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
       if ((gmask >> i) & 1u) ++gcount;
       if ((tmask >> i) & 1u) {
+        const bool large = (lmask >> i) & 1u;
         tr[pos] = vals[i];
-        tg[pos] = (uint16_t)((gcount - 1) | (((lmask >> i) & 1u) ? kLargeFlag : 0u));
+        tg[pos] = (uint16_t)((gcount - 1) | (large ? kLargeFlag : 0u));
+        te[pos] = (uint16_t)(large ? pos : pos + after[i]);  // tied rows of a group are consecutive in the list
         ++pos;
       }
     }
@@ -268,7 +273,12 @@ __global__ void __launch_bounds__(SORT_THREADS)
     s.s5o = s5;
     s.cconst = 0;
     stats[col] = s;
-    atomicMax(max_tied, n_large > 0 ? 0x40000000 : (int)ntied);  // large groups need the heavy shape
+    // what the pair kernel's launch tiers are selected by (on the device)
+    if (n_large > 0) {
+      atomicMax(max_tied + 0, 1);
+      atomicMax(max_tied + 1, n_large);
+    }
+    atomicMax(max_tied + 2, K);
   }
 }
 
@@ -283,7 +293,7 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
-                                                        tab.trow, tab.trun, tab.nabits, tab.firstbits, tab.gstart,
+                                                        tab.trow, tab.trun, tab.tend, tab.nabits, tab.firstbits, tab.gstart,
                                                         (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -291,7 +301,7 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
 __global__ void __launch_bounds__(RANK_THREADS)
     column_rank_kernel(const unsigned long long* __restrict__ skeys, int n, int nstride, int wstride,
                        uint16_t* __restrict__ perm, uint16_t* __restrict__ rank,
-                       uint16_t* __restrict__ trow, uint16_t* __restrict__ trun,
+                       uint16_t* __restrict__ trow, uint16_t* __restrict__ trun, uint16_t* __restrict__ tend,
                        uint32_t* __restrict__ firstbits, uint32_t* __restrict__ grpstart,
                        uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
                        uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
@@ -307,6 +317,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
   uint16_t* rk = rank + (size_t)col * nstride;
   uint16_t* tr = trow + (size_t)col * nstride;
   uint16_t* tg = trun + (size_t)col * nstride;
+  uint16_t* te = tend + (size_t)col * nstride;
   uint32_t* gpos = gpos_all + (size_t)col * (nstride + 64);
   const int n32 = (n + 31) & ~31;
   const int nwords = n32 >> 5;
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
   int gcarry = 0;
   for (int t0 = 0; t0 < n32; t0 += RANK_THREADS) {
     const int t = t0 + tid;
-    int flag = 0, r = 0, gstart = 0, large = 0;
+    int flag = 0, r = 0, gstart = 0, large = 0, after = 0;
     uint16_t row = 0;
     if (t < n && t >= g0size) {
       row = pm[t];
@@ -391,6 +402,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
       const uint32_t sz = gpos[r + 1] - gpos[r];
       flag = sz > 1;
       large = sz >= (uint32_t)kLargeTie;
+      after = (int)gpos[r + 1] - t;
       gstart = flag && (gpos[r] == (uint32_t)t);
     }
     int total, gtotal;
@@ -399,6 +411,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
     if (flag) {
       tr[carry + excl] = row;
       tg[carry + excl] = (uint16_t)((gcarry + gincl - 1) | (large ? kLargeFlag : 0u));
+      te[carry + excl] = (uint16_t)(large ? carry + excl : carry + excl + after);
     }
     carry += total;
     gcarry += gtotal;
@@ -421,7 +434,11 @@ __global__ void __launch_bounds__(RANK_THREADS)
     s.s5o = s5;
     s.cconst = 0;
     stats[col] = s;
-    atomicMax(max_tied, n_large > 0 ? 0x40000000 : (int)ntied);
+    if (n_large > 0) {
+      atomicMax(max_tied + 0, 1);
+      atomicMax(max_tied + 1, n_large);
+    }
+    atomicMax(max_tied + 2, K);
   }
 }
 
@@ -454,7 +471,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   // the bit arrays are written in full (words below n32/32) by the kernels below; the padding
   // words up to wstride were zeroed once when the plan was created
   const int items = (n + SORT_THREADS - 1) / SORT_THREADS;
-  if (cudaMemsetAsync(tab.max_tied, 0, sizeof(int32_t), stream) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
   if (items <= 16 && !getenv("ICIKT_NO_FUSED_COLUMNS")) {
     int l;
     if (items <= 2) l = launch_column_fused<2>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
@@ -484,7 +501,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
       return -1;
     launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
-                                                       tab.trow, tab.trun, tab.firstbits, tab.grpstart,
+                                                       tab.trow, tab.trun, tab.tend, tab.firstbits, tab.grpstart,
                                                        wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;

@@ -18,7 +18,9 @@ struct ColumnTables {
   uint16_t* perm = nullptr;       // [C][nstride] row ids in ascending value order, missing first
   uint16_t* rank = nullptr;       // [C][nstride] dense rank of every row
   uint16_t* trow = nullptr;       // [C][nstride] rows of tied (non-first-group) elements, sorted order
-  uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1)
+  uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1), | kLargeFlag
+  uint16_t* tend = nullptr;       // [C][nstride] index in the tied-row list one past the row's group
+                                  //              (= the row's own index for rows of large groups)
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
   uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group (long-column path only)
@@ -26,7 +28,7 @@ struct ColumnTables {
   uint16_t* gstart = nullptr;     // [C][gstride] sorted position where the group of dense rank r starts; [K] = n
   int64_t gstride = 0;            // nstride + 64
   ColStats* stats = nullptr;      // [C]
-  int32_t* max_tied = nullptr;    // [1] max over columns of ColStats::n_tied
+  int32_t* max_tied = nullptr;    // [4] over the columns: [0] any large tie group, [1] max large groups, [2] max distinct values
 };
 
 // A unit of pair work: column `col` is staged in shared memory and correlated with
@@ -55,7 +57,11 @@ struct TiledShape {
   int scratch_stride = 0;
   int scratch_ctas = 0;
 };
-TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm);
+// tier 0: no column has a large tie group (region = pass A's two u16 buffers, 4*cap bytes);
+// tier 1: large tie groups, sorted in place with rank counters in a fifth quarter (5*cap);
+// tier 2: so many large groups x distinct values that pass B takes the tied rows instead (8*cap).
+// Every tier is enqueued; the launch reads K1's device-side maxima and exits if it is not its turn.
+TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm);
 
 struct PairLaunch {
   const ColumnTables* tab;
@@ -90,11 +96,8 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
 int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream);
 
 // K2 (tiled) and K2-naive; both fill raw[P].
-// runs only if tied_gt < max_tied (device value written by K1) <= tied_le; unit_counter must be zero
-int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int tied_le, int tied_gt,
-                       cudaStream_t stream);
-// longest tied-row list (rows) the shape's shared-memory region can take in pass B
-int tiled_tied_capacity(const TiledShape& sh);
+// runs only if the device-side maxima written by K1 select `tier`; unit_counter must be zero
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int tier, cudaStream_t stream);
 int launch_pairs_naive(const PairLaunch& pl, int64_t P, uint32_t* d_scratch, int64_t n_threads,
                        cudaStream_t stream);
 size_t naive_scratch_bytes(int64_t n, int64_t n_threads);

@@ -591,26 +591,26 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
 }
 
 // Small tie groups of x (fewer than kLargeTie rows, other than the first): the inversions and the
-// joint ties inside each group by direct comparison.  `keys` receives (group index << 16 | y rank)
-// of all m tied rows of x in x order (rows of large groups carry kLargeFlag and are skipped); every
-// thread takes a row and walks forward to the end of its group -- the lanes of a warp read
-// consecutive words.  At most kLargeTie/2 comparisons per row, one for the usual isolated tie.
+// joint ties inside each group by direct comparison.  `keys` receives the y ranks (u16) of all m
+// tied rows of x in x order; every thread takes a row and walks forward to the end of its group
+// (tend[], from K1; rows of large groups end at themselves and are skipped) -- the lanes of a warp
+// read consecutive keys.  At most kLargeTie/2 comparisons per row, one for the usual isolated tie.
 template <bool G>
 __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, const int m,
                                                     const uint16_t* __restrict__ trow,
-                                                    const uint16_t* __restrict__ trun,
+                                                    const uint16_t* __restrict__ tend,
                                                     typename Mem<G>::ptr rank_tbl, uint32_t& inv, uint32_t& ties) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, T = blockDim.x;
   for (int t = tid; t < m; t += T)
-    M::st32(M::add(keys, t << 2), ((uint32_t)trun[t] << 16) | M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)trow[t] << 1))));
+    M::st16(M::add(keys, t << 1), M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)trow[t] << 1))));
   __syncthreads();
   for (int k = tid; k < m; k += T) {
-    const uint32_t mine = M::ld32(M::add(keys, k << 2));
-    if (mine & (kLargeFlag << 16)) continue;
-    for (int j = k + 1; j < m; ++j) {
-      const uint32_t other = M::ld32(M::add(keys, j << 2));
-      if ((other ^ mine) >= 0x10000u) break;  // next group
+    const int end = tend[k];
+    if (end <= k + 1) continue;
+    const uint32_t mine = M::ld16(M::add(keys, k << 1));
+    for (int j = k + 1; j < end; ++j) {
+      const uint32_t other = M::ld16(M::add(keys, j << 1));
       inv += (other < mine);
       ties += (other == mine);
     }
@@ -620,10 +620,11 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
 
 // Large tie groups of x (other than the first): their rows' y-ranks, already gathered into the
 // sequence in x order, are rewritten in ascending order group by group, so that the groups
-// contribute no inversions to pass A and their rows need not go through the bucketed pass B.
-// Same histogram technique as group_hist, several groups per round: bin = (group in batch) * K + rank,
-// as many groups per batch as the counter area holds.  Returns (summed over the threads) the joint
-// ties inside those groups.  `pre` is a shared array of 256 words; `lg` the column's (start, size) table.
+// contribute no inversions to pass A.  Same histogram technique as group_hist, several groups per
+// round: bin = (group in batch) * K + rank, as many groups per batch as the counter area holds; if
+// not even one group's K counters fit, one group at a time in windows of ranks.  Returns (summed
+// over the threads) the joint ties inside those groups.  `pre` is a shared array of 256 words;
+// `lg` the column's (start, size) table.
 template <bool G>
 __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                         const int hist_words, const uint16_t* __restrict__ permX,
@@ -634,91 +635,104 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
                                                         const int nwarps) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
-  const int gb_max = max(1, min(255, (2 * hist_words) / K));  // groups per batch (pre[] holds 256 words)
+  const int bins_avail = 2 * hist_words;
+  const int gb_max = max(1, min(255, bins_avail / K));  // groups per batch (pre[] holds 256 words)
+  const int Kw = min(K, bins_avail);                    // ranks per window (< K only if gb_max == 1)
   uint32_t ties = 0;
   for (int g0 = 0; g0 < nlg; g0 += gb_max) {
     const int nb = min(gb_max, nlg - g0);
-    const int bins = nb * K, hw = (bins + 1) >> 1, wpt = (hw + T - 1) / T;
-    if (tid == 0) {
-      uint32_t acc = 0;
-      for (int j = 0; j < nb; ++j) {
-        pre[j] = acc;
-        acc += lg[2 * (g0 + j) + 1];
+    uint32_t done = 0;  // rows of the (single) group written by earlier windows
+    for (int k0 = 0; k0 < K; k0 += Kw) {
+      const int kw = min(Kw, K - k0);
+      const int bins = nb * kw, hw = (bins + 1) >> 1, wpt = (hw + T - 1) / T;
+      if (tid == 0) {
+        uint32_t acc = 0;
+        for (int j = 0; j < nb; ++j) {
+          pre[j] = acc;
+          acc += lg[2 * (g0 + j) + 1];
+        }
+        *list_n = 0u;
       }
-      pre[nb] = acc;
-      *list_n = 0u;
-    }
-    for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
-    __syncthreads();
-    for (int j = 0; j < nb; ++j) {  // 1. histogram; rows of one bin met by several lanes are added once
-      const int s0 = lg[2 * (g0 + j)], t = lg[2 * (g0 + j) + 1];
-      for (int qw = tid & ~31; qw < t; qw += T) {  // warp-uniform trip count
-        const int q = qw + lane;
-        uint32_t bin = 0x80000000u | (uint32_t)lane;  // idle lanes: a key of their own
-        if (q < t) bin = (uint32_t)(j * K) + M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)permX[s0 + q] << 1)));
-        const uint32_t peers = __match_any_sync(FULL, bin);
-        if (q < t && (peers & ((1u << lane) - 1u)) == 0u)
-          M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), (uint32_t)__popc(peers) << ((bin & 1u) * 16u));
-      }
-    }
-    __syncthreads();
-    // 2. rows per thread range of counters, block scan
-    const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
-    uint32_t mine = 0;
-    for (int w = w0; w < w1; ++w) {
-      const uint32_t c = M::ld32(M::add(hist, w << 2));
-      mine += (c & 0xffffu) + (c >> 16);
-    }
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl += t;
-    }
-    if (lane == 31) descT[warp] = incl;
-    __syncthreads();
-    const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
-    uint32_t pos = __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
-    // 3. write the runs: rank r of group j goes to start_j + (rows of the batch before it) - (rows of earlier groups)
-    int b = 2 * w0;
-    int j = b / K, r = b - j * K;
-    for (int w = w0; w < w1; ++w) {
-      const uint32_t cw = M::ld32(M::add(hist, w << 2));
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
-        if (b < bins && c != 0u) {
-          const uint32_t dst = (uint32_t)lg[2 * (g0 + j)] + (pos - pre[j]);
-          if (c == 1u) {
-            M::st16(M::add(buf, (int32_t)(dst << 1)), (uint32_t)r);
-          } else {
-            ties += (c * (c - 1u)) >> 1;
-            uint32_t slot = 0xffffffffu;
-            if (c >= 48u) slot = atomicAdd(list_n, 1u);
-            if (slot < (uint32_t)list_cap) {
-              list[3 * slot + 0] = (uint32_t)r;
-              list[3 * slot + 1] = dst;
-              list[3 * slot + 2] = c;
-            } else {
-              for (uint32_t k = 0; k < c; ++k) M::st16(M::add(buf, (int32_t)((dst + k) << 1)), (uint32_t)r);
-            }
+      for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
+      __syncthreads();
+      for (int j = 0; j < nb; ++j) {  // 1. histogram; rows of one bin met by several lanes are added once
+        const int s0 = lg[2 * (g0 + j)], t = lg[2 * (g0 + j) + 1];
+        for (int qw = tid & ~31; qw < t; qw += T) {  // warp-uniform trip count
+          const int q = qw + lane;
+          uint32_t bin = 0x80000000u | (uint32_t)lane;  // idle lanes: a key of their own
+          bool in = false;
+          if (q < t) {
+            const uint32_t r = M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)permX[s0 + q] << 1))) - (uint32_t)k0;
+            in = r < (uint32_t)kw;
+            if (in) bin = (uint32_t)(j * kw) + r;
           }
-          pos += c;
-        }
-        ++b;
-        if (++r == K) {
-          r = 0;
-          ++j;
+          const uint32_t peers = __match_any_sync(FULL, bin);
+          if (in && (peers & ((1u << lane) - 1u)) == 0u)
+            M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), (uint32_t)__popc(peers) << ((bin & 1u) * 16u));
         }
       }
+      __syncthreads();
+      // 2. rows per thread range of counters, block scan
+      const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
+      uint32_t mine = 0;
+      for (int w = w0; w < w1; ++w) {
+        const uint32_t c = M::ld32(M::add(hist, w << 2));
+        mine += (c & 0xffffu) + (c >> 16);
+      }
+      uint32_t incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) descT[warp] = incl;
+      __syncthreads();
+      const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+      const uint32_t total = __reduce_add_sync(FULL, v);
+      uint32_t pos = __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
+      // 3. write the runs: rank r of group j goes to start_j + (rows of the batch before it) - (rows of earlier groups)
+      int b = 2 * w0;
+      int j = b / kw, r = b - j * kw;
+      for (int w = w0; w < w1; ++w) {
+        const uint32_t cw = M::ld32(M::add(hist, w << 2));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
+          if (b < bins && c != 0u) {
+            const uint32_t dst = (uint32_t)lg[2 * (g0 + j)] + done + (pos - (kw == K ? pre[j] : 0u));
+            const uint32_t rank = (uint32_t)(k0 + r);
+            if (c == 1u) {
+              M::st16(M::add(buf, (int32_t)(dst << 1)), rank);
+            } else {
+              ties += (c * (c - 1u)) >> 1;
+              uint32_t slot = 0xffffffffu;
+              if (c >= 48u) slot = atomicAdd(list_n, 1u);
+              if (slot < (uint32_t)list_cap) {
+                list[3 * slot + 0] = rank;
+                list[3 * slot + 1] = dst;
+                list[3 * slot + 2] = c;
+              } else {
+                for (uint32_t k = 0; k < c; ++k) M::st16(M::add(buf, (int32_t)((dst + k) << 1)), rank);
+              }
+            }
+            pos += c;
+          }
+          ++b;
+          if (++r == kw) {
+            r = 0;
+            ++j;
+          }
+        }
+      }
+      done += total;
+      __syncthreads();
+      const uint32_t nl = min(*list_n, (uint32_t)list_cap);
+      for (uint32_t e = 0; e < nl; ++e) {
+        const uint32_t r2 = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
+        for (uint32_t k = tid; k < c; k += T) M::st16(M::add(buf, (int32_t)((off + k) << 1)), r2);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    const uint32_t nl = min(*list_n, (uint32_t)list_cap);
-    for (uint32_t e = 0; e < nl; ++e) {
-      const uint32_t r2 = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
-      for (uint32_t k = tid; k < c; k += T) M::st16(M::add(buf, (int32_t)((off + k) << 1)), r2);
-    }
-    __syncthreads();
   }
   return ties;
 }
@@ -734,6 +748,7 @@ struct TiledParams {
   const uint16_t* rank;
   const uint16_t* trow;
   const uint16_t* trun;
+  const uint16_t* tend;
   const uint32_t* nabits;
   const uint32_t* firstbits;
   const ColStats* stats;
@@ -751,11 +766,12 @@ struct TiledParams {
   long long n_units;
   int n, n32, nstride, wstride;
   int kk;  // pass A: 8-key runs per thread (odd); a warp covers 8*kk 32-element chunks
-  // the launch runs only if  tied_gt < *max_tied <= tied_le  (longest tied-row list over the
-  // columns, written by K1): lets the host enqueue the shape for light ties and the shape for
-  // heavy ties back to back without reading the value back
+  // the launch runs only if K1's device-side maxima (any large tie group, most large groups,
+  // most distinct values of a column) select its tier: lets the host enqueue the shapes of all
+  // tiers back to back without reading anything back
   const int32_t* max_tied;
-  int tied_le, tied_gt;
+  int tier;
+  long long budget;  // large groups x distinct values above which pass B takes the tied rows
   PipeConst pc;
 };
 
@@ -844,8 +860,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
   {
-    const int mt = *p.max_tied;
-    if (mt > p.tied_le || mt <= p.tied_gt) return;
+    const bool large = p.max_tied[0] != 0;
+    const bool costly = (long long)p.max_tied[1] * p.max_tied[2] > p.budget;
+    const int turn = !large ? 0 : (costly ? 2 : 1);
+    if (turn != p.tier) return;
   }
   const int n = p.n;
   const int nwords = p.n32 >> 5;
@@ -933,12 +951,11 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       // If the large groups' rank counters would cost more than pass B (very many distinct y
       // values x very many large groups), pass B does all tied rows after pass A instead.
       const int m = XS.n_tied, nlg = XS.flags >> 8;
-      const bool heavy_region = p.region_bytes >= 8 * cap;
-      const bool by_pass_b = nlg > 0 && (!heavy_region || (long long)nlg * YS.n_groups > 16LL * cap);
+      const bool by_pass_b = nlg > 0 && p.tier == 2 && (long long)nlg * YS.n_groups > p.budget;
       uint32_t accB = 0;
-      if (m > 0 && !by_pass_b)
-        small_groups_direct<G>(heavy_region ? M::add(bufA, 4 * cap) : bufA, m, p.trow + (size_t)xcol * p.nstride,
-                               p.trun + (size_t)xcol * p.nstride, rank_tbl, accB, ties);
+      if (m > 0 && !by_pass_b)  // keys: 2 m <= 2 cap bytes, the still empty sequence buffer
+        small_groups_direct<G>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tend + (size_t)xcol * p.nstride,
+                               rank_tbl, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
       if (f > 0) {
         if (PW && XS.n_na > 0)
@@ -987,9 +1004,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       }
       __syncthreads();
       if (nlg > 0 && !by_pass_b) {
-        // large tie groups of x: sorted by y in place (the counters live in the upper half of the
-        // heavy region)
-        ties += large_groups_sorted<G>(bufA, M::add(bufA, 4 * cap), cap, permX, rank_tbl, YS.n_groups,
+        // large tie groups of x: sorted by y in place (the counters live behind the two pass-A buffers)
+        ties += large_groups_sorted<G>(bufA, M::add(bufA, 4 * cap), (p.region_bytes - 4 * cap) >> 2, permX, rank_tbl, YS.n_groups,
                                        p.lgrp + (size_t)xcol * kLargeStride, nlg,
                                        reinterpret_cast<uint32_t*>(sm.red), sm.fmask, fmask_words(nwarps, kkc) / 3,
                                        sm.descT, sm.mini + 16, nwarps);
@@ -1333,6 +1349,7 @@ TiledParams make_params(const PairLaunch& pl) {
   p.rank = t.rank;
   p.trow = t.trow;
   p.trun = t.trun;
+  p.tend = t.tend;
   p.nabits = t.nabits;
   p.firstbits = t.firstbits;
   p.stats = t.stats;
@@ -1354,8 +1371,8 @@ TiledParams make_params(const PairLaunch& pl) {
   p.scratch_stride = 0;
   p.kk = 0;
   p.max_tied = t.max_tied;
-  p.tied_le = 0x7fffffff;
-  p.tied_gt = -1;
+  p.tier = 0;
+  p.budget = 16LL * t.n;
   p.pc.one = 1u;
   p.pc.two = 2u;
   p.pc.c64k = 65536u;
@@ -1365,12 +1382,6 @@ TiledParams make_params(const PairLaunch& pl) {
 }  // namespace
 
 int64_t tiled_max_n() { return 65535; }
-
-int tiled_tied_capacity(const TiledShape& sh) {
-  // pass B ping-pongs two u32 buffers of W * kkB * 32 keys inside the region
-  const int per = sh.warps * 32;
-  return (sh.region_bytes / 8) / per * per;
-}
 
 int measure_smem_bandwidth(double* gbps32, double* gbps128) {
   int dev = 0, n_sm = 0;
@@ -1412,15 +1423,13 @@ static int const_warps(int64_t n) {
 // Launch shape for vectors of length n: warps per CTA, 8-key runs per thread (odd), bytes of the
 // ping-pong region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied
 // list), and whether the region fits shared memory or has to live in the global scratch.
-TiledShape tiled_shape(int64_t n, int64_t max_tied, int64_t wstride, int n_sm) {
+TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm) {
   TiledShape sh;
-  const int mchunks = (int)((max_tied + 31) / 32);
   auto region_of = [&](int w) {
     const int cap = w * odd_runs(n, w) * 256;
-    const int capB = w * ((mchunks + w - 1) / w) * 32;
-    // pass A: two u16 buffers; heavy shapes: + as much again for the tied rows' keys, the rank
-    // counters of the large tie groups, or pass B's two u32 buffers
-    return (std::max((mchunks > 0 ? 8 : 4) * cap, 2 * 4 * capB) + 15) & ~15;
+    // pass A: two u16 buffers (4*cap bytes); + a quarter more for the rank counters of the large
+    // tie groups; or twice as much for pass B's two u32 buffers
+    return ((tier == 0 ? 4 : tier == 1 ? 5 : 8) * cap + 15) & ~15;
   };
   auto smem_of = [&](int w) {
     return tiled_smem_bytes(region_of(w), (int)wstride, fmask_words(w, odd_runs(n, w) << 3));
@@ -1523,11 +1532,9 @@ int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, 
 
 }  // namespace
 
-int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int tied_le, int tied_gt,
-                       cudaStream_t stream) {
+int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int tier, cudaStream_t stream) {
   TiledParams p = make_params(pl);
-  p.tied_le = tied_le;
-  p.tied_gt = tied_gt;
+  p.tier = tier;
   p.kk = sh.kk;
   p.region_bytes = sh.region_bytes;
   p.scratch = pl.scratch;
