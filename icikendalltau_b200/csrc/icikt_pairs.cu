@@ -1425,11 +1425,18 @@ static int const_warps(int64_t n) {
 // list), and whether the region fits shared memory or has to live in the global scratch.
 TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm) {
   TiledShape sh;
+  auto smem_with = [&](int w, int quarters) {
+    const int cap = w * odd_runs(n, w) * 256;
+    return tiled_smem_bytes((quarters * cap + 15) & ~15, (int)wstride, fmask_words(w, odd_runs(n, w) << 3));
+  };
+  // pass A: two u16 buffers (4*cap bytes).  Tier 1 adds a quarter more (cap bytes) for the rank
+  // counters of the large tie groups -- a larger counter area means fewer rounds over the large
+  // groups but fewer CTAs per SM, which measured worse (profiles/).  Tier 2: twice as much for
+  // pass B's two u32 buffers.
+  auto quarters_of = [&](int) { return tier == 0 ? 4 : tier == 1 ? 5 : 8; };
   auto region_of = [&](int w) {
     const int cap = w * odd_runs(n, w) * 256;
-    // pass A: two u16 buffers (4*cap bytes); + a quarter more for the rank counters of the large
-    // tie groups; or twice as much for pass B's two u32 buffers
-    return ((tier == 0 ? 4 : tier == 1 ? 5 : 8) * cap + 15) & ~15;
+    return (quarters_of(w) * cap + 15) & ~15;
   };
   auto smem_of = [&](int w) {
     return tiled_smem_bytes(region_of(w), (int)wstride, fmask_words(w, odd_runs(n, w) << 3));
