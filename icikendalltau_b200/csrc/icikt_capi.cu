@@ -450,9 +450,10 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   if (nlit) CK(cudaMemcpyAsync(p->d_global_na, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, p->stream));
   CK(cudaEventRecord(p->ev[2], p->stream));
   // the largest tier decides whether the global scratch may be needed at all
-  p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm);
-  p->shape_mid = tiled_shape(p->n, 1, p->tab.wstride, p->n_sm);
-  p->shape_heavy = tiled_shape(p->n, 2, p->tab.wstride, p->n_sm);
+  const int64_t n_units = (int64_t)p->units.size();
+  p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm, n_units);
+  p->shape_mid = tiled_shape(p->n, 1, p->tab.wstride, p->n_sm, n_units);
+  p->shape_heavy = tiled_shape(p->n, 2, p->tab.wstride, p->n_sm, n_units);
   const TiledShape& worst = p->shape_heavy;
   const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
   const int slot_ctas = std::max(std::max(worst.max_ctas, p->shape.max_ctas), std::max(p->shape_mid.max_ctas, p->n_sm * 2));

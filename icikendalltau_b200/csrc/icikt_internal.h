@@ -61,7 +61,7 @@ struct TiledShape {
 // tier 1: large tie groups, sorted in place with rank counters in a fifth quarter (5*cap);
 // tier 2: so many large groups x distinct values that pass B takes the tied rows instead (8*cap).
 // Every tier is enqueued; the launch reads K1's device-side maxima and exits if it is not its turn.
-TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm);
+TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n_units = 0);
 
 struct PairLaunch {
   const ColumnTables* tab;

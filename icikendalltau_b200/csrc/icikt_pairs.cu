@@ -1423,7 +1423,7 @@ static int const_warps(int64_t n) {
 // Launch shape for vectors of length n: warps per CTA, 8-key runs per thread (odd), bytes of the
 // ping-pong region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied
 // list), and whether the region fits shared memory or has to live in the global scratch.
-TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm) {
+TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n_units) {
   TiledShape sh;
   auto smem_with = [&](int w, int quarters) {
     const int cap = w * odd_runs(n, w) * 256;
@@ -1452,9 +1452,15 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm) {
     if (kk == 0) continue;
     const size_t smem = smem_of(w);
     if (smem > 227 * 1024) continue;
-    const int ctas = (int)std::min<size_t>(std::min(32, 2048 / (32 * w)), (228 * 1024) / (smem + 1024));
-    const double rw = std::min(32.0, (double)w * std::max(1, ctas));
-    const double cost = 256.0 * w * kk * (1.0 + 2.0 / kk) * std::pow(32.0 / rw, 0.4);
+    // resident CTAs per SM: threads, shared memory, registers (64 per thread in the roomy class)
+    const int ctas = std::max(1, (int)std::min<size_t>(std::min(std::min(32, 2048 / (32 * w)), 32 / w),
+                                                       (228 * 1024) / (smem + 1024)));
+    const double rw = std::min(32.0, (double)w * ctas);
+    double cost = 256.0 * w * kk * (1.0 + 2.0 / kk) * std::pow(32.0 / rw, 0.4);
+    if (n_units > 0) {  // small jobs: whole rounds of equal-cost pairs over the resident CTAs
+      const double per_cta = (double)n_units / ((double)n_sm * ctas);
+      if (per_cta < 64.0) cost *= std::ceil(per_cta) / per_cta;
+    }
     if (cost < best) { best = cost; W = w; }
   }
   if (const char* e = getenv("ICIKT_WARPS")) {
