@@ -576,3 +576,34 @@ def test_multi_gpu_call_matches_single_gpu():
     res = ik.ici_kendalltau(x, global_na=(np.nan,), colnames=[f"s{i}" for i in range(23)], n_gpus=min(2, max(ndev, 1)))
     ref = ik.ici_kendalltau(x, global_na=(np.nan,), colnames=[f"s{i}" for i in range(23)])
     np.testing.assert_array_equal(res["cor"], ref["cor"])
+
+
+@pytest.mark.gpu
+def test_random_small_matrices_all_modes():
+    """Many small random matrices with every mix of ties, missingness, constant / all-missing columns:
+    all three modes against the oracle.  Group sizes straddle the large-tie threshold (64) so that
+    direct comparison, in-place histogram sort and the first-group emission all take part."""
+    rng = np.random.default_rng(20240611)
+    for case in range(60):
+        n = int(rng.choice([2, 3, 5, 17, 64, 65, 130, 257, 400, 900]))
+        C = int(rng.integers(2, 7))
+        levels = int(rng.choice([1, 2, 3, 6, 20, 1000]))
+        x = rng.normal(size=(n, C))
+        x = np.round(x * levels / 3.0) if levels < 1000 else x
+        for c in range(C):
+            frac = float(rng.choice([0.0, 0.0, 0.1, 0.5, 0.9, 1.0]))
+            x[rng.random(n) < frac, c] = np.nan
+        x = np.asfortranarray(x)
+        pi = np.array([i for i in range(C) for j in range(C)], dtype=np.int32)
+        pj = np.array([j for i in range(C) for j in range(C)], dtype=np.int32)
+        for persp in ("global", "local"):
+            got = ik.run_pairs(x, (), pi=pi, pj=pj, perspective=persp, want_counts=True)
+            assert_parity(got, oracle_pairs(x, pi=pi, pj=pj, perspective=persp), f"case {case} n={n} {persp}")
+        got = ik.run_pairs(x, (), pi=pi, pj=pj, perspective="complete", want_counts=True)
+        ref = _oracle_complete(x, pi, pj)
+        assert np.array_equal(got["status"], ref["status"]), f"case {case} complete status"
+        ok = ref["status"] == 0
+        for k, nm in enumerate(COUNT_NAMES[:6]):
+            assert np.array_equal(got["counts"][ok, k], ref["counts"][ok, k]), f"case {case} complete {nm}"
+        np.testing.assert_allclose(got["raw"][ok], ref["raw"][ok], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(got["pvalue"][ok], ref["pvalue"][ok], rtol=1e-9, atol=0)
