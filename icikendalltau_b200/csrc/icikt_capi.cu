@@ -451,9 +451,10 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   CK(cudaEventRecord(p->ev[2], p->stream));
   // the largest tier decides whether the global scratch may be needed at all
   const int64_t n_units = (int64_t)p->units.size();
-  p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm, n_units);
-  p->shape_mid = tiled_shape(p->n, 1, p->tab.wstride, p->n_sm, n_units);
-  p->shape_heavy = tiled_shape(p->n, 2, p->tab.wstride, p->n_sm, n_units);
+  const bool inplace_ok = p->opts.perspective != ICIKT_PERSPECTIVE_COMPLETE;  // that mode has no in-place kernel
+  p->shape = tiled_shape(p->n, 0, p->tab.wstride, p->n_sm, n_units, inplace_ok);
+  p->shape_mid = tiled_shape(p->n, 1, p->tab.wstride, p->n_sm, n_units, inplace_ok);
+  p->shape_heavy = tiled_shape(p->n, 2, p->tab.wstride, p->n_sm, n_units, inplace_ok);
   const TiledShape& worst = p->shape_heavy;
   const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
   const int slot_ctas = std::max(std::max(worst.max_ctas, p->shape.max_ctas), std::max(p->shape_mid.max_ctas, p->n_sm * 2));

@@ -50,6 +50,7 @@ struct TiledShape {
   int kk = 0;            // 32-element chunks per warp (even)
   int region_bytes = 0;  // ping-pong region per CTA
   int const_region_bytes = 0;  // pass-A buffers of the per-column constant kernel (32 warps)
+  int inplace_kk = 0;    // != 0: in-place variant for long vectors (one sequence buffer, kk fixed at compile time)
   bool gmem = false;     // region lives in the global scratch (does not fit shared memory)
   bool const_gmem = false;  // same for the per-column constant kernel
   int max_ctas = 0;      // CTAs the scratch must provide for
@@ -61,7 +62,7 @@ struct TiledShape {
 // tier 1: large tie groups, sorted in place with rank counters in a fifth quarter (5*cap);
 // tier 2: so many large groups x distinct values that pass B takes the tied rows instead (8*cap).
 // Every tier is enqueued; the launch reads K1's device-side maxima and exits if it is not its turn.
-TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n_units = 0);
+TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n_units = 0, bool allow_inplace = true);
 
 struct PairLaunch {
   const ColumnTables* tab;

@@ -438,6 +438,91 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
   }
 }
 
+// Pass A for long vectors, IN PLACE: the same two-bit levels as count_pass, but a thread keeps its
+// KK runs (8*KK keys) in registers from the counting sweep to the scatter sweep, so the keys can go
+// back into the SAME buffer once every thread has read its range (the barrier that publishes the
+// warp totals guarantees that).  One u16 buffer instead of two: vectors up to 64 512 rows stay in
+// shared memory (2*cap <= 126 KB) instead of falling back to the L2-resident scratch.
+template <int KK>
+__device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int nwarps, const int L,
+                                                   uint32_t* descA, uint32_t* descB, const int lane,
+                                                   const int warp, const PipeConst pc, unsigned long long& acc64) {
+  typedef Mem<false> M;
+  const uint32_t tid = ((uint32_t)warp << 5) + (uint32_t)lane;
+  constexpr uint32_t R = (uint32_t)KK << 3;
+  const uint32_t my_off = tid * (R << 1);
+  const uint32_t my_pos = tid * R;
+  const uint32_t cap = ((uint32_t)nwarps << 5) * R;
+  const uint32_t ra = a + my_off;
+  for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
+    uint32_t w[KK][4];
+    uint32_t cl = 0, ch = 0, cb = 0;
+#pragma unroll
+    for (int c = 0; c < KK; ++c) {
+      M::ld128(ra + (c << 4), w[c][0], w[c][1], w[c][2], w[c][3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = (w[c][j] >> s) & 0x00010001u, hi = (w[c][j] >> (s + 1)) & 0x00010001u;
+        cl = M::fadd(cl, lo, pc.one);
+        ch = M::fadd(ch, hi, pc.one);
+        cb = M::fadd(cb, lo & hi, pc.one);
+      }
+    }
+    const uint32_t n3 = (cb & 0xffffu) + (cb >> 16);
+    const uint32_t n2 = (ch & 0xffffu) + (ch >> 16) - n3;
+    const uint32_t n1 = (cl & 0xffffu) + (cl >> 16) - n3;
+    const uint32_t A = n1 | (n2 << 16), B = n3;
+    uint32_t inclA = A, inclB = B;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t tA = __shfl_up_sync(FULL, inclA, d), tB = __shfl_up_sync(FULL, inclB, d);
+      if (lane >= d) {
+        inclA += tA;
+        inclB += tB;
+      }
+    }
+    if (lane == 31) {
+      descA[warp] = inclA;
+      descB[warp] = inclB;
+    }
+    __syncthreads();  // every range is in registers: the buffer may be overwritten
+    const uint32_t vA = (lane < nwarps) ? descA[lane] : 0u, vB = (lane < nwarps) ? descB[lane] : 0u;
+    const uint32_t totA = __reduce_add_sync(FULL, vA), totB = __reduce_add_sync(FULL, vB);
+    const uint32_t exA = __reduce_add_sync(FULL, (lane < warp) ? vA : 0u) + inclA - A;
+    const uint32_t exB = __reduce_add_sync(FULL, (lane < warp) ? vB : 0u) + inclB - B;
+    const uint32_t e1 = exA & 0xffffu, e2 = exA >> 16, e3 = exB;
+    const uint32_t N1 = totA & 0xffffu, N2 = totA >> 16, N3 = totB;
+    const uint32_t N0 = cap - N1 - N2 - N3;
+    uint32_t Q01 = ((N0 + e1) << 16) | (my_pos - e1 - e2 - e3);
+    uint32_t Q23 = ((N0 + N1 + N2 + e3) << 16) | (N0 + N1 + e2);
+    uint32_t S = e2 + e3, acc = 0, acc2 = 0;
+    uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
+    asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));
+    if (s > 0) {
+#pragma unroll
+      for (int c = 0; c < KK; ++c) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          M::step4(Q01, Q23, S, acc, acc2, w[c][j], bLl, bHl, w[c][j], a, pc.two);
+          M::step4(Q01, Q23, S, acc, acc2, w[c][j], bLh, bHh, M::hi16(w[c][j], pc.c64k), a, pc.two);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < KK; ++c) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          M::step4c(Q01, Q23, S, acc, acc2, w[c][j], bLl, bHl);
+          M::step4c(Q01, Q23, S, acc, acc2, w[c][j], bLh, bHh);
+        }
+      }
+    }
+    const uint32_t n0 = R - n1 - n2 - n3;
+    acc64 += (unsigned long long)(acc + acc2 - n0 * N0 - n2 * (N0 + N2));
+    __syncthreads();
+  }
+}
+
 // Per-thread sums of the complete-observations mode for one side of a pair (see group_hist).
 struct PwSide {
   unsigned long long S = 0;   // sum over the group's rows of (present rows of the other column below it)
@@ -595,15 +680,18 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
 // tied rows of x in x order; every thread takes a row and walks forward to the end of its group
 // (tend[], from K1; rows of large groups end at themselves and are skipped) -- the lanes of a warp
 // read consecutive keys.  At most kLargeTie/2 comparisons per row, one for the usual isolated tie.
-template <bool G>
+template <bool G, bool RG>
 __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, const int m,
                                                     const uint16_t* __restrict__ trow,
                                                     const uint16_t* __restrict__ tend,
-                                                    typename Mem<G>::ptr rank_tbl, uint32_t& inv, uint32_t& ties) {
+                                                    typename Mem<G>::ptr rank_tbl,
+                                                    const uint16_t* __restrict__ rank_g, uint32_t& inv,
+                                                    uint32_t& ties) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, T = blockDim.x;
   for (int t = tid; t < m; t += T)
-    M::st16(M::add(keys, t << 1), M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)trow[t] << 1))));
+    M::st16(M::add(keys, t << 1), RG ? (uint32_t)__ldg(rank_g + trow[t])
+                                     : M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)trow[t] << 1))));
   __syncthreads();
   for (int k = tid; k < m; k += T) {
     const int end = tend[k];
@@ -625,10 +713,11 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
 // not even one group's K counters fit, one group at a time in windows of ranks.  Returns (summed
 // over the threads) the joint ties inside those groups.  `pre` is a shared array of 256 words;
 // `lg` the column's (start, size) table.
-template <bool G>
+template <bool G, bool RG>
 __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                         const int hist_words, const uint16_t* __restrict__ permX,
-                                                        typename Mem<G>::ptr rank_tbl, const int K,
+                                                        typename Mem<G>::ptr rank_tbl,
+                                                        const uint16_t* __restrict__ rank_g, const int K,
                                                         const uint16_t* __restrict__ lg, const int nlg,
                                                         uint32_t* __restrict__ pre, uint32_t* __restrict__ list,
                                                         const int list_cap, uint32_t* descT, uint32_t* list_n,
@@ -662,7 +751,9 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
           uint32_t bin = 0x80000000u | (uint32_t)lane;  // idle lanes: a key of their own
           bool in = false;
           if (q < t) {
-            const uint32_t r = M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)permX[s0 + q] << 1))) - (uint32_t)k0;
+            const uint32_t row = permX[s0 + q];
+            const uint32_t r = (RG ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)))) -
+                               (uint32_t)k0;
             in = r < (uint32_t)kw;
             if (in) bin = (uint32_t)(j * kw) + r;
           }
@@ -853,9 +944,13 @@ __device__ __forceinline__ void block_sum4(unsigned long long* red, int nwarps, 
 
 // PW: complete-observations mode (kt_fast use = "pairwise.complete.obs"): besides the global
 // counts the kernel takes the rows missing in either column out of the pair, see PairComplete.
-template <int MAXT, int MINB, bool G, bool PW>
+// IP: 0, or the compile-time run count KK of the in-place variant for long vectors (one sequence
+// buffer, keys in registers across a level, y's rank table read from global memory).
+template <int MAXT, int MINB, bool G, bool PW, int IP = 0>
 __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledParams p) {
   typedef Mem<G> M;
+  constexpr bool RG = G || IP != 0;    // rank table not staged
+  constexpr int AQ = IP != 0 ? 2 : 4;  // bytes of the pass-A buffers in units of cap
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
@@ -887,8 +982,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
     }
     const uint16_t* rankY_g = p.rank + (size_t)ycol * p.nstride;
     const uint32_t* g0Yg = ((YS.flags & 1) ? p.firstbits : p.nabits) + (size_t)ycol * p.wstride;
-    // y's dense-rank table: staged into the second ping-pong buffer (shared variant) or read in place
-    const typename M::ptr rank_tbl = G ? (typename M::ptr)(size_t)rankY_g : bufB16;
+    // y's dense-rank table: staged into the second ping-pong buffer, or read in place (RG)
+    const typename M::ptr rank_tbl = bufB16;
     const int L = YS.levels;
     const uint32_t padA = (1u << L) - 1u;
     __syncthreads();
@@ -938,7 +1033,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const int f = (PW && XS.n_na > 0) ? XS.n_na : XS.first_run;
       PwSide pwy, pwx;  // y without x's missing rows / x without y's missing rows
       uint32_t ties = 0;
-      if (!G) {  // dense ranks of y go to the second ping-pong buffer until pass A starts
+      if (!RG) {  // dense ranks of y go to the second ping-pong buffer until pass A starts
         const uint4* src = reinterpret_cast<const uint4*>(rankY_g);
         for (int i = tid; i < (p.nstride >> 3); i += T) {
           const uint4 v = __ldg(src + i);
@@ -954,16 +1049,16 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const bool by_pass_b = nlg > 0 && p.tier == 2 && (long long)nlg * YS.n_groups > p.budget;
       uint32_t accB = 0;
       if (m > 0 && !by_pass_b)  // keys: 2 m <= 2 cap bytes, the still empty sequence buffer
-        small_groups_direct<G>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tend + (size_t)xcol * p.nstride,
-                               rank_tbl, accB, ties);
+        small_groups_direct<G, RG>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tend + (size_t)xcol * p.nstride,
+                                   rank_tbl, rankY_g, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
       if (f > 0) {
         if (PW && XS.n_na > 0)
-          ties += group_hist<G, true, true, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
+          ties += group_hist<G, true, true, RG>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, rankY_g, sm.mini,
                                                   sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
                                                   nwarps, p.gstart + (size_t)ycol * p.gstride, YS.n_na, pwy);
         else
-          ties += group_hist<G, true, false, false>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, nullptr, sm.mini,
+          ties += group_hist<G, true, false, RG>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, rankY_g, sm.mini,
                                                    sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
                                                    nwarps, nullptr, 0, pwy);
       }
@@ -973,6 +1068,9 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
                                          fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16, nwarps,
                                          p.gstart + (size_t)xcol * p.gstride, XS.n_na, pwx);
       {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
+        auto rk = [&](uint32_t row) -> uint32_t {
+          return RG ? (uint32_t)__ldg(rankY_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)));
+        };
         const uint4* px8 = reinterpret_cast<const uint4*>(permX);
         for (int q8 = (f >> 3) + tid; q8 < (cap >> 3); q8 += T) {
           const int q0 = q8 << 3;
@@ -982,14 +1080,13 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
             const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = M::ld16(M::add(rank_tbl, (int32_t)((pw[j] & 0xffffu) << 1))) |
-                     (M::ld16(M::add(rank_tbl, (int32_t)((pw[j] >> 16) << 1))) << 16);
+              o[j] = rk(pw[j] & 0xffffu) | (rk(pw[j] >> 16) << 16);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int qa = q0 + 2 * j, qb = qa + 1;
-              const uint32_t lo = (qa < n) ? M::ld16(M::add(rank_tbl, (int32_t)permX[qa] << 1)) : padA;
-              const uint32_t hi = (qb < n) ? M::ld16(M::add(rank_tbl, (int32_t)permX[qb] << 1)) : padA;
+              const uint32_t lo = (qa < n) ? rk(permX[qa]) : padA;
+              const uint32_t hi = (qb < n) ? rk(permX[qb]) : padA;
               o[j] = lo | (hi << 16);
             }
           }
@@ -1005,14 +1102,18 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       __syncthreads();
       if (nlg > 0 && !by_pass_b) {
         // large tie groups of x: sorted by y in place (the counters live behind the two pass-A buffers)
-        ties += large_groups_sorted<G>(bufA, M::add(bufA, 4 * cap), (p.region_bytes - 4 * cap) >> 2, permX, rank_tbl, YS.n_groups,
+        ties += large_groups_sorted<G, RG>(bufA, M::add(bufA, AQ * cap), (p.region_bytes - AQ * cap) >> 2, permX, rank_tbl, rankY_g, YS.n_groups,
                                        p.lgrp + (size_t)xcol * kLargeStride, nlg,
                                        reinterpret_cast<uint32_t*>(sm.red), sm.fmask, fmask_words(nwarps, kkc) / 3,
                                        sm.descT, sm.mini + 16, nwarps);
       }
       unsigned long long accA = 0;
-      count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
-      if (m > 0 && by_pass_b) {
+      if (IP != 0)
+        count_pass_inplace<(IP != 0 ? IP : 1)>(smem_addr(sm.region_ptr), nwarps, L, sm.descT,
+                                               reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
+      else
+        count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
+      if (IP == 0 && m > 0 && by_pass_b) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
         const int capB = (nwarps * kkB) << 5;
         const uint16_t* trow = p.trow + (size_t)xcol * p.nstride;
@@ -1423,7 +1524,7 @@ static int const_warps(int64_t n) {
 // Launch shape for vectors of length n: warps per CTA, 8-key runs per thread (odd), bytes of the
 // ping-pong region (pass A: two u16 buffers; pass B: two u32 buffers sized for the largest tied
 // list), and whether the region fits shared memory or has to live in the global scratch.
-TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n_units) {
+TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n_units, bool allow_inplace) {
   TiledShape sh;
   auto smem_with = [&](int w, int quarters) {
     const int cap = w * odd_runs(n, w) * 256;
@@ -1471,22 +1572,37 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n
   sh.warps = W;
   sh.kk = odd_runs(n, W);
   sh.region_bytes = region_of(W);
+  if (best >= 1e300 && tier <= 1 && allow_inplace && !getenv("ICIKT_FORCE_GMEM") && !getenv("ICIKT_WARPS")) {
+    // nothing fits shared memory with two sequence buffers: the in-place variant (one buffer,
+    // the keys of a level held in registers, kk fixed at compile time) takes up to 28 warps
+    constexpr int KK = 9;
+    const int w = (int)((n + 256LL * KK - 1) / (256LL * KK));
+    const int cap = 256 * KK * std::max(w, 1);
+    const int region = ((tier == 0 ? 2 : 3) * cap + 15) & ~15;
+    if (w >= 1 && w <= 28 && cap <= 65536 &&
+        tiled_smem_bytes(region, (int)wstride, fmask_words(w, KK << 3)) <= 227 * 1024) {
+      sh.inplace_kk = KK;
+      sh.warps = W = w;
+      sh.kk = KK;
+      sh.region_bytes = region;
+    }
+  }
   {  // the per-column constant kernel has its own shape: its pass-A buffers must fit a scratch slot too
     const int Wc = const_warps(n);
     sh.const_region_bytes = (2 * 2 * (Wc * odd_runs(n, Wc) * 256) + 15) & ~15;
     sh.const_gmem = tiled_smem_bytes(sh.const_region_bytes, (int)wstride, fmask_words(Wc, odd_runs(n, Wc) << 3)) > 227 * 1024 ||
                     getenv("ICIKT_FORCE_GMEM") != nullptr;
   }
-  sh.gmem = smem_of(W) > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr;
+  sh.gmem = sh.inplace_kk == 0 && (smem_of(W) > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr);
   sh.max_ctas = n_sm * std::max(1, 2048 / (32 * W));
   return sh;
 }
 
 namespace {
 
-template <int MAXT, int MINB, bool G, bool PW = false>
+template <int MAXT, int MINB, bool G, bool PW = false, int IP = 0>
 int tiled_occupancy(int threads, size_t smem) {
-  auto kern = pairs_tiled_kernel<MAXT, MINB, G, PW>;
+  auto kern = pairs_tiled_kernel<MAXT, MINB, G, PW, IP>;
   if (threads > MAXT) return 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
@@ -1500,9 +1616,9 @@ int tiled_occupancy(int threads, size_t smem) {
   return per_sm;
 }
 
-template <int MAXT, int MINB, bool G, bool PW = false>
+template <int MAXT, int MINB, bool G, bool PW = false, int IP = 0>
 int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size_t smem, cudaStream_t stream) {
-  pairs_tiled_kernel<MAXT, MINB, G, PW><<<(unsigned)grid, threads, smem, stream>>>(p);
+  pairs_tiled_kernel<MAXT, MINB, G, PW, IP><<<(unsigned)grid, threads, smem, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1511,6 +1627,12 @@ int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size
 template <bool G>
 int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, cudaStream_t stream) {
   const int threads = 32 * sh.warps;
+  if (!G && sh.inplace_kk == 9) {  // long vectors in place: 28 warps at most, ~72 registers
+    const int occ = tiled_occupancy<896, 1, false, false, 9>(threads, smem);
+    if (occ < 1) return -1;
+    long long grid = std::max<long long>(1, std::min<long long>((long long)n_sm * occ, p.n_units));
+    return launch_tiled_variant<896, 1, false, false, 9>(p, threads, grid, smem, stream);
+  }
   if (p.pw) {  // complete-observations mode: one register class
     const int occ = tiled_occupancy<1024, 1, G, true>(threads, smem);
     if (occ < 1) return -1;
