@@ -689,9 +689,23 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
                                                     uint32_t& ties) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, T = blockDim.x;
-  for (int t = tid; t < m; t += T)
-    M::st16(M::add(keys, t << 1), RG ? (uint32_t)__ldg(rank_g + trow[t])
-                                     : M::ld16(M::add(rank_tbl, (int32_t)((uint32_t)trow[t] << 1))));
+  {  // eight rows per thread and step (the list is readable up to nstride, a multiple of 64)
+    const uint4* tr8 = reinterpret_cast<const uint4*>(trow);
+    for (int t8 = tid; t8 < ((m + 7) >> 3); t8 += T) {
+      const uint4 pv = __ldg(tr8 + t8);
+      const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t r0 = pw[j] & 0xffffu, r1 = pw[j] >> 16;
+        const bool v0 = (t8 << 3) + 2 * j < m, v1 = (t8 << 3) + 2 * j + 1 < m;  // rows behind m are stale
+        const uint32_t k0 = !v0 ? 0u : RG ? (uint32_t)__ldg(rank_g + r0) : M::ld16(M::add(rank_tbl, (int32_t)(r0 << 1)));
+        const uint32_t k1 = !v1 ? 0u : RG ? (uint32_t)__ldg(rank_g + r1) : M::ld16(M::add(rank_tbl, (int32_t)(r1 << 1)));
+        o[j] = k0 | (k1 << 16);
+      }
+      M::st128(M::add(keys, t8 << 4), o[0], o[1], o[2], o[3]);
+    }
+  }
   __syncthreads();
   for (int k = tid; k < m; k += T) {
     const int end = tend[k];
