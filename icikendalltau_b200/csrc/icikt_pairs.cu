@@ -711,6 +711,7 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
     const int end = tend[k];
     if (end <= k + 1) continue;
     const uint32_t mine = M::ld16(M::add(keys, k << 1));
+#pragma unroll 4
     for (int j = k + 1; j < end; ++j) {
       const uint32_t other = M::ld16(M::add(keys, j << 1));
       inv += (other < mine);
