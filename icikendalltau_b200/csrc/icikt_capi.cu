@@ -117,7 +117,6 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->tab.tend);
   cudaFree(p->tab.nabits);
   cudaFree(p->tab.firstbits);
-  cudaFree(p->tab.grpstart);
   cudaFree(p->tab.gstart);
   cudaFree(p->tab.lgrp);
   cudaFree(p->tab.stats);
@@ -344,7 +343,6 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.tend, ne));
   PCK(dmalloc(&t.nabits, nw));
   PCK(dmalloc(&t.firstbits, nw));
-  PCK(dmalloc(&t.grpstart, nw));
   t.gstride = t.nstride + 64;
   PCK(dmalloc(&t.gstart, (size_t)t.gstride * C));
   PCK(dmalloc(&t.lgrp, (size_t)kLargeStride * C));
@@ -353,7 +351,6 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   // padding words of the bit arrays (beyond n32/32) are never written by the kernels
   PCK(cudaMemsetAsync(t.nabits, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.firstbits, 0, sizeof(uint32_t) * nw, p->stream));
-  PCK(cudaMemsetAsync(t.grpstart, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.max_tied, 0, 4 * sizeof(int32_t), p->stream));
   p->shape = tiled_shape(n, 0, t.wstride, p->n_sm);
   PCK(dmalloc(&p->wk.keys_in, ne));

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
     column_rank_kernel(const unsigned long long* __restrict__ skeys, int n, int nstride, int wstride,
                        uint16_t* __restrict__ perm, uint16_t* __restrict__ rank,
                        uint16_t* __restrict__ trow, uint16_t* __restrict__ trun, uint16_t* __restrict__ tend,
-                       uint32_t* __restrict__ firstbits, uint32_t* __restrict__ grpstart,
+                       uint32_t* __restrict__ firstbits,
                        uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
                        uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
                        int32_t* __restrict__ max_tied) {
@@ -348,8 +348,6 @@ __global__ void __launch_bounds__(RANK_THREADS)
       rk[pm[t]] = (uint16_t)r;
       if (flag) gpos[r] = (uint32_t)t;
     }
-    const uint32_t m = __ballot_sync(FULL, flag != 0);
-    if ((tid & 31) == 0 && t < n32) grpstart[(size_t)col * wstride + (t >> 5)] = m;
     carry += total;
   }
   const int K = carry;
@@ -501,7 +499,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
       return -1;
     launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
-                                                       tab.trow, tab.trun, tab.tend, tab.firstbits, tab.grpstart,
+                                                       tab.trow, tab.trun, tab.tend, tab.firstbits,
                                                        wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;

@@ -23,7 +23,6 @@ struct ColumnTables {
                                   //              (= the row's own index for rows of large groups)
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
-  uint32_t* grpstart = nullptr;   // [C][wstride] bit t: sorted position t starts a tie group (long-column path only)
   uint16_t* lgrp = nullptr;       // [C][kLargeStride] (start position, size) of every large tie group
   uint16_t* gstart = nullptr;     // [C][gstride] sorted position where the group of dense rank r starts; [K] = n
   int64_t gstride = 0;            // nstride + 64
