@@ -65,7 +65,7 @@ __device__ __forceinline__ int block_scan_excl(int v, int* warp_sums, int& total
   }
   if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
-  int ws = (lane < (RANK_THREADS / 32)) ? warp_sums[lane] : 0;
+  int ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
   int wincl = ws;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -85,7 +85,7 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* buf) {
   if (lane == 0) buf[warp] = v;
   __syncthreads();
   long long t = 0;
-  for (int w = 0; w < RANK_THREADS / 32; ++w) t += buf[w];
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += buf[w];
   __syncthreads();
   return t;
 }
@@ -98,11 +98,10 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* buf) {
 // Replaces six launches (~150 us for 100 columns of 5 000 rows, two thirds of it in
 // cub::DeviceSegmentedSort) where the per-column work is a visible share of the whole job.
 // Each phase is one pass over the registers plus one block scan.
-constexpr int SORT_THREADS = RANK_THREADS;
 struct KeyLess {
   __device__ __forceinline__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
 };
-template <int ITEMS>
+template <int SORT_THREADS, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
     column_fused_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
                         const double* __restrict__ global_na, int n_global_na, int na_inf,
@@ -282,14 +281,14 @@ __global__ void __launch_bounds__(SORT_THREADS)
   }
 }
 
-template <int ITEMS>
+template <int SORT_THREADS, int ITEMS>
 int launch_column_fused(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na, int na_inf,
                         ColumnTables& tab, cudaStream_t stream) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * (CAP / 32);
   const size_t smem = std::max(sizeof(typename Sort::TempStorage), post);
-  auto kern = column_fused_kernel<ITEMS>;
+  auto kern = column_fused_kernel<SORT_THREADS, ITEMS>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
@@ -468,17 +467,20 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   int launches = 0;
   // the bit arrays are written in full (words below n32/32) by the kernels below; the padding
   // words up to wstride were zeroed once when the plan was created
-  const int items = (n + SORT_THREADS - 1) / SORT_THREADS;
+  // short columns: 512 threads (more CTAs per SM when there are many columns), else 1024
   if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
-  if (items <= 16 && !getenv("ICIKT_NO_FUSED_COLUMNS")) {
+  if (n <= 8192 && !getenv("ICIKT_NO_FUSED_COLUMNS")) {
     int l;
-    if (items <= 2) l = launch_column_fused<2>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
-    else if (items <= 4) l = launch_column_fused<4>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
-    else if (items <= 6) l = launch_column_fused<6>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
-    else if (items <= 8) l = launch_column_fused<8>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
-    else if (items <= 10) l = launch_column_fused<10>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
-    else if (items <= 12) l = launch_column_fused<12>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
-    else l = launch_column_fused<16>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream);
+#define ICIKT_FUSED(T, I) l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream)
+    if (n <= 512) ICIKT_FUSED(512, 1);
+    else if (n <= 1024) ICIKT_FUSED(512, 2);
+    else if (n <= 2048) ICIKT_FUSED(512, 4);
+    else if (n <= 3072) ICIKT_FUSED(512, 6);
+    else if (n <= 4096) ICIKT_FUSED(1024, 4);
+    else if (n <= 5120) ICIKT_FUSED(1024, 5);
+    else if (n <= 6144) ICIKT_FUSED(1024, 6);
+    else ICIKT_FUSED(1024, 8);
+#undef ICIKT_FUSED
     if (l < 0) return -1;
     launches += l;
   } else {
