@@ -1,7 +1,4 @@
 set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$? | tee -a gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-python tools/gpu_diag.py > gpurun_out/diag.log 2>&1; tail -1 gpurun_out/diag.log
-python bench.py --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/q_config2.json
-python bench.py --workload config1 --steps 10 --warmup 3 --quick 2>/dev/null | tail -1 > gpurun_out/q_config1.json
-python bench.py --workload config5 --steps 3 --warmup 3 --quick 2>/dev/null | tail -1 > gpurun_out/q_config5.json
+for seed in 1 2 3 4 5 6 7 8; do ICIKT_TEST_SEED=$seed python -m pytest tests/test_gpu_parity.py -q -k "random_small or repeated_runs or uneven" 2>&1 | tail -1; done
