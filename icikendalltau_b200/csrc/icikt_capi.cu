@@ -629,6 +629,7 @@ void icikt_plan_destroy(icikt_plan* p) { free_plan(p); }
 
 // One cached plan for the one-shot entry points (all-pairs shape only).
 static icikt_plan* g_cached = nullptr;
+static icikt_plan* g_cached_multi[64] = {};  // one slot per worker of icikt_all_pairs_multi
 static std::mutex g_cache_mu;
 
 static bool cache_matches(const icikt_plan* p, int64_t n, int64_t C, const icikt_opts& o) {
@@ -701,6 +702,8 @@ int icikt_pair_from_index(int64_t C, int32_t include_diag, int64_t index, int32_
 void icikt_release_workspace(void) {
   std::lock_guard<std::mutex> lock(g_cache_mu);
   if (g_cached) { icikt_plan_destroy(g_cached); g_cached = nullptr; }
+  for (icikt_plan*& s : g_cached_multi)
+    if (s) { icikt_plan_destroy(s); s = nullptr; }
 }
 
 int icikt_measure_smem_bandwidth(int32_t device, double* g32, double* g128) {
@@ -733,6 +736,7 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
   if (opts) base = *opts; else icikt_default_opts(&base);
   base.want_counts = counts ? 1 : 0;
   const int64_t ptot = tri_pairs(C) + (base.include_diag ? C : 0);
+  std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached plans are not re-entrant
   struct Work {
     int rc = ICIKT_OK;
     std::string err;
@@ -750,8 +754,21 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
       o.pair_hi = ptot * (k + 1) / n_devices;
       const int64_t lo = o.pair_lo, cnt = o.pair_hi - o.pair_lo;
       if (cnt <= 0) return;
+      // one cached plan per slot, like the one-shot entry points: repeated calls of the same
+      // shape do not pay the device allocations again
+      icikt_plan*& slot = g_cached_multi[k];
       icikt_plan* p = nullptr;
-      w.rc = icikt_plan_create(&p, n, C, nullptr, nullptr, 0, &o);
+      if (cache_matches(slot, n, C, o) && (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || slot->d_pw)) {
+        p = slot;
+        p->opts.perspective = o.perspective;
+        p->opts.alternative = o.alternative;
+        p->opts.continuity = o.continuity;
+        p->opts.na_inf = o.na_inf;
+      } else {
+        if (slot) { icikt_plan_destroy(slot); slot = nullptr; }
+        w.rc = icikt_plan_create(&p, n, C, nullptr, nullptr, 0, &o);
+        if (w.rc == ICIKT_OK) slot = p;
+      }
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_upload(p, data, ld);
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns(p, global_na, n_global_na);
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_pairs(p);
@@ -760,8 +777,10 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
                                    completeness ? completeness + lo : nullptr, status ? status + lo : nullptr,
                                    counts ? counts + lo * ICIKT_NCOUNTS : nullptr, &w.mx);
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_timings(p, &w.tm);
-      if (w.rc != ICIKT_OK) w.err = g_err;  // thread-local message of this worker
-      if (p) icikt_plan_destroy(p);
+      if (w.rc != ICIKT_OK) {
+        w.err = g_err;  // thread-local message of this worker
+        if (slot) { icikt_plan_destroy(slot); slot = nullptr; }
+      }
     });
   }
   for (auto& t : threads) t.join();
