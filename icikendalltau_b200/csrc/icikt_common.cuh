@@ -41,8 +41,8 @@ struct ColStats {
 // writes them into the sequence already sorted by the other column (rank histogram, like the
 // first group); the rows of the smaller groups are compared directly inside their group.  In the
 // tied-row list the rows of large groups carry kLargeFlag in their group index.
-constexpr int kLargeTie = 64;
-constexpr int kLargeStride = 2048;  // u16 per column in the large-group table: (start, size) x 1024
+constexpr int kLargeTie = 128;
+constexpr int kLargeStride = 1024;  // u16 per column in the large-group table: (start, size) x 512
 constexpr unsigned kLargeFlag = 0x8000u;
 
 struct PairOut {
