@@ -626,6 +626,7 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
     // 3. write the runs / sum up
     for (int w = w0; w < w1; ++w) {
       const uint32_t cw = M::ld32(M::add(hist, w << 2));
+      if (!PW && cw == 0u) continue;  // empty counters only matter to the complete-observations sums
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
@@ -801,6 +802,15 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
       int j = b / kw, r = b - j * kw;
       for (int w = w0; w < w1; ++w) {
         const uint32_t cw = M::ld32(M::add(hist, w << 2));
+        if (cw == 0u) {  // most counters are empty: a group touches at most as many ranks as it has rows
+          b += 2;
+          r += 2;
+          while (r >= kw) {
+            r -= kw;
+            ++j;
+          }
+          continue;
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
