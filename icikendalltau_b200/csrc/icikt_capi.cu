@@ -79,6 +79,7 @@ struct icikt_plan {
   size_t scratch_bytes = 0;
 
   std::vector<PairUnit> units;
+  int max_unit_pairs = 1;  // longest unit
   PairUnit* d_units = nullptr;
   int32_t* d_pj = nullptr;
   PairRaw* d_raw = nullptr;
@@ -315,6 +316,7 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   }
   rc = build_units(p, pi, pj, P);
   if (rc != ICIKT_OK) { free_plan(p); return rc; }
+  for (const PairUnit& u : p->units) p->max_unit_pairs = std::max(p->max_unit_pairs, (int)u.count);
 
 #define PCK(call)                                                \
   do {                                                           \
@@ -518,6 +520,7 @@ int icikt_plan_pairs(icikt_plan* p) {
     el.tab = &p->tab;
     el.units = p->d_units;
     el.n_units = pl.n_units;
+    el.max_unit_pairs = p->max_unit_pairs;
     el.pj_list = p->d_pj;
     el.raw = p->d_raw;
     el.pw = pl.pw;

@@ -107,6 +107,7 @@ struct EpilogueLaunch {
   const ColumnTables* tab;
   const PairUnit* units;
   int64_t n_units;
+  int max_unit_pairs = 32;  // longest unit (pairs): sets the threads per unit
   const int32_t* pj_list;
   const PairRaw* raw;
   const PairComplete* pw = nullptr;

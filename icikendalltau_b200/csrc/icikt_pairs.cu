@@ -1353,16 +1353,18 @@ struct EpiParams {
   long long n_units;
   long long n;
   int perspective, alternative, continuity;
+  int lane_shift;  // 2^lane_shift threads per unit (the smallest power of two that covers the longest unit)
 };
 
 __global__ void __launch_bounds__(128) epilogue_kernel(const EpiParams p) {
-  // 4 units per block, one warp per unit (a unit holds at most 32 pairs)
-  const long long u = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  // 2^lane_shift consecutive threads per unit, one pair per thread and step
+  const long long gt = (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long u = gt >> p.lane_shift;
+  const int lane = threadIdx.x & 31, sub = (int)(gt & ((1 << p.lane_shift) - 1));
   double mx = -1.0;
   if (u < p.n_units) {
     const PairUnit unit = p.units[u];
-    for (int k = lane; k < unit.count; k += 32) {
+    for (int k = sub; k < unit.count; k += 1 << p.lane_shift) {
       const long long slot = unit.slot0 + k;
       const int xcol = unit.j_explicit ? p.pj_list[slot] : unit.j0 + k;
       PairRaw r = p.raw[slot];
@@ -1767,7 +1769,9 @@ int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream) {
   p.alternative = el.alternative;
   p.continuity = el.continuity;
   if (el.n_units <= 0) return 0;
-  const long long grid = (el.n_units + 3) / 4;
+  p.lane_shift = 0;
+  while ((1 << p.lane_shift) < el.max_unit_pairs && p.lane_shift < 5) ++p.lane_shift;
+  const long long grid = ((el.n_units << p.lane_shift) + 127) / 128;
   epilogue_kernel<<<(unsigned)grid, 128, 0, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
