@@ -68,6 +68,35 @@ struct PipeConst {
   uint32_t one, two, c64k;
 };
 
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (sm_90+) ---------------------
+// Used for the one contiguous bulk transfer of the pair kernel: y's dense-rank table into the
+// second sequence buffer.  One thread issues it; the copy engine moves the bytes while the CTA
+// does the bit-mask counting, then everybody waits on the barrier's phase.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  // earlier generic-proxy accesses to the destination are ordered before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 template <bool G>
 struct Mem;
 template <>
@@ -992,6 +1021,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   const int cap = (nwarps * kkc) << 5;
   Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kkc));
   const typename M::ptr bufA = region_base<G>(sm, p), bufB16 = M::add(bufA, 2 * cap);
+  const uint32_t mbar = smem_addr(sm.unit_slot + 1);  // 8 bytes behind the unit slot
+  uint32_t tma_phase = 0;
+  if (!RG && tid == 0) mbar_init(mbar, 1);
+  // (the first __syncthreads of the unit loop publishes the initialised barrier)
 
   for (;;) {
     if (tid == 0) *sm.unit_slot = (long long)atomicAdd(p.unit_counter, 1ull);
@@ -1021,6 +1054,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const uint32_t* fbXg = p.firstbits + (size_t)xcol * p.wstride;
       const uint32_t* nbXg = p.nabits + (size_t)xcol * p.wstride;
       const bool absorbed = ((XS.flags | YS.flags) & 1) != 0;
+      // y's dense ranks go to the second sequence buffer (free since the barrier that ended the
+      // previous pair) as one TMA bulk copy, in flight during the mask counting below
+      if (!RG && tid == 0)
+        bulk_g2s(smem_addr(sm.region_ptr) + 2u * (uint32_t)cap, rankY_g, (uint32_t)p.nstride * 2u, mbar);
       // joint-missing rows (b) and joint lowest group (g00, differs from b only if a column's
       // missing rows tie with its minimum)
       uint32_t bpart = 0, g00part = 0;
@@ -1028,6 +1065,10 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         const uint32_t nb = nbXg[i];
         bpart += __popc(nb & sm.nabY[i]);
         if (absorbed) g00part += __popc(((XS.flags & 1) ? fbXg[i] : nb) & g0Yg[i]);
+      }
+      if (!RG) {  // the rank table has landed (also on the early exit below: the barrier is reused)
+        mbar_wait(mbar, tma_phase);
+        tma_phase ^= 1u;
       }
       if (YS.n_groups < 2 || XS.n_groups < 2) {
         // a constant or all-missing column: K3 reports NA; only the joint-missing count is kept
@@ -1058,14 +1099,6 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const int f = (PW && XS.n_na > 0) ? XS.n_na : XS.first_run;
       PwSide pwy, pwx;  // y without x's missing rows / x without y's missing rows
       uint32_t ties = 0;
-      if (!RG) {  // dense ranks of y go to the second ping-pong buffer until pass A starts
-        const uint4* src = reinterpret_cast<const uint4*>(rankY_g);
-        for (int i = tid; i < (p.nstride >> 3); i += T) {
-          const uint4 v = __ldg(src + i);
-          M::st128(M::add(bufB16, i << 4), v.x, v.y, v.z, v.w);
-        }
-        __syncthreads();
-      }
       // Tied x groups other than the first: small ones are compared directly (before anything is
       // written into the sequence buffer), large ones are sorted by y in place after the gather.
       // If the large groups' rank counters would cost more than pass B (very many distinct y
