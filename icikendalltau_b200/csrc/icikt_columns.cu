@@ -194,10 +194,16 @@ __global__ void __launch_bounds__(SORT_THREADS)
   __syncthreads();
   for (int g = tid; g <= K; g += SORT_THREADS) gstart[(size_t)col * gstride + g] = gpos[g];
   // tie sums over group sizes (count_rank_tie, :103-118), exact int64
-  long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
+  long long s2 = 0, s3 = 0, s5 = 0, ntied = 0, lsq = 0;
+  for (int g = tid + 1; g < K; g += SORT_THREADS) {
+    const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
+    if (t >= kLargeTie) lsq += t * t;
+  }
+  lsq = block_sum_ll(lsq, llbuf);
+  const int large_from = lsq > (long long)kDirectBudget * n ? kLargeTie : 0x7fffffff;
   for (int g = tid; g < K; g += SORT_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
-    if (g > 0 && t >= kLargeTie) {  // large tie group: also listed by (start position, size)
+    if (g > 0 && t >= large_from) {  // large tie group: also listed by (start position, size)
       const int k = atomicAdd(&n_large, 1);
       lgrp[(size_t)col * kLargeStride + 2 * k] = gpos[g];
       lgrp[(size_t)col * kLargeStride + 2 * k + 1] = (uint16_t)t;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const int sz = (int)gpos[r + 1] - (int)gpos[r];
         const bool tied = sz > 1;
         tmask |= (uint32_t)tied << i;
-        lmask |= (uint32_t)(sz >= kLargeTie) << i;
+        lmask |= (uint32_t)(sz >= large_from) << i;
         after[i] = (int)gpos[r + 1] - t;
         gmask |= (uint32_t)(tied && (int)gpos[r] == t) << i;
       }
@@ -355,10 +361,16 @@ __global__ void __launch_bounds__(RANK_THREADS)
   for (int g = tid; g <= K; g += RANK_THREADS) gstart_tab[(size_t)col * gstride + g] = (uint16_t)gpos[g];  // n <= 65535
 
   // tie sums over group sizes (count_rank_tie, src/kendallc.cpp:103-118), exact int64
-  long long s2 = 0, s3 = 0, s5 = 0, ntied = 0;
+  long long s2 = 0, s3 = 0, s5 = 0, ntied = 0, lsq = 0;
+  for (int g = tid + 1; g < K; g += RANK_THREADS) {
+    const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
+    if (t >= kLargeTie) lsq += t * t;
+  }
+  lsq = block_sum_ll(lsq, llbuf);
+  const long long large_from = lsq > (long long)kDirectBudget * n ? kLargeTie : 0x7fffffff;
   for (int g = tid; g < K; g += RANK_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
-    if (g > 0 && t >= kLargeTie) {  // large tie group: also listed by (start position, size)
+    if (g > 0 && t >= large_from) {  // large tie group: also listed by (start position, size)
       const int k = atomicAdd(&n_large, 1);
       lgrp[(size_t)col * kLargeStride + 2 * k] = (uint16_t)gpos[g];
       lgrp[(size_t)col * kLargeStride + 2 * k + 1] = (uint16_t)t;
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
       r = rk[row];
       const uint32_t sz = gpos[r + 1] - gpos[r];
       flag = sz > 1;
-      large = sz >= (uint32_t)kLargeTie;
+      large = (long long)sz >= large_from;
       after = (int)gpos[r + 1] - t;
       gstart = flag && (gpos[r] == (uint32_t)t);
     }

@@ -42,6 +42,10 @@ struct ColStats {
 // first group); the rows of the smaller groups are compared directly inside their group.  In the
 // tied-row list the rows of large groups carry kLargeFlag in their group index.
 constexpr int kLargeTie = 128;
+// ... unless all such groups of a column are cheap enough to compare directly as well: sum of
+// size^2 over them at most kDirectBudget * n (then the column has no "large" groups at all and
+// can stay in the light launch tier)
+constexpr int kDirectBudget = 24;
 constexpr int kLargeStride = 1024;  // u16 per column in the large-group table: (start, size) x 512
 constexpr unsigned kLargeFlag = 0x8000u;
 

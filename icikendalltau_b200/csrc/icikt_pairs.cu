@@ -709,7 +709,9 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
 // joint ties inside each group by direct comparison.  `keys` receives the y ranks (u16) of all m
 // tied rows of x in x order; every thread takes a row and walks forward to the end of its group
 // (tend[], from K1; rows of large groups end at themselves and are skipped) -- the lanes of a warp
-// read consecutive keys.  At most kLargeTie/2 comparisons per row, one for the usual isolated tie.
+// read consecutive keys.  One comparison for the usual isolated tie; K1 bounds the total (groups of
+// kLargeTie rows or more are only left to this routine while the sum of their size^2 stays below
+// kDirectBudget * n).
 template <bool G, bool RG>
 __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, const int m,
                                                     const uint16_t* __restrict__ trow,
