@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <condition_variable>
 #include <thread>
 #include <vector>
 
@@ -252,6 +253,43 @@ int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes) {
   }
   return ICIKT_OK;
 }
+
+// host -> device copy of columns [c_lo, c_hi) into the plan's own matrix buffer
+int upload_columns(icikt_plan* p, const double* data, int64_t ld, int64_t c_lo, int64_t c_hi) {
+  CK(cudaSetDevice(p->device));
+  if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  if (c_hi > c_lo)
+    CK(cudaMemcpy2DAsync(p->d_data_own + (size_t)c_lo * p->n, sizeof(double) * p->n, data + (size_t)c_lo * ld,
+                         sizeof(double) * ld, sizeof(double) * p->n, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice,
+                         p->stream));
+  p->d_data = p->d_data_own;
+  p->ld = p->n;
+  p->columns_done = false;
+  return ICIKT_OK;
+}
+
+// reusable barrier for the worker threads of icikt_all_pairs_multi
+class HostBarrier {
+ public:
+  explicit HostBarrier(int n) : n_(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    const int gen = gen_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++gen_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lk, [&] { return gen != gen_; });
+    }
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int n_, count_ = 0, gen_ = 0;
+};
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
@@ -740,6 +778,21 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
   base.want_counts = counts ? 1 : 0;
   const int64_t ptot = tri_pairs(C) + (base.include_diag ? C : 0);
   std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached plans are not re-entrant
+  // Input distribution: if every pair of devices can reach each other directly (NVLink /
+  // NVSwitch), each device uploads only its slice of the columns over its own PCIe link and pulls
+  // the other slices from its peers (an all-gather of the matrix by peer copies); otherwise every
+  // device uploads the whole matrix.
+  bool gather = n_devices >= 2 && C >= n_devices && ptot >= n_devices && !std::getenv("ICIKT_NO_PEER_GATHER");
+  for (int a = 0; gather && a < n_devices; ++a)
+    for (int b = 0; gather && b < n_devices; ++b) {
+      const int da = devices ? devices[a] : a, db = devices ? devices[b] : b;
+      if (a == b) continue;
+      int ok = 0;
+      if (da == db || cudaDeviceCanAccessPeer(&ok, da, db) != cudaSuccess || !ok) gather = false;
+    }
+  cudaGetLastError();
+  HostBarrier barrier(n_devices);
+  std::vector<double*> dev_matrix((size_t)n_devices, nullptr);
   struct Work {
     int rc = ICIKT_OK;
     std::string err;
@@ -772,7 +825,35 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
         w.rc = icikt_plan_create(&p, n, C, nullptr, nullptr, 0, &o);
         if (w.rc == ICIKT_OK) slot = p;
       }
-      if (w.rc == ICIKT_OK) w.rc = icikt_plan_upload(p, data, ld);
+      if (!gather) {
+        if (w.rc == ICIKT_OK) w.rc = icikt_plan_upload(p, data, ld);
+      } else {
+        // every worker passes both barriers whatever happened to it, so nobody is left waiting
+        const auto col_lo = [&](int j) { return C * j / n_devices; };
+        if (w.rc == ICIKT_OK) w.rc = upload_columns(p, data, ld, col_lo(k), col_lo(k + 1));
+        if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "slice upload");
+        dev_matrix[(size_t)k] = (w.rc == ICIKT_OK) ? p->d_data_own : nullptr;
+        barrier.wait();  // all slices are on their devices
+        bool all_ok = true;
+        for (int j = 0; j < n_devices; ++j) all_ok = all_ok && dev_matrix[(size_t)j] != nullptr;
+        if (w.rc == ICIKT_OK && !all_ok) w.rc = fail(ICIKT_ERR_CUDA, "a peer device failed to upload its slice");
+        if (w.rc == ICIKT_OK) {
+          for (int j = 0; j < n_devices && w.rc == ICIKT_OK; ++j) {
+            if (j == k) continue;
+            const int dj = devices ? devices[j] : j;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { w.rc = cuda_fail(e, "cudaDeviceEnablePeerAccess"); break; }
+            cudaGetLastError();
+            const size_t off = (size_t)col_lo(j) * (size_t)n, cnt_el = (size_t)(col_lo(j + 1) - col_lo(j)) * (size_t)n;
+            if (cudaMemcpyPeerAsync(p->d_data_own + off, o.device, dev_matrix[(size_t)j] + off, dj, sizeof(double) * cnt_el,
+                                    p->stream) != cudaSuccess)
+              w.rc = cuda_fail(cudaGetLastError(), "cudaMemcpyPeerAsync");
+          }
+          if (w.rc == ICIKT_OK && cudaEventRecord(p->ev[1], p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "event");
+          if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "peer gather");
+        }
+        barrier.wait();  // nobody's matrix is touched (or freed) before every pull has finished
+      }
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns(p, global_na, n_global_na);
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_pairs(p);
       if (w.rc == ICIKT_OK)
