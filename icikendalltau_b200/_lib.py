@@ -28,8 +28,10 @@ EXPORTS = [
     "icikt_plan_columns", "icikt_plan_pairs", "icikt_plan_sync", "icikt_plan_download",
     "icikt_plan_column_info", "icikt_plan_stream", "icikt_plan_timings", "icikt_plan_destroy",
     "icikt_pnorm_device", "icikt_release_workspace", "icikt_measure_smem_bandwidth",
-    "icikt_pair_from_index",
+    "icikt_pair_from_index", "icikt_all_pairs_multi", "icikt_matrices", "icikt_plan_download_matrices",
+    "icikt_pairwise_completeness",
 ]
+NSTATUS = 10
 
 
 class IciktError(RuntimeError):
@@ -106,6 +108,17 @@ def load():
     L.icikt_plan_sync.restype = ctypes.c_int
     L.icikt_plan_download.argtypes = [vp, _dp, _dp, _dp, _dp, _ip, _lp, _dp]
     L.icikt_plan_download.restype = ctypes.c_int
+    L.icikt_plan_download_matrices.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, _ip, _dp, _dp, _dp, _dp, _dp,
+                                               _lp, _dp]
+    L.icikt_plan_download_matrices.restype = ctypes.c_int
+    L.icikt_matrices.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp, ctypes.c_int32,
+                                 _ip, _ip, ctypes.c_int64, ctypes.POINTER(Opts), ctypes.c_int32, ctypes.c_int32,
+                                 _ip, _dp, _dp, _dp, _dp, _dp, _lp, _dp, ctypes.POINTER(Timings)]
+    L.icikt_matrices.restype = ctypes.c_int
+    L.icikt_pairwise_completeness.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
+                                              ctypes.c_int32, ctypes.c_int32, _ip, _ip, ctypes.c_int64, _ip,
+                                              _dp, _dp]
+    L.icikt_pairwise_completeness.restype = ctypes.c_int
     L.icikt_plan_column_info.argtypes = [vp, _ip]
     L.icikt_plan_column_info.restype = ctypes.c_int
     L.icikt_plan_stream.argtypes = [vp]
@@ -204,6 +217,62 @@ def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, devices=N
                max_taumax=mx.value, timings=t.as_dict())
     if want_counts:
         out["counts"] = counts
+    return out
+
+
+MATRIX_NAMES = ("cor", "raw", "pvalue", "taumax", "completeness")
+
+
+def run_matrices(data, global_na=(), scale_max=True, diag_good=True, n_good=None, pi=None, pj=None,
+                 want=MATRIX_NAMES, **opt_kw):
+    """icikt_matrices: the pair results as symmetric C x C matrices filled on the device
+    (scale_and_reshape, R/kendalltau.R:357-421).  Returns the requested matrices plus
+    status_counts (pairs per status class), max_taumax and timings."""
+    L = load()
+    data = np.asfortranarray(data, dtype=np.float64)
+    if data.ndim != 2:
+        raise ValueError("data must be a 2-D array (features x samples)")
+    n, C = data.shape
+    o = make_opts(**opt_kw)
+    mats = {k: (np.empty((C, C), dtype=np.float64, order="F") if k in want else None) for k in MATRIX_NAMES}
+    hist = np.zeros(NSTATUS, dtype=np.int64)
+    mx = ctypes.c_double(float("nan"))
+    t = Timings()
+    g, gp, ng = _global_na_array(global_na)
+    if pi is not None:
+        pi = np.ascontiguousarray(pi, dtype=np.int32)
+        pj = np.ascontiguousarray(pj, dtype=np.int32)
+    ngood = None if n_good is None else np.ascontiguousarray(n_good, dtype=np.int32)
+    check(L.icikt_matrices(_ptr(data, _dp), n, C, n, gp, ng, _ptr(pi, _ip), _ptr(pj, _ip),
+                           0 if pi is None else int(pi.size), ctypes.byref(o), int(bool(scale_max)),
+                           int(bool(diag_good)), _ptr(ngood, _ip), *(_ptr(mats[k], _dp) for k in MATRIX_NAMES),
+                           _ptr(hist, _lp), ctypes.byref(mx), ctypes.byref(t)))
+    out = {k: v for k, v in mats.items() if v is not None}
+    out.update(status_counts=hist, max_taumax=mx.value, timings=t.as_dict())
+    return out
+
+
+def pairwise_completeness(data, global_na=(), pi=None, pj=None, want_matrix=False, device=0):
+    """icikt_pairwise_completeness: rows missing in either column and 1 - missing/n per pair
+    (all pairs in combn order followed by the diagonal when pi is None)."""
+    L = load()
+    data = np.asfortranarray(data, dtype=np.float64)
+    n, C = data.shape
+    if pi is not None:
+        pi = np.ascontiguousarray(pi, dtype=np.int32)
+        pj = np.ascontiguousarray(pj, dtype=np.int32)
+        P = int(pi.size)
+    else:
+        P = C * (C - 1) // 2 + C
+    missing = np.empty(P, dtype=np.int32)
+    comp = np.empty(P, dtype=np.float64)
+    mat = np.empty((C, C), dtype=np.float64, order="F") if want_matrix else None
+    g, gp, ng = _global_na_array(global_na)
+    check(L.icikt_pairwise_completeness(_ptr(data, _dp), n, C, n, gp, ng, int(device), _ptr(pi, _ip), _ptr(pj, _ip),
+                                        P, _ptr(missing, _ip), _ptr(comp, _dp), _ptr(mat, _dp)))
+    out = dict(missing=missing, completeness=comp)
+    if want_matrix:
+        out["matrix"] = mat
     return out
 
 

@@ -53,6 +53,13 @@ def _warn_status(status):
             warnings.warn(text if cnt == 1 else f"{text} ({cnt} pairs)", RuntimeWarning, stacklevel=3)
 
 
+def _warn_status_counts(counts):
+    for code, text in _STATUS_WARNING.items():
+        cnt = int(counts[code])
+        if cnt:
+            warnings.warn(text if cnt == 1 else f"{text} ({cnt} pairs)", RuntimeWarning, stacklevel=3)
+
+
 def _arg_name(default):
     return default
 
@@ -220,6 +227,21 @@ def ici_kendalltau(data_matrix, global_na=(np.nan, np.inf, 0), perspective="glob
 
     log.info("Running correlations ...")
     t1 = time.perf_counter()
+    if return_matrix and n_gpus <= 1:
+        # scale_and_reshape on the device: the five C x C matrices come back filled (:357-421)
+        n_good = (~exclude_loc).sum(axis=0)
+        if all_pairs:
+            r = _lib.run_matrices(data, global_na, scale_max, diag_good, n_good, **kw)
+        else:
+            r = _lib.run_matrices(data, global_na, scale_max, diag_good, n_good, pi=pi, pj=pj, **kw)
+        run_time = time.perf_counter() - t1
+        _warn_status_counts(r["status_counts"])
+        log.info("Generating the output matrix ...")
+        out = {k: r[k] for k in _lib.MATRIX_NAMES}
+        out["keep"] = (~exclude_loc).T
+        out["run_time"] = run_time
+        out["names"] = names
+        return out
     if all_pairs and n_gpus > 1:  # one call, the pair order sliced over the GPUs inside the library
         r = _lib.run_pairs(data, global_na, include_diag=not diag_good, devices=range(n_gpus), **kw)
     elif all_pairs:
@@ -356,19 +378,14 @@ def pairwise_completeness(data_matrix, global_na=(np.nan, np.inf, 0), include_on
     n, C = data.shape
     global_na = [float(v) for v in global_na]
     pi, pj, all_pairs = setup_comparisons(names, include_only, diag_good=False)
-    # completeness needs no correlation: a constant helper column keeps every column
-    # non-degenerate so that status never hides the completeness value
-    kw = dict(perspective="global", device=device, want_counts=True)
+    # missing-row bit masks and popc(x | y) on the device; no pair kernel runs
     if all_pairs:
-        r = _lib.run_pairs(data, global_na, include_diag=True, **kw)
+        r = _lib.pairwise_completeness(data, global_na, want_matrix=return_matrix, device=device)
+        if return_matrix:
+            return r["matrix"]
     else:
-        r = _lib.run_pairs(data, global_na, pi=pi, pj=pj, **kw)
-    # count-based so that degenerate pairs (constant columns) still report completeness
-    excl = setup_missing_matrix(data, global_na) | np.isnan(data)
-    a = excl.sum(axis=0)
-    b = r["counts"][:, _lib.NCOUNTS - 1]
-    missing = a[pi] + a[pj] - b
-    comp = 1 - missing / n
+        r = _lib.pairwise_completeness(data, global_na, pi=pi, pj=pj, device=device)
+    missing, comp = r["missing"].astype(np.float64), r["completeness"]
     if not return_matrix:
         nm = np.asarray(names, dtype=object)
         return dict(s1=nm[pi], s2=nm[pj], missingness=missing, completeness=comp)

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libicikt_b200.so")
-SOURCES = ["icikt_capi.cu", "icikt_columns.cu", "icikt_pairs.cu"]
+SOURCES = ["icikt_capi.cu", "icikt_columns.cu", "icikt_pairs.cu", "icikt_reshape.cu"]
 HEADERS = ["icikt_common.cuh", "icikt_internal.h", os.path.join("..", "..", "include", "icikt_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -100,6 +100,12 @@ struct icikt_plan {
   unsigned long long* d_scalars = nullptr;  // [0] unit counter, [1] max taumax bits
   uint32_t* d_naive = nullptr;
   int64_t naive_threads = 0;
+  // matrix output (icikt_plan_download_matrices), allocated on first use
+  double* d_mat = nullptr;          // 5 x [C][C]: cor, raw, pvalue, taumax, completeness
+  unsigned char* h_mat = nullptr;   // pinned copy of all five (small C only)
+  unsigned long long* d_hist = nullptr;  // [16] pairs per status class
+  int32_t* d_ngood = nullptr;       // [C] caller-supplied n_good
+  bool pairs_done = false;
 
   cudaEvent_t ev[9]{};
   icikt_timings tm{};
@@ -144,6 +150,10 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->d_scalars);
   cudaFree(p->d_naive);
   cudaFree(p->d_scratch);
+  cudaFree(p->d_mat);
+  if (p->h_mat) cudaFreeHost(p->h_mat);
+  cudaFree(p->d_hist);
+  cudaFree(p->d_ngood);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -456,6 +466,7 @@ int icikt_plan_upload(icikt_plan* p, const double* data, int64_t ld) {
   p->d_data = p->d_data_own;
   p->ld = p->n;
   p->columns_done = false;
+  p->pairs_done = false;
   return ICIKT_OK;
 }
 
@@ -578,6 +589,7 @@ int icikt_plan_pairs(icikt_plan* p) {
   }
   CK(cudaEventRecord(p->ev[5], p->stream));
   p->tm.n_launches = (p->tm.n_launches & 0xffff) | (launches << 16);
+  p->pairs_done = true;
   return ICIKT_OK;
 }
 
@@ -635,6 +647,94 @@ int icikt_plan_download(icikt_plan* p, double* raw, double* pvalue, double* taum
   return ICIKT_OK;
 }
 
+int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_good, const int32_t* n_good,
+                                 double* cor, double* raw, double* pvalue, double* taumax, double* completeness,
+                                 int64_t* status_counts, double* max_taumax) {
+  if (!p || !p->pairs_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_pairs has not run");
+  CK(cudaSetDevice(p->device));
+  const size_t C = (size_t)p->C, cc = C * C;
+  double* outs[5] = {cor, raw, pvalue, taumax, completeness};
+  if (!p->d_mat) {
+    if (dmalloc(&p->d_mat, 5 * cc) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ICIKT_ERR_ALLOC, "device allocation of the result matrices failed");
+    }
+    CK(dmalloc(&p->d_hist, 16));
+    CK(dmalloc(&p->d_ngood, C));
+  }
+  CK(cudaEventRecord(p->ev[6], p->stream));
+  // entries no pair writes stay 0 (R/kendalltau.R:389-396 start from matrix(0, ...)); with every pair
+  // and the diagonal present nothing needs clearing
+  const int64_t ptot = tri_pairs(p->C) + (p->opts.include_diag ? p->C : 0);
+  const bool covered = !p->d_pj && p->P == ptot && (p->opts.include_diag || diag_good);
+  MatrixFill mf{};
+  for (int k = 0; k < 5; ++k) {
+    mf.m[k] = outs[k] ? p->d_mat + (size_t)k * cc : nullptr;
+    if (outs[k] && !covered) CK(cudaMemsetAsync(mf.m[k], 0, sizeof(double) * cc, p->stream));
+  }
+  CK(cudaMemsetAsync(p->d_hist, 0, 16 * sizeof(unsigned long long), p->stream));
+  if (n_good) CK(cudaMemcpyAsync(p->d_ngood, n_good, sizeof(int32_t) * C, cudaMemcpyHostToDevice, p->stream));
+  mf.units = p->d_units;
+  mf.n_units = (int64_t)p->units.size();
+  mf.max_unit_pairs = p->max_unit_pairs;
+  mf.pj_list = p->d_pj;
+  mf.tau = p->d_tau;
+  mf.pvalue = p->d_p;
+  mf.taumax = p->d_tm;
+  mf.completeness = p->d_comp;
+  mf.status = p->d_status;
+  mf.max_taumax_bits = p->d_maxbits;
+  mf.stats = p->tab.stats;
+  mf.n_good = n_good ? p->d_ngood : nullptr;
+  mf.n = p->n;
+  mf.C = p->C;
+  mf.scale_max = scale_max != 0;
+  mf.diag_good = diag_good != 0;
+  mf.hist = p->d_hist;
+  if (p->P <= 0) mf.n_units = 0;
+  if (launch_matrix_fill(mf, p->stream) < 0) return cuda_fail(cudaGetLastError(), "matrix fill kernel");
+  const size_t all_bytes = 5 * cc * sizeof(double);
+  if (all_bytes <= stage_all()) {
+    if (!p->h_mat) CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_mat), all_bytes));
+    for (int k = 0; k < 5; ++k)
+      if (outs[k])
+        CK(cudaMemcpyAsync(p->h_mat + (size_t)k * cc * sizeof(double), mf.m[k], sizeof(double) * cc,
+                           cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int k = 0; k < 5; ++k)
+      if (outs[k]) std::memcpy(outs[k], p->h_mat + (size_t)k * cc * sizeof(double), sizeof(double) * cc);
+  } else {
+    if (!p->h_stage[0]) {
+      p->stage_bytes = stage_chunk();
+      for (int i = 0; i < 2; ++i) {
+        CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_stage[i]), p->stage_bytes));
+        CK(cudaEventCreateWithFlags(&p->stage_ev[i], cudaEventDisableTiming));
+      }
+    }
+    for (int k = 0; k < 5; ++k)
+      if (outs[k]) {
+        const int rc = staged_copy_out(p, outs[k], mf.m[k], sizeof(double) * cc);
+        if (rc != ICIKT_OK) return rc;
+      }
+  }
+  unsigned long long hist[16], bits = 0;
+  CK(cudaMemcpyAsync(hist, p->d_hist, sizeof(hist), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(&bits, p->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaEventRecord(p->ev[7], p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (status_counts) {
+    int64_t bad = 0;
+    for (int k = 1; k < ICIKT_NSTATUS; ++k) { status_counts[k] = (int64_t)hist[k]; bad += status_counts[k]; }
+    status_counts[0] = p->P - bad;
+  }
+  if (max_taumax) {
+    double v;
+    std::memcpy(&v, &bits, sizeof(v));
+    *max_taumax = bits ? v : std::nan("");
+  }
+  return ICIKT_OK;
+}
+
 int icikt_plan_column_info(icikt_plan* p, int32_t* n_na) {
   if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
   CK(cudaSetDevice(p->device));
@@ -679,12 +779,19 @@ static bool cache_matches(const icikt_plan* p, int64_t n, int64_t C, const icikt
          p->opts.pair_hi == o.pair_hi && p->want_counts == (o.want_counts != 0);
 }
 
+struct MatrixOut {  // the download step of one_shot as matrices instead of per-pair arrays
+  int32_t scale_max, diag_good;
+  const int32_t* n_good;
+  double* cor;
+  int64_t* status_counts;
+};
+
 static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
                     int32_t n_global_na, const int32_t* pi, const int32_t* pj, int64_t P,
                     const icikt_opts* opts, double* raw, double* pvalue, double* taumax,
                     double* completeness, int32_t* status, int64_t* counts, double* max_taumax,
-                    icikt_timings* timings) {
-  if (!data || !raw) return fail(ICIKT_ERR_BAD_ARG, "data and raw must not be NULL");
+                    icikt_timings* timings, const MatrixOut* mat = nullptr) {
+  if (!data || (!raw && !mat)) return fail(ICIKT_ERR_BAD_ARG, "data and raw must not be NULL");
   icikt_opts o;
   if (opts) o = *opts; else icikt_default_opts(&o);
   o.want_counts = counts ? 1 : 0;
@@ -708,7 +815,11 @@ static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const 
   rc = icikt_plan_upload(p, data, ld);
   if (rc == ICIKT_OK) rc = icikt_plan_columns(p, global_na, n_global_na);
   if (rc == ICIKT_OK) rc = icikt_plan_pairs(p);
-  if (rc == ICIKT_OK) rc = icikt_plan_download(p, raw, pvalue, taumax, completeness, status, counts, max_taumax);
+  if (rc == ICIKT_OK && mat)
+    rc = icikt_plan_download_matrices(p, mat->scale_max, mat->diag_good, mat->n_good, mat->cor, raw, pvalue, taumax,
+                                      completeness, mat->status_counts, max_taumax);
+  else if (rc == ICIKT_OK)
+    rc = icikt_plan_download(p, raw, pvalue, taumax, completeness, status, counts, max_taumax);
   if (rc == ICIKT_OK && timings) rc = icikt_plan_timings(p, timings);
   const std::string keep = g_err;
   if (!cacheable) {
@@ -763,6 +874,91 @@ int icikt_all_pairs(const double* data, int64_t n, int64_t C, int64_t ld, const 
                     double* max_taumax, icikt_timings* timings) {
   return one_shot(data, n, C, ld, global_na, n_global_na, nullptr, nullptr, 0, opts, raw, pvalue, taumax,
                   completeness, status, counts, max_taumax, timings);
+}
+
+int icikt_matrices(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                   int32_t n_global_na, const int32_t* pi, const int32_t* pj, int64_t P, const icikt_opts* opts,
+                   int32_t scale_max, int32_t diag_good, const int32_t* n_good, double* cor, double* raw,
+                   double* pvalue, double* taumax, double* completeness, int64_t* status_counts,
+                   double* max_taumax, icikt_timings* timings) {
+  if ((pi == nullptr) != (pj == nullptr)) return fail(ICIKT_ERR_BAD_ARG, "pi and pj must both be given");
+  icikt_opts o;
+  if (opts) o = *opts; else icikt_default_opts(&o);
+  if (!pi && (o.pair_lo != 0 || o.pair_hi != 0))
+    return fail(ICIKT_ERR_BAD_ARG, "matrix output needs the whole pair order on one device");
+  if (!pi) o.include_diag = diag_good ? 0 : 1;  // setup_comparisons, R/kendalltau.R:191-194
+  const MatrixOut mo{scale_max, diag_good, n_good, cor, status_counts};
+  return one_shot(data, n, C, ld, global_na, n_global_na, pi, pj, P, &o, raw, pvalue, taumax, completeness,
+                  nullptr, nullptr, max_taumax, timings, &mo);
+}
+
+int icikt_pairwise_completeness(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                                int32_t n_global_na, int32_t device, const int32_t* pi, const int32_t* pj,
+                                int64_t P, int32_t* missing, double* completeness, double* matrix) {
+  if (!data || n < 1 || C < 1 || ld < n) return fail(ICIKT_ERR_BAD_ARG, "bad matrix arguments");
+  if ((pi == nullptr) != (pj == nullptr)) return fail(ICIKT_ERR_BAD_ARG, "pi and pj must both be given");
+  if (n_global_na < 0 || (n_global_na > 0 && !global_na)) return fail(ICIKT_ERR_BAD_ARG, "bad global_na");
+  if (matrix && pi) return fail(ICIKT_ERR_BAD_ARG, "the matrix output covers all pairs; pass pi = pj = NULL");
+  if (!pi) P = tri_pairs(C) + C;
+  if (pi)
+    for (int64_t k = 0; k < P; ++k)
+      if (pi[k] < 0 || pi[k] >= C || pj[k] < 0 || pj[k] >= C) return fail(ICIKT_ERR_BAD_ARG, "pair index out of range");
+  int rc = select_device(device);
+  if (rc != ICIKT_OK) return rc;
+  // R/utils.R:6-15: NA and Inf entries of global_na select classes, the rest are literals
+  double lit[64];
+  int nlit = 0, na_nan = 0, na_inf = 0;
+  for (int i = 0; i < n_global_na; ++i) {
+    const double v = global_na[i];
+    if (std::isnan(v)) { na_nan = 1; continue; }
+    if (std::isinf(v)) { na_inf = 1; continue; }
+    if (nlit == 64) return fail(ICIKT_ERR_BAD_ARG, "more than 64 global_na literals");
+    lit[nlit++] = v;
+  }
+  const int64_t words = (n + 31) / 32;
+  const bool per_pair = missing || completeness;
+  struct Buffers {
+    double *data = nullptr, *lit = nullptr, *comp = nullptr, *mat = nullptr;
+    uint32_t* bits = nullptr;
+    int32_t *pi = nullptr, *pj = nullptr, *miss = nullptr;
+    cudaStream_t stream = nullptr;
+    ~Buffers() {
+      cudaFree(data); cudaFree(lit); cudaFree(comp); cudaFree(mat); cudaFree(bits);
+      cudaFree(pi); cudaFree(pj); cudaFree(miss);
+      if (stream) cudaStreamDestroy(stream);
+    }
+  } b;
+  CK(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+  CK(dmalloc(&b.data, (size_t)n * C));
+  CK(dmalloc(&b.lit, 64));
+  CK(dmalloc(&b.bits, (size_t)words * C));
+  CK(cudaMemcpy2DAsync(b.data, sizeof(double) * n, data, sizeof(double) * ld, sizeof(double) * n, (size_t)C,
+                       cudaMemcpyHostToDevice, b.stream));
+  if (nlit) CK(cudaMemcpyAsync(b.lit, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, b.stream));
+  if (launch_missing_bits(b.data, n, n, C, b.lit, nlit, na_nan, na_inf, b.bits, words, b.stream) < 0)
+    return cuda_fail(cudaGetLastError(), "missing-mask kernel");
+  if (per_pair) {
+    if (pi) {
+      CK(dmalloc(&b.pi, (size_t)P));
+      CK(dmalloc(&b.pj, (size_t)P));
+      CK(cudaMemcpyAsync(b.pi, pi, sizeof(int32_t) * P, cudaMemcpyHostToDevice, b.stream));
+      CK(cudaMemcpyAsync(b.pj, pj, sizeof(int32_t) * P, cudaMemcpyHostToDevice, b.stream));
+    }
+    if (missing) CK(dmalloc(&b.miss, (size_t)P));
+    if (completeness) CK(dmalloc(&b.comp, (size_t)P));
+    if (launch_pair_missing(b.bits, words, n, C, b.pi, b.pj, P, b.miss, b.comp, b.stream) < 0)
+      return cuda_fail(cudaGetLastError(), "pair completeness kernel");
+    if (missing) CK(cudaMemcpyAsync(missing, b.miss, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, b.stream));
+    if (completeness) CK(cudaMemcpyAsync(completeness, b.comp, sizeof(double) * P, cudaMemcpyDeviceToHost, b.stream));
+  }
+  if (matrix) {
+    CK(dmalloc(&b.mat, (size_t)C * C));
+    if (launch_missing_matrix(b.bits, words, n, C, b.mat, b.stream) < 0)
+      return cuda_fail(cudaGetLastError(), "completeness matrix kernel");
+    CK(cudaMemcpyAsync(matrix, b.mat, sizeof(double) * C * C, cudaMemcpyDeviceToHost, b.stream));
+  }
+  CK(cudaStreamSynchronize(b.stream));
+  return ICIKT_OK;
 }
 
 int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,

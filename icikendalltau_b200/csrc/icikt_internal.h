@@ -122,6 +122,37 @@ struct EpilogueLaunch {
 };
 int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream);
 
+// scale_and_reshape on the device (R/kendalltau.R:357-421): symmetric scatter of the per-pair
+// results into C x C column-major matrices (any of m[] may be null), cor = raw / max(taumax),
+// the diagonal of diag_good; hist[10] counts the pairs of every status class.
+struct MatrixFill {
+  const PairUnit* units;
+  int64_t n_units;
+  int max_unit_pairs;
+  const int32_t* pj_list;
+  const double *tau, *pvalue, *taumax, *completeness;
+  const int32_t* status;
+  const unsigned long long* max_taumax_bits;
+  const ColStats* stats;
+  const int32_t* n_good;  // device [C] or null: n - n_na of the column tables
+  int64_t n, C;
+  int scale_max, diag_good;
+  double* m[5];  // cor, raw, pvalue, taumax, completeness
+  unsigned long long* hist;  // device [16], zeroed by the caller
+};
+int launch_matrix_fill(const MatrixFill& mf, cudaStream_t stream);
+
+// pairwise_completeness (R/kendalltau.R:563-629) from missing-row bit masks:
+// bits[w][C] (word-major so that neighbouring pairs read neighbouring words)
+int launch_missing_bits(const double* d_data, int64_t ld, int64_t n, int64_t C, const double* d_lit, int nlit,
+                        int na_nan, int na_inf, uint32_t* bits, int64_t words, cudaStream_t stream);
+// pi == null: pair order of icikt_all_pairs with the diagonal appended
+int launch_pair_missing(const uint32_t* bits, int64_t words, int64_t n, int64_t C, const int32_t* pi,
+                        const int32_t* pj, int64_t P, int32_t* missing, double* completeness,
+                        cudaStream_t stream);
+int launch_missing_matrix(const uint32_t* bits, int64_t words, int64_t n, int64_t C, double* matrix,
+                          cudaStream_t stream);
+
 int launch_pnorm(const double* d_z, int64_t n, int lower, double* d_out, cudaStream_t stream);
 
 int64_t tiled_max_n();

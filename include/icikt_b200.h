@@ -57,6 +57,7 @@ extern "C" {
 #define ICIKT_STATUS_SINGLE_UNIQUE 3 /* :234-244  "... have only a single unique value"      */
 #define ICIKT_STATUS_ALL_TIED 4      /* :291-298  "Ties equal the total"                     */
 #define ICIKT_STATUS_UNSUPPORTED 9   /* complete-observations mode only, see ICIKT_PERSPECTIVE_COMPLETE */
+#define ICIKT_NSTATUS 10             /* length of a per-class count array                    */
 
 #define ICIKT_PERSPECTIVE_GLOBAL 0 /* any string other than "local", src/kendallc.cpp:180 */
 #define ICIKT_PERSPECTIVE_LOCAL 1
@@ -147,6 +148,28 @@ int icikt_pair_list(const double* data, int64_t n, int64_t C, int64_t ld,
                     double* pvalue, double* taumax, double* completeness, int32_t* status,
                     int64_t* counts, double* max_taumax, icikt_timings* timings);
 
+/* ici_kendalltau(return_matrix = TRUE) in one call: icikt_all_pairs (pi == NULL; the diagonal
+ * pairs are computed iff !diag_good, like setup_comparisons) or icikt_pair_list (pi, pj, P)
+ * followed by icikt_plan_download_matrices; see there for the outputs.                      */
+int icikt_matrices(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                   int32_t n_global_na, const int32_t* pi, const int32_t* pj, int64_t P,
+                   const icikt_opts* opts, int32_t scale_max, int32_t diag_good,
+                   const int32_t* n_good, double* cor, double* raw, double* pvalue, double* taumax,
+                   double* completeness, int64_t* status_counts, double* max_taumax,
+                   icikt_timings* timings);
+
+/* pairwise_completeness (R/kendalltau.R:563-629): missing[k] = rows missing in column pi[k] or
+ * pj[k] (missing_either, :626-629), completeness[k] = 1 - missing/n (:617).  Here, as in
+ * setup_missing_matrix (R/utils.R:1-23), NaN/NA rows are missing only if global_na holds a NaN,
+ * +-Inf rows only if it holds an Inf.  pi == pj == NULL: all pairs in combn order followed by
+ * the C diagonal pairs (diag_good = FALSE, :586), P = C*(C-1)/2 + C outputs; then `matrix`
+ * (C x C, may be NULL) receives the symmetric completeness matrix (:598-605).  missing and
+ * completeness may be NULL.  No pair kernel runs: bit masks and popc only.                  */
+int icikt_pairwise_completeness(const double* data, int64_t n, int64_t C, int64_t ld,
+                                const double* global_na, int32_t n_global_na, int32_t device,
+                                const int32_t* pi, const int32_t* pj, int64_t P, int32_t* missing,
+                                double* completeness, double* matrix);
+
 /* ---- plan API: keeps the matrix, the per-column tables and the results resident in
  * HBM so that repeated runs (benchmarks, several perspectives on one matrix) do not
  * pay the copies.  A plan is bound to one device and is not thread-safe.            */
@@ -170,6 +193,17 @@ int icikt_plan_sync(icikt_plan* plan);
 int icikt_plan_download(icikt_plan* plan, double* raw, double* pvalue, double* taumax,
                         double* completeness, int32_t* status, int64_t* counts,
                         double* max_taumax);
+/* scale_and_reshape (R/kendalltau.R:357-421) on the device: the results of the plan's pairs as
+ * symmetric C x C column-major matrices (each may be NULL): cor = raw / max(taumax) if scale_max
+ * else raw (:368-372); entries without a computed pair are 0 (:389-396); if diag_good the diagonal
+ * is n_good/max(n_good) in cor and raw, 0 in pvalue, 1 in taumax, n_good/n in completeness
+ * (:374-386) with n_good[C] from the caller or, if NULL, n minus the column's missing count.
+ * Degenerate pairs hold NaN; status_counts[ICIKT_NSTATUS] (may be NULL) receives the number of
+ * pairs per status class so that the host can raise each warning once.                    */
+int icikt_plan_download_matrices(icikt_plan* plan, int32_t scale_max, int32_t diag_good,
+                                 const int32_t* n_good, double* cor, double* raw, double* pvalue,
+                                 double* taumax, double* completeness, int64_t* status_counts,
+                                 double* max_taumax);
 /* per-column by-products: n_na[C] (missing count per column, gives n_good and
  * frac_complete of R/kendalltau.R:165-167); may be NULL                             */
 int icikt_plan_column_info(icikt_plan* plan, int32_t* n_na);

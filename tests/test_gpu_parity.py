@@ -620,3 +620,116 @@ def test_repeated_runs_are_identical():
         again = ik.run_pairs(x, (), perspective="local", want_counts=True)
         for k in ("counts", "status", "raw", "pvalue", "taumax", "completeness"):
             np.testing.assert_array_equal(first[k], again[k], err_msg=k)
+
+
+# ---------------------------------------------------------------- result formats on the device
+def host_matrices(x, global_na, scale_max, diag_good, pi=None, pj=None, **kw):
+    """scale_and_reshape (R/kendalltau.R:357-421) done on the host from the per-pair arrays."""
+    n, C = x.shape
+    if pi is None:
+        r = ik.run_pairs(x, global_na, include_diag=not diag_good, **kw)
+        pi, pj = O.setup_comparisons(C, None, diag_good)
+    else:
+        r = ik.run_pairs(x, global_na, pi=pi, pj=pj, **kw)
+    raw = r["raw"]
+    cols = dict(cor=raw / r["max_taumax"] if scale_max else raw.copy(), raw=raw, pvalue=r["pvalue"],
+                taumax=r["taumax"], completeness=r["completeness"])
+    out = {}
+    excl = O.setup_missing_matrix(x, global_na) if len(global_na) else np.zeros(x.shape, dtype=bool)
+    n_good = (~excl).sum(axis=0)
+    for k, v in cols.items():
+        m = np.zeros((C, C))
+        m[pi, pj] = v
+        m[pj, pi] = v
+        if diag_good:
+            dg = {"cor": n_good / n_good.max(), "raw": n_good / n_good.max(), "pvalue": np.zeros(C),
+                  "taumax": np.ones(C), "completeness": n_good / n}[k]
+            m[np.arange(C), np.arange(C)] = dg
+        out[k] = m
+    return out, r, n_good
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale_max,diag_good", [(True, True), (True, False), (False, True), (False, False)])
+def test_device_matrix_fill_matches_host_reshape(scale_max, diag_good):
+    x = gen(700, 23, "mixed", 0.2, seed=31)
+    x[:, 5] = 3.0  # a constant column: degenerate pairs, NaN entries, a warning class
+    gna = (np.nan, np.inf, 0.0)
+    ref, r, n_good = host_matrices(x, gna, scale_max, diag_good, perspective="global")
+    got = _lib.run_matrices(x, gna, scale_max, diag_good, n_good, perspective="global")
+    for k in _lib.MATRIX_NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+        assert np.array_equal(got[k], got[k].T, equal_nan=True), k
+    hist = np.bincount(r["status"], minlength=_lib.NSTATUS)
+    assert list(got["status_counts"]) == list(hist)
+    assert got["max_taumax"] == r["max_taumax"]
+    # n_good from the device's own missing counts (global_na holds NaN, so they agree)
+    got2 = _lib.run_matrices(x, gna, scale_max, diag_good, None, perspective="global", want=("cor", "completeness"))
+    assert set(got2) & set(_lib.MATRIX_NAMES) == {"cor", "completeness"}
+    for k in ("cor", "completeness"):
+        assert np.array_equal(got2[k], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_device_matrix_fill_pair_list_and_chunked_copy(monkeypatch):
+    x = gen(500, 40, "ties", 0.25, seed=32)
+    rng = np.random.default_rng(7)
+    pi_all, pj_all = O.setup_comparisons(40, None, True)
+    sel = np.sort(rng.choice(pi_all.size, size=300, replace=False))
+    pi, pj = pi_all[sel].astype(np.int32), pj_all[sel].astype(np.int32)
+    ref, r, n_good = host_matrices(x, (), True, True, pi=pi, pj=pj, perspective="local")
+    got = _lib.run_matrices(x, (), True, True, n_good, pi=pi, pj=pj, perspective="local")
+    for k in _lib.MATRIX_NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert (got["raw"] == 0).sum() >= 40 * 40 - 2 * 300 - 40  # pairs that were not asked for stay 0
+    # matrices above the staging limit leave the device through the two pinned chunks
+    monkeypatch.setenv("ICIKT_STAGE_ALL", "1024")
+    monkeypatch.setenv("ICIKT_STAGE_CHUNK", "1000")
+    _lib.release_workspace()
+    ref, r, n_good = host_matrices(x, (), True, False, perspective="global")
+    got = _lib.run_matrices(x, (), True, False, n_good, perspective="global")
+    _lib.release_workspace()
+    for k in _lib.MATRIX_NAMES:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_ici_kendalltau_matrix_path_matches_long_format():
+    x = gen(900, 17, "heavy", 0.3, seed=33)
+    names = [f"s{i}" for i in range(17)]
+    for diag_good in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = ik.ici_kendalltau(x, colnames=names, diag_good=diag_good)
+            l = ik.ici_kendalltau(x, colnames=names, diag_good=diag_good, return_matrix=False)["cor"]
+        idx = {s: k for k, s in enumerate(names)}
+        i = np.array([idx[s] for s in l["s1"]]); j = np.array([idx[s] for s in l["s2"]])
+        for k in ("cor", "raw", "pvalue", "taumax", "completeness"):
+            assert np.array_equal(m[k][i, j], l[k], equal_nan=True), k
+            assert np.array_equal(m[k][j, i], l[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gna", [(np.nan, np.inf, 0.0), (0.0,), (np.inf, 2.0, 3.0), ()])
+def test_pairwise_completeness_kernel(gna):
+    x = gen(1000, 19, "heavy", 0.2, seed=34)
+    x[5, 3] = np.inf
+    x[7, 4] = -np.inf
+    excl = O.setup_missing_matrix(x, gna) if len(gna) else np.zeros(x.shape, dtype=bool)
+    pi, pj = O.setup_comparisons(19, None, False)
+    miss = np.array([(excl[:, a] | excl[:, b]).sum() for a, b in zip(pi, pj)])
+    r = _lib.pairwise_completeness(x, gna, want_matrix=True)
+    assert np.array_equal(r["missing"], miss)
+    assert np.array_equal(r["completeness"], 1 - miss / 1000)
+    m = np.zeros((19, 19))
+    m[pi, pj] = 1 - miss / 1000
+    m[pj, pi] = 1 - miss / 1000
+    assert np.array_equal(r["matrix"], m)
+    sel = np.array([3, 50, 7, 7, 120])
+    r2 = _lib.pairwise_completeness(x, gna, pi=pj[sel], pj=pi[sel])  # either order
+    assert np.array_equal(r2["missing"], miss[sel])
+    names = [f"s{i}" for i in range(19)]
+    assert np.array_equal(ik.pairwise_completeness(x, gna, colnames=names), m)
+    long = ik.pairwise_completeness(x, gna, colnames=names, include_only="s3", return_matrix=False)
+    keep = (pi == 3) | (pj == 3)
+    assert np.array_equal(long["missingness"], miss[keep])
