@@ -252,7 +252,7 @@ def run_matrices(data, global_na=(), scale_max=True, diag_good=True, n_good=None
     return out
 
 
-def pairwise_completeness(data, global_na=(), pi=None, pj=None, want_matrix=False, device=0):
+def pairwise_completeness(data, global_na=(), pi=None, pj=None, want_matrix=False, want_pairs=True, device=0):
     """icikt_pairwise_completeness: rows missing in either column and 1 - missing/n per pair
     (all pairs in combn order followed by the diagonal when pi is None)."""
     L = load()
@@ -264,13 +264,13 @@ def pairwise_completeness(data, global_na=(), pi=None, pj=None, want_matrix=Fals
         P = int(pi.size)
     else:
         P = C * (C - 1) // 2 + C
-    missing = np.empty(P, dtype=np.int32)
-    comp = np.empty(P, dtype=np.float64)
+    missing = np.empty(P, dtype=np.int32) if want_pairs else None
+    comp = np.empty(P, dtype=np.float64) if want_pairs else None
     mat = np.empty((C, C), dtype=np.float64, order="F") if want_matrix else None
     g, gp, ng = _global_na_array(global_na)
     check(L.icikt_pairwise_completeness(_ptr(data, _dp), n, C, n, gp, ng, int(device), _ptr(pi, _ip), _ptr(pj, _ip),
                                         P, _ptr(missing, _ip), _ptr(comp, _dp), _ptr(mat, _dp)))
-    out = dict(missing=missing, completeness=comp)
+    out = dict(missing=missing, completeness=comp) if want_pairs else {}
     if want_matrix:
         out["matrix"] = mat
     return out

@@ -208,8 +208,16 @@ def ici_kendalltau(data_matrix, global_na=(np.nan, np.inf, 0), perspective="glob
     global_na = [float(v) for v in global_na]
     exclude_loc = setup_missing_matrix(data, global_na)
     log.info("Figuring out comparisons to do ...")
-    pi, pj, all_pairs = setup_comparisons(names, include_only, diag_good)
-    n_todo = pi.size
+    if include_only is None and return_matrix and n_gpus <= 1 and not check_timing:
+        # every pair, in the library's own order, straight into matrices: no pair list on the host
+        pi = pj = None
+        all_pairs = True
+        if C < 2 and diag_good:
+            raise ValueError("No comparisons to do. Check the list of column names in "
+                             "`include_only` vs those in the samples.")
+    else:
+        pi, pj, all_pairs = setup_comparisons(names, include_only, diag_good)
+        n_todo = pi.size
 
     kw = dict(perspective=perspective, alternative=alternative, continuity=continuity, device=device)
     if check_timing:  # R/kendalltau.R:141-148, 633-669
@@ -377,12 +385,12 @@ def pairwise_completeness(data_matrix, global_na=(np.nan, np.inf, 0), include_on
     data, names = _colnames_of(data_matrix, colnames, "data_matrix")
     n, C = data.shape
     global_na = [float(v) for v in global_na]
-    pi, pj, all_pairs = setup_comparisons(names, include_only, diag_good=False)
     # missing-row bit masks and popc(x | y) on the device; no pair kernel runs
+    if include_only is None and return_matrix:  # the pair order itself is not needed
+        return _lib.pairwise_completeness(data, global_na, want_matrix=True, want_pairs=False, device=device)["matrix"]
+    pi, pj, all_pairs = setup_comparisons(names, include_only, diag_good=False)
     if all_pairs:
-        r = _lib.pairwise_completeness(data, global_na, want_matrix=return_matrix, device=device)
-        if return_matrix:
-            return r["matrix"]
+        r = _lib.pairwise_completeness(data, global_na, device=device)
     else:
         r = _lib.pairwise_completeness(data, global_na, pi=pi, pj=pj, device=device)
     missing, comp = r["missing"].astype(np.float64), r["completeness"]

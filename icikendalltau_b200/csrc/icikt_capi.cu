@@ -237,6 +237,34 @@ int select_device(int device) {
   return ICIKT_OK;
 }
 
+// memcpy into the caller's (usually freshly allocated, not yet faulted-in) array: one thread moves
+// about 5 GB/s there, a PCIe 5 link delivers ten times that, so large blocks are split over a few
+// threads (ICIKT_COPY_THREADS, default min(8, hardware threads); 1 = plain memcpy)
+void host_copy(void* dst, const void* src, size_t bytes) {
+  static const int n_threads = [] {
+    const char* e = std::getenv("ICIKT_COPY_THREADS");
+    int t = e ? std::atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, std::min(t, 64));
+  }();
+  constexpr size_t kMinPart = 2u << 20;
+  const int parts = (int)std::min<size_t>((size_t)n_threads, bytes / kMinPart);
+  if (parts <= 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+  std::vector<std::thread> th;
+  th.reserve((size_t)parts - 1);
+  for (int k = 1; k < parts; ++k) {
+    const size_t o = per * k;
+    if (o >= bytes) break;
+    const size_t l = std::min(per, bytes - o);
+    th.emplace_back([=] { std::memcpy(static_cast<unsigned char*>(dst) + o, static_cast<const unsigned char*>(src) + o, l); });
+  }
+  std::memcpy(dst, src, std::min(per, bytes));
+  for (auto& t : th) t.join();
+}
+
 // Device -> pageable host memory through two pinned chunks: the copy of chunk k+1 runs while chunk k
 // is moved from the staging buffer into the caller's array (cudaMemcpyAsync straight into pageable
 // memory is staged by the driver at a fraction of the link rate).
@@ -249,7 +277,7 @@ int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes) {
     const int cur = k & 1;
     if (len[cur]) {  // the chunk issued two steps ago has landed in h_stage[cur]
       CK(cudaEventSynchronize(p->stage_ev[cur]));
-      std::memcpy(out + off[cur], p->h_stage[cur], len[cur]);
+      host_copy(out + off[cur], p->h_stage[cur], len[cur]);
       len[cur] = 0;
     }
     if (o < bytes) {
@@ -617,11 +645,11 @@ int icikt_plan_download(icikt_plan* p, double* raw, double* pvalue, double* taum
     const size_t npad = std::max<size_t>(np, 1);
     const double* h = reinterpret_cast<const double*>(p->h_res);
     if (np) {
-      if (raw) std::memcpy(raw, h, sizeof(double) * np);
-      if (pvalue) std::memcpy(pvalue, h + npad, sizeof(double) * np);
-      if (taumax) std::memcpy(taumax, h + 2 * npad, sizeof(double) * np);
-      if (completeness) std::memcpy(completeness, h + 3 * npad, sizeof(double) * np);
-      if (status) std::memcpy(status, p->h_res + 4 * npad * sizeof(double) + sizeof(unsigned long long), sizeof(int32_t) * np);
+      if (raw) host_copy(raw, h, sizeof(double) * np);
+      if (pvalue) host_copy(pvalue, h + npad, sizeof(double) * np);
+      if (taumax) host_copy(taumax, h + 2 * npad, sizeof(double) * np);
+      if (completeness) host_copy(completeness, h + 3 * npad, sizeof(double) * np);
+      if (status) host_copy(status, p->h_res + 4 * npad * sizeof(double) + sizeof(unsigned long long), sizeof(int32_t) * np);
     }
     std::memcpy(&bits, h + 4 * npad, sizeof(bits));
   } else {
@@ -702,7 +730,7 @@ int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_
                            cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     for (int k = 0; k < 5; ++k)
-      if (outs[k]) std::memcpy(outs[k], p->h_mat + (size_t)k * cc * sizeof(double), sizeof(double) * cc);
+      if (outs[k]) host_copy(outs[k], p->h_mat + (size_t)k * cc * sizeof(double), sizeof(double) * cc);
   } else {
     if (!p->h_stage[0]) {
       p->stage_bytes = stage_chunk();
