@@ -34,14 +34,24 @@ __global__ void __launch_bounds__(128) matrix_fill_kernel(const FillParams p) {
     const long long slot = unit.slot0 + k;
     const long long i = unit.col, j = unit.j_explicit ? f.pj_list[slot] : unit.j0 + k;
     const long long a = j + i * C, b = i + j * C;
+    const int st = f.status[slot];
+    if (st != 0) {
+      // degenerate pair: the reference returns four NA (src/kendallc.cpp:193-199,225-244,292-298).  R's
+      // NA_real_ is the NaN with low word 1954; written as bits so that an R binder needs no fix-up
+      // pass over the matrices (a genuine NaN, e.g. the p-value of a two-row pair, stays a NaN)
+      const double na = __longlong_as_double(0x7ff00000000007a2LL);
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        if (f.m[q]) { f.m[q][a] = na; f.m[q][b] = na; }
+      atomicAdd(f.hist + (st & 15), 1ULL);  // degenerate pairs are rare
+      continue;
+    }
     const double raw = f.tau[slot];
     if (f.m[0]) { const double v = f.scale_max ? raw / mx : raw; f.m[0][a] = v; f.m[0][b] = v; }
     if (f.m[1]) { f.m[1][a] = raw; f.m[1][b] = raw; }
     if (f.m[2]) { const double v = f.pvalue[slot]; f.m[2][a] = v; f.m[2][b] = v; }
     if (f.m[3]) { const double v = f.taumax[slot]; f.m[3][a] = v; f.m[3][b] = v; }
     if (f.m[4]) { const double v = f.completeness[slot]; f.m[4][a] = v; f.m[4][b] = v; }
-    const int st = f.status[slot];
-    if (st != 0) atomicAdd(f.hist + (st & 15), 1ULL);  // degenerate pairs are rare
   }
 }
 

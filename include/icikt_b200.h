@@ -198,8 +198,9 @@ int icikt_plan_download(icikt_plan* plan, double* raw, double* pvalue, double* t
  * else raw (:368-372); entries without a computed pair are 0 (:389-396); if diag_good the diagonal
  * is n_good/max(n_good) in cor and raw, 0 in pvalue, 1 in taumax, n_good/n in completeness
  * (:374-386) with n_good[C] from the caller or, if NULL, n minus the column's missing count.
- * Degenerate pairs hold NaN; status_counts[ICIKT_NSTATUS] (may be NULL) receives the number of
- * pairs per status class so that the host can raise each warning once.                    */
+ * Degenerate pairs (status != 0) hold the NaN with R's NA_real_ bit pattern 0x7FF00000000007A2 in all
+ * five matrices; status_counts[ICIKT_NSTATUS] (may be NULL) receives the number of pairs per status
+ * class so that the host can raise each warning once.                                     */
 int icikt_plan_download_matrices(icikt_plan* plan, int32_t scale_max, int32_t diag_good,
                                  const int32_t* n_good, double* cor, double* raw, double* pvalue,
                                  double* taumax, double* completeness, int64_t* status_counts,

@@ -140,6 +140,21 @@ ici_kendalltau = function(data_matrix, global_na = c(NA, Inf, 0), perspective = 
                                 t_all / 60, t_all / 3600, t_all / 216000)))
   }
 
+  if (return_matrix && length(device) == 1L) {
+    # scale_and_reshape (R/kendalltau.R:357-421) on the device: the five matrices come back filled,
+    # degenerate pairs already NA; only the dimnames and `keep` are added here
+    t1 = Sys.time()
+    r = .Call(C_icikt_matrices, data_matrix, as.double(global_na[is.finite(global_na)]),
+              if (plan$all_pairs) NULL else plan$i, if (plan$all_pairs) NULL else plan$j,
+              perspective, alternative, continuity, any(is.infinite(global_na)), as.integer(device),
+              scale_max, diag_good, as.integer(colSums(!exclude_loc)))
+    run_time = as.numeric(difftime(Sys.time(), t1, units = "secs"))
+    .warn_status(rep(seq_along(r$status_counts) - 1L, times = r$status_counts))
+    mats = lapply(r[c("cor", "raw", "pvalue", "taumax", "completeness")],
+                  function(m) { dimnames(m) = list(samples, samples); m })
+    return(c(mats, list(keep = t(!exclude_loc), run_time = run_time)))
+  }
+
   t1 = Sys.time()
   r = .run_pairs(data_matrix, global_na, plan, !diag_good, perspective, alternative, continuity, device)
   run_time = as.numeric(difftime(Sys.time(), t1, units = "secs"))
@@ -219,18 +234,25 @@ kt_fast = function(x, y = NULL, use = "everything", alternative = "two.sided", c
 }
 
 pairwise_completeness = function(data_matrix, global_na = c(NA, Inf, 0), include_only = NULL,
-                                 return_matrix = TRUE) {
-  # 1 - (rows missing in either sample) / n, incl. (i,i); pure mask arithmetic, stays on the host
+                                 return_matrix = TRUE, device = 0L) {
+  # 1 - (rows missing in either sample) / n, incl. (i,i) (R/kendalltau.R:563-629): missing-row bit
+  # masks and popc(x | y) on the device, no pair kernel
   data_matrix = .as_numeric_matrix(data_matrix, deparse(substitute(data_matrix)))
   samples = colnames(data_matrix)
-  excl = .missing_matrix(data_matrix, global_na)
-  plan = .plan_pairs(samples, include_only, diag_good = FALSE)
-  either = vapply(seq_along(plan$i), function(k) sum(excl[, plan$i[k]] | excl[, plan$j[k]]), numeric(1))
-  comp = 1 - either / nrow(data_matrix)
+  plan = .plan_pairs(samples, include_only, diag_good = FALSE, deparse(substitute(include_only)))
+  r = .Call(C_icikt_pairwise_completeness, data_matrix, as.double(global_na),
+            if (plan$all_pairs) NULL else plan$i, if (plan$all_pairs) NULL else plan$j,
+            as.integer(device), return_matrix && plan$all_pairs)
   if (!return_matrix) {
-    return(data.frame(s1 = samples[plan$i], s2 = samples[plan$j], core = 0, missingness = either, completeness = comp))
+    return(data.frame(s1 = samples[plan$i], s2 = samples[plan$j], core = 0,
+                      missingness = as.numeric(r$missingness), completeness = r$completeness))
   }
-  .fill_matrices(samples, plan$i, plan$j, list(completeness = comp))$completeness
+  if (plan$all_pairs) {
+    m = r$matrix
+    dimnames(m) = list(samples, samples)
+    return(m)
+  }
+  .fill_matrices(samples, plan$i, plan$j, list(completeness = r$completeness))$completeness
 }
 
 .onUnload = function(libpath) {

@@ -125,6 +125,104 @@ SEXP C_icikt_pair_list(SEXP data, SEXP global_na, SEXP pi, SEXP pj, SEXP perspec
   return res;
 }
 
+/* .Call("C_icikt_matrices", data, global_na, i, j, perspective, alternative, continuity, na_inf,
+ *       device, scale_max, diag_good, n_good)
+ * scale_and_reshape (R/kendalltau.R:357-421) done on the device: returns the five C x C matrices
+ * cor, raw, pvalue, taumax, completeness (degenerate pairs already NA_real_), status_counts
+ * (pairs per status class 0..9) and max_taumax.  i = j = NULL: all pairs (+ the diagonal pairs
+ * iff !diag_good); else 1-based column indices of the pairs (include_only).  n_good: integer[C],
+ * colSums(!exclude_loc).                                                                    */
+SEXP C_icikt_matrices(SEXP data, SEXP global_na, SEXP pi, SEXP pj, SEXP perspective, SEXP alternative,
+                      SEXP continuity, SEXP na_inf, SEXP device, SEXP scale_max, SEXP diag_good, SEXP n_good) {
+  if (!isReal(data) || !isMatrix(data)) error("`data` must be a double matrix");
+  if (!isReal(global_na)) error("`global_na` must be a double vector");
+  const int64_t n = nrows(data), C = ncols(data);
+  if (!isInteger(n_good) || XLENGTH(n_good) != C) error("`n_good` must be an integer vector with one entry per column");
+  const int have_list = !isNull(pi);
+  if (have_list && (!isInteger(pi) || !isInteger(pj) || XLENGTH(pi) != XLENGTH(pj)))
+    error("`i` and `j` must be integer vectors of one length");
+  icikt_opts o;
+  fill_opts(&o, perspective, alternative, continuity, ScalarLogical(FALSE), na_inf, device);
+  const R_xlen_t P = have_list ? XLENGTH(pi) : 0;
+  int32_t *zi = NULL, *zj = NULL;
+  if (have_list) {
+    zi = (int32_t*)R_alloc((size_t)P, sizeof(int32_t));
+    zj = (int32_t*)R_alloc((size_t)P, sizeof(int32_t));
+    for (R_xlen_t k = 0; k < P; ++k) {
+      zi[k] = INTEGER(pi)[k] - 1;
+      zj[k] = INTEGER(pj)[k] - 1;
+    }
+  }
+  const char* names[] = {"cor", "raw", "pvalue", "taumax", "completeness", "status_counts", "max_taumax", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, names));
+  double* m[5];
+  for (int k = 0; k < 5; ++k) {
+    SEXP v = allocMatrix(REALSXP, (int)C, (int)C);
+    SET_VECTOR_ELT(res, k, v);
+    m[k] = REAL(v);
+  }
+  SEXP counts = allocVector(REALSXP, ICIKT_NSTATUS);
+  SET_VECTOR_ELT(res, 5, counts);
+  SEXP mxs = allocVector(REALSXP, 1);
+  SET_VECTOR_ELT(res, 6, mxs);
+  int64_t hist[ICIKT_NSTATUS];
+  double mx = NA_REAL;
+  const int rc = icikt_matrices(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), zi, zj, (int64_t)P,
+                                &o, asLogical(scale_max) == TRUE, asLogical(diag_good) == TRUE, INTEGER(n_good),
+                                m[0], m[1], m[2], m[3], m[4], hist, &mx, NULL);
+  if (rc != ICIKT_OK) {
+    UNPROTECT(1);
+    error("libicikt_b200 (%d): %s", rc, icikt_last_error());
+  }
+  for (int k = 0; k < ICIKT_NSTATUS; ++k) REAL(counts)[k] = (double)hist[k];
+  REAL(mxs)[0] = ISNAN(mx) ? NA_REAL : mx;
+  UNPROTECT(1);
+  return res;
+}
+
+/* .Call("C_icikt_pairwise_completeness", data, global_na, i, j, device, want_matrix)
+ * pairwise_completeness (R/kendalltau.R:563-629).  global_na as the user gave it (NA and Inf
+ * entries select classes, R/utils.R:6-15).  i = j = NULL: all pairs in combn order followed by
+ * the diagonal pairs; want_matrix then adds the symmetric C x C completeness matrix.        */
+SEXP C_icikt_pairwise_completeness(SEXP data, SEXP global_na, SEXP pi, SEXP pj, SEXP device, SEXP want_matrix) {
+  if (!isReal(data) || !isMatrix(data)) error("`data` must be a double matrix");
+  if (!isReal(global_na)) error("`global_na` must be a double vector");
+  const int64_t n = nrows(data), C = ncols(data);
+  const int have_list = !isNull(pi), want_m = asLogical(want_matrix) == TRUE && !have_list;
+  if (have_list && (!isInteger(pi) || !isInteger(pj) || XLENGTH(pi) != XLENGTH(pj)))
+    error("`i` and `j` must be integer vectors of one length");
+  /* NA_real_ in global_na is a NaN, which is what the library looks for */
+  const R_xlen_t P = have_list ? XLENGTH(pi) : (R_xlen_t)(C * (C - 1) / 2 + C);
+  int32_t *zi = NULL, *zj = NULL;
+  if (have_list) {
+    zi = (int32_t*)R_alloc((size_t)P, sizeof(int32_t));
+    zj = (int32_t*)R_alloc((size_t)P, sizeof(int32_t));
+    for (R_xlen_t k = 0; k < P; ++k) {
+      zi[k] = INTEGER(pi)[k] - 1;
+      zj[k] = INTEGER(pj)[k] - 1;
+    }
+  }
+  const char* names[] = {"missingness", "completeness", "matrix", ""};
+  SEXP res = PROTECT(mkNamed(VECSXP, names));
+  SEXP miss = allocVector(INTSXP, P), comp = allocVector(REALSXP, P);
+  SET_VECTOR_ELT(res, 0, miss);
+  SET_VECTOR_ELT(res, 1, comp);
+  double* mat = NULL;
+  if (want_m) {
+    SEXP v = allocMatrix(REALSXP, (int)C, (int)C);
+    SET_VECTOR_ELT(res, 2, v);
+    mat = REAL(v);
+  }
+  const int rc = icikt_pairwise_completeness(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na),
+                                             asInteger(device), zi, zj, (int64_t)P, INTEGER(miss), REAL(comp), mat);
+  if (rc != ICIKT_OK) {
+    UNPROTECT(1);
+    error("libicikt_b200 (%d): %s", rc, icikt_last_error());
+  }
+  UNPROTECT(1);
+  return res;
+}
+
 SEXP C_icikt_device_count(void) { return ScalarInteger(icikt_device_count()); }
 
 SEXP C_icikt_release(void) {
@@ -136,6 +234,8 @@ SEXP C_icikt_release(void) {
 static const R_CallMethodDef CallEntries[] = {
     {"C_icikt_all_pairs", (DL_FUNC)&C_icikt_all_pairs, 8},
     {"C_icikt_pair_list", (DL_FUNC)&C_icikt_pair_list, 9},
+    {"C_icikt_matrices", (DL_FUNC)&C_icikt_matrices, 12},
+    {"C_icikt_pairwise_completeness", (DL_FUNC)&C_icikt_pairwise_completeness, 6},
     {"C_icikt_device_count", (DL_FUNC)&C_icikt_device_count, 0},
     {"C_icikt_release", (DL_FUNC)&C_icikt_release, 0},
     {NULL, NULL, 0}};

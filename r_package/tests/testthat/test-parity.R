@@ -45,3 +45,32 @@ test_that("matrix interface agrees with the pair interface", {
   only = ici_kendalltau(x, include_only = "s1", global_na = c(NA))
   expect_equal(sum(only$cor == 0), 20 * 20 - (2 * 19 + 20))
 })
+
+test_that("device-filled matrices agree with the long format and the host scatter", {
+  set.seed(42)
+  x = matrix(rnorm(3000), 150, 20); x[sample(length(x), 400)] = NA
+  x[, 7] = 1                                           # a constant column: NA entries and one warning class
+  colnames(x) = paste0("s", seq_len(ncol(x)))
+  suppressWarnings({
+    m = ici_kendalltau(x, global_na = c(NA))           # C_icikt_matrices
+    l = ici_kendalltau(x, global_na = c(NA), return_matrix = FALSE)$cor
+  })
+  for (what in c("cor", "raw", "pvalue", "taumax", "completeness")) {
+    expect_identical(m[[what]][cbind(l$s1, l$s2)], l[[what]])
+    expect_identical(m[[what]][cbind(l$s2, l$s1)], l[[what]])
+  }
+  expect_true(is.na(m$raw["s7", "s1"]) && !is.nan(m$raw["s7", "s1"]))   # NA_real_, not NaN
+  expect_equal(unname(diag(m$taumax)), rep(1, 20))
+})
+
+test_that("pairwise_completeness matches the mask arithmetic of the reference", {
+  set.seed(7)
+  x = matrix(rpois(4000, 1), 200, 20); storage.mode(x) = "double"
+  colnames(x) = paste0("s", seq_len(ncol(x)))
+  excl = x == 0
+  m = pairwise_completeness(x)
+  expect_equal(m["s2", "s5"], 1 - sum(excl[, 2] | excl[, 5]) / 200)
+  expect_equal(unname(diag(m)), unname(1 - colSums(excl) / 200))
+  l = pairwise_completeness(x, include_only = "s3", return_matrix = FALSE)
+  expect_equal(l$missingness, vapply(seq_len(nrow(l)), function(k) sum(excl[, l$s1[k]] | excl[, l$s2[k]]), numeric(1)))
+})

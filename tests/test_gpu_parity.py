@@ -662,6 +662,8 @@ def test_device_matrix_fill_matches_host_reshape(scale_max, diag_good):
         assert np.array_equal(got[k], got[k].T, equal_nan=True), k
     hist = np.bincount(r["status"], minlength=_lib.NSTATUS)
     assert list(got["status_counts"]) == list(hist)
+    # degenerate pairs carry R's NA_real_ bit pattern (low word 1954), so an R binder needs no fix-up
+    assert got["raw"].view(np.uint64)[5, 0] == 0x7FF00000000007A2 and got["cor"].view(np.uint64)[0, 5] == 0x7FF00000000007A2
     assert got["max_taumax"] == r["max_taumax"]
     # n_good from the device's own missing counts (global_na holds NaN, so they agree)
     got2 = _lib.run_matrices(x, gna, scale_max, diag_good, None, perspective="global", want=("cor", "completeness"))
