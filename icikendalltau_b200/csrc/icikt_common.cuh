@@ -128,6 +128,49 @@ ICIKT_HD double pnorm_std(double x, bool lower_tail) {
 
 ICIKT_HD double qnan() { return nan(""); }
 
+// (double)(1.0L - (long double)m / (long double)n) bit for bit as x87 extended precision evaluates
+// it -- the reference's completeness (src/kendallc.cpp:205-212: `long double completeness =
+// 1 - (missingness / either_na_length)`, stored into a double) on x86-64: the quotient rounded to a
+// 64-bit significand, the difference rounded to 64 bits again, then to double.  For pairs with few
+// complete rows the cancellation makes this differ from the correctly rounded (n - m) / n by a few
+// ulps, so it is reproduced with integer arithmetic instead.  0 <= m <= n < 2^31.
+ICIKT_HD double one_minus_ratio_x87(uint64_t m, uint64_t n) {
+  if (m == 0) return 1.0;
+  if (m >= n) return 0.0;
+  int e = 0;
+  uint64_t mm = m;
+  while (mm < n) {  // m/n in [2^-e, 2^-(e-1)), n <= mm < 2n
+    mm <<= 1;
+    ++e;
+  }
+  // Q = round-to-nearest-even(mm * 2^63 / n), 2^63 <= Q < 2^64: long division in base 2^32
+  const uint64_t lo = (mm & 1ull) << 63;
+  uint64_t r = mm >> 1;  // < n
+  const uint64_t d1 = (r << 32) | (lo >> 32), q1 = d1 / n;
+  r = d1 - q1 * n;
+  const uint64_t d2 = (r << 32), q2 = d2 / n;  // the low 32 bits of the dividend are zero
+  r = d2 - q2 * n;
+  uint64_t Q = (q1 << 32) | q2;
+  if (2 * r > n || (2 * r == n && (Q & 1ull))) ++Q;
+  // 1 - Q * 2^-(63+e) = D * 2^-(63+e) with D = (2^k - 1) * 2^64 + L, k = e - 1, L = 2^64 - Q:
+  // D has 64 + k bits, the low k are rounded away (nearest even); the result is kept * 2^-64
+  const uint64_t L = 0ull - Q;
+  const int k = e - 1;
+  uint64_t kept = L;
+  if (k > 0) {
+    const uint64_t dropped = L & ((1ull << k) - 1ull), half = 1ull << (k - 1);
+    kept = (~0ull << (64 - k)) | (L >> k);
+    if (dropped > half || (dropped == half && (kept & 1ull))) {
+      if (++kept == 0ull) return 1.0;
+    }
+  }
+#ifdef __CUDA_ARCH__
+  return __ull2double_rn(kept) * 5.421010862427522170037e-20;  // 2^-64, exact scaling
+#else
+  return (double)kept * 5.421010862427522170037e-20;  // u64 -> double rounds to nearest even
+#endif
+}
+
 // tau, tau_max and the variance-based p-value from the exact integer counts of one pair
 // (src/kendallc.cpp:280-335).  s2/s3/s5 are the column's sums of t(t-1), t(t-1)(t-2), t(t-1)(2t+5)
 // over its tie groups on the np rows that enter.  Sets status 4 and returns false if every pair
@@ -213,10 +256,9 @@ ICIKT_HD void pair_epilogue(int64_t n, const ColStats& X, const ColStats& Y, int
                        Y.s3o + t0y * (t0y - 1) * (t0y - 2), Y.s5o + t0y * (t0y - 1) * (2 * t0y + 5), ntie,
                        dis, alternative, continuity, o))
     return;
-  // :205-212  completeness = 1 - card(NA_x or NA_y) / length, evaluated as one correctly
-  // rounded quotient (the reference uses x87 long double and rounds once at the end)
+  // :205-212  completeness = 1 - card(NA_x or NA_y) / length in long double, stored as double
   const int64_t miss = a + c - b - bb;
-  o.completeness = (double)(np - miss) / (double)np;
+  o.completeness = one_minus_ratio_x87((uint64_t)miss, (uint64_t)np);
 }
 
 // Counts of one pair restricted to the rows present in BOTH columns (kt_fast with

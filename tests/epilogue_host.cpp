@@ -15,3 +15,7 @@ extern "C" int epilogue_host(long long n, const long long* xs, const long long* 
   out_counts[0] = o.xtie; out_counts[1] = o.ytie; out_counts[2] = o.tot; out_counts[3] = o.n_entry;
   return o.status;
 }
+
+extern "C" double one_minus_ratio_host(unsigned long long m, unsigned long long n) {
+  return icikt::one_minus_ratio_x87(m, n);
+}

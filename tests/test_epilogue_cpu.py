@@ -2,7 +2,7 @@
 oracle: per-column tie statistics + (dis, ntie, b) of the GLOBAL problem must reproduce the
 reference's results for both perspectives, including the degenerate statuses.
 Tolerances: tau/tau_max 1e-12 relative (north_star), p-value 1e-9 relative (z^2-amplified,
-SURVEY.md 7.3), completeness 1 ulp."""
+SURVEY.md 7.3), completeness bit-exact (x87 long-double arithmetic reproduced with integers)."""
 import ctypes
 import os
 import subprocess
@@ -113,7 +113,7 @@ def test_epilogue_random(epi, persp):
             assert (oc[0], oc[1], oc[2], oc[3]) == (ref.xtie, ref.ytie, ref.tot, ref.n_entry)
             assert close(out4[0], ref.tau, 1e-12) and close(out4[2], ref.tau_max, 1e-12)
             assert close(out4[1], ref.pvalue, 1e-9), (out4[1], ref.pvalue)
-            assert close(out4[3], ref.completeness, 2.3e-16)
+            assert out4[3] == ref.completeness  # bit-exact
         else:
             assert np.isnan(out4).all()
     assert n_checked > 200
@@ -157,3 +157,22 @@ def test_epilogue_n2_gives_nan_pvalue(epi):
     ref = O.ici_kt(x, y, "global")
     st, out4, _ = run(epi, x, y, "global", "two.sided", False)
     assert st == 0 and out4[0] == ref.tau == -1.0 and np.isnan(out4[1]) and np.isnan(ref.pvalue)
+
+
+def test_completeness_reproduces_x87_long_double(epi):
+    """src/kendallc.cpp:205-212 evaluates 1 - m/n in long double (x87 extended precision on the
+    reference's x86-64 builds) and stores a double; the epilogue reproduces it bit for bit."""
+    if np.finfo(np.longdouble).nmant != 63:
+        pytest.skip("numpy longdouble is not the x87 80-bit format here")
+    epi.one_minus_ratio_host.argtypes = [ctypes.c_ulonglong, ctypes.c_ulonglong]
+    epi.one_minus_ratio_host.restype = ctypes.c_double
+    rng = np.random.default_rng(5)
+    one = np.longdouble(1)
+    cases = [(m, n) for n in (1, 2, 3, 7, 10, 96, 100, 1000, 4099, 28672, 65535) for m in range(0, min(n, 300) + 1)]
+    cases += [(n - d, n) for n in (5000, 20000, 28672, 60000, 65535) for d in range(0, 400)]
+    cases += [(int(rng.integers(0, n + 1)), n) for n in rng.integers(1, 2 ** 31 - 1, size=20000).tolist()]
+    bad = 0
+    for m, n in cases:
+        want = float(one - np.longdouble(m) / np.longdouble(n))
+        bad += epi.one_minus_ratio_host(m, n) != want
+    assert bad == 0

@@ -1,9 +1,14 @@
 """Executed-instruction / shared-memory-wavefront share per barrier-delimited region of a kernel
-(ncu source page).  Usage: python tools/ncu_regions.py report.ncu-rep [--ops]"""
+(ncu source page).  Usage: python tools/ncu_regions.py report.ncu-rep [--ops] [--skip K]
+(--skip K: the report holds several launches, read the K-th)"""
 import csv, subprocess, sys
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr, data = rows[1], rows[2:]
+starts = [k for k, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+which = int(sys.argv[sys.argv.index('--skip') + 1]) if '--skip' in sys.argv else 0
+rows = rows[starts[which]:starts[which + 1]]
+print(rows[0][1][:100])
+hdr, data = rows[1], [r for r in rows[2:] if len(r) > 10]
 iS, iE, iSm = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('# Samples')
 iW, iWi = hdr.index('L1 Wavefronts Shared'), hdr.index('L1 Wavefronts Shared Ideal')
 def num(x):
