@@ -18,11 +18,11 @@
 #include <cstdlib>
 
 #include "icikt_internal.h"
+#include "icikt_count.cuh"
 
 namespace icikt {
 namespace {
 
-constexpr unsigned FULL = 0xffffffffu;
 constexpr int RANK_THREADS = 512;
 
 __device__ __forceinline__ unsigned long long order_key(double v) {
@@ -84,10 +84,42 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* buf) {
   for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
   if (lane == 0) buf[warp] = v;
   __syncthreads();
-  long long t = 0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += buf[w];
+  long long t = (lane < (int)(blockDim.x >> 5)) ? buf[lane] : 0;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
   __syncthreads();
   return t;
+}
+
+// four sums with one pair of barriers; buf holds 4 * 32 values
+__device__ __forceinline__ void block_sum_ll4(long long& a, long long& b, long long& c, long long& d, long long* buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    a += __shfl_xor_sync(FULL, a, s);
+    b += __shfl_xor_sync(FULL, b, s);
+    c += __shfl_xor_sync(FULL, c, s);
+    d += __shfl_xor_sync(FULL, d, s);
+  }
+  if (lane == 0) {
+    buf[warp] = a;
+    buf[32 + warp] = b;
+    buf[64 + warp] = c;
+    buf[96 + warp] = d;
+  }
+  __syncthreads();
+  a = lane < nw ? buf[lane] : 0;
+  b = lane < nw ? buf[32 + lane] : 0;
+  c = lane < nw ? buf[64 + lane] : 0;
+  d = lane < nw ? buf[96 + lane] : 0;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    a += __shfl_xor_sync(FULL, a, s);
+    b += __shfl_xor_sync(FULL, b, s);
+    c += __shfl_xor_sync(FULL, c, s);
+    d += __shfl_xor_sync(FULL, d, s);
+  }
+  __syncthreads();
 }
 
 // Short columns (n <= 8192): the WHOLE per-column preprocessing in one kernel, one CTA per
@@ -109,14 +141,15 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         uint16_t* __restrict__ trun, uint16_t* __restrict__ tend, uint32_t* __restrict__ nabits,
                         uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
                         uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
-                        int32_t* __restrict__ max_tied) {
+                        int32_t* __restrict__ max_tied, const PipeConst pc) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
   __shared__ int warp_sums[32];
-  __shared__ long long llbuf[32];
+  __shared__ long long llbuf[128];
   __shared__ unsigned long long mnkey;
   __shared__ int n_large;
+  __shared__ uint32_t descA[32], descB[32];
   typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
   const int col = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) n_large = 0;
@@ -214,10 +247,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
     s3 += t * (t - 1) * (t - 2);
     s5 += t * (t - 1) * (2 * t + 5);
   }
-  s2 = block_sum_ll(s2, llbuf);
-  s3 = block_sum_ll(s3, llbuf);
-  s5 = block_sum_ll(s5, llbuf);
-  ntied = block_sum_ll(ntied, llbuf);
+  block_sum_ll4(s2, s3, s5, ntied, llbuf);
   const int g0size = (K > 0) ? (int)gpos[1] : 0;
   const int first_run = g0size > 1 ? g0size : 0;
   // membership mask of the first group; rows of the other tied groups with their dense group index
@@ -285,6 +315,38 @@ __global__ void __launch_bounds__(SORT_THREADS)
     }
     atomicMax(max_tied + 2, K);
   }
+  // ---- cconst: pass A (icikt_count.cuh) over the column's own sorted dense ranks.  They hold no
+  // inversion, so what the bucket-free pass counts on them is exactly the per-column constant the
+  // pair kernel subtracts.  One 8-key run per thread (kk = 1), two u16 buffers in the shared
+  // memory the sort and the tables above no longer need.
+  if (K < 2) return;  // constant or all-missing column: cconst stays 0 (block-uniform)
+  __syncthreads();    // gpos / bits have been read by everyone
+  {
+    const int nw = (n + 255) >> 8;  // warps whose 256 positions hold keys; the others only keep the barriers
+    const int capc = nw << 8;
+    const int L = max(1, 32 - __clz(K - 1));
+    const uint32_t bufA = smem_addr(sort_smem), bufB = bufA + 2u * (uint32_t)capc;
+    int r = excl - 1;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      if ((fmask >> i) & 1u) ++r;
+      if (base + i < n) Mem<false>::st16(bufA + 2u * (uint32_t)(base + i), (uint32_t)r);
+    }
+    const uint32_t pad = (1u << L) - 1u;
+    for (int q = n + tid; q < capc; q += SORT_THREADS) Mem<false>::st16(bufA + 2u * (uint32_t)q, pad);
+    __syncthreads();
+    unsigned long long acc = 0;
+    if ((tid >> 5) < nw) {
+      count_pass<false>(bufA, bufB, 1, nw, L, descA, descB, tid & 31, tid >> 5, pc, acc);
+    } else {  // count_pass has two block-wide barriers per two-bit level
+      for (int lv = (L - 1) & ~1; lv >= 0; lv -= 2) {
+        __syncthreads();
+        __syncthreads();
+      }
+    }
+    const long long total = block_sum_ll((long long)acc, llbuf);
+    if (tid == 0) stats[col].cconst = (uint64_t)total;
+  }
 }
 
 template <int SORT_THREADS, int ITEMS>
@@ -293,13 +355,18 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * (CAP / 32);
-  const size_t smem = std::max(sizeof(typename Sort::TempStorage), post);
+  const size_t pass_a = 2 * 2 * (size_t)SORT_THREADS * 8;  // two u16 buffers of 8 keys per thread
+  const size_t smem = std::max(std::max(sizeof(typename Sort::TempStorage), post), pass_a);
+  PipeConst pc;
+  pc.one = 1u;
+  pc.two = 2u;
+  pc.c64k = 65536u;
   auto kern = column_fused_kernel<SORT_THREADS, ITEMS>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
                                                         tab.trow, tab.trun, tab.tend, tab.nabits, tab.firstbits, tab.gstart,
-                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
+                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, pc);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -313,7 +380,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        int32_t* __restrict__ max_tied) {
   __shared__ int n_large;
   __shared__ int warp_sums[32];
-  __shared__ long long llbuf[32];
+  __shared__ long long llbuf[128];
   __shared__ uint32_t bits[2048];
   const int col = blockIdx.x;
   const int tid = threadIdx.x;
@@ -381,10 +448,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
     s3 += t * (t - 1) * (t - 2);
     s5 += t * (t - 1) * (2 * t + 5);
   }
-  s2 = block_sum_ll(s2, llbuf);
-  s3 = block_sum_ll(s3, llbuf);
-  s5 = block_sum_ll(s5, llbuf);
-  ntied = block_sum_ll(ntied, llbuf);
+  block_sum_ll4(s2, s3, s5, ntied, llbuf);
   const int g0size = (K > 0) ? (int)gpos[1] : 0;
   const int first_run = g0size > 1 ? g0size : 0;
 
@@ -494,7 +558,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     else ICIKT_FUSED(1024, 8);
 #undef ICIKT_FUSED
     if (l < 0) return -1;
-    launches += l;
+    return launches + l;  // the fused kernel computes the pass-A constants itself
   } else {
     seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, C, nstride, n);
     ++launches;

@@ -1,0 +1,331 @@
+// icikt_count.cuh -- the memory-space accessors and pass A, the bucket-free inversion-counting
+// pass on 16-bit keys (see icikt_pairs.cu for the counting scheme).  Shared by the pair kernel
+// (icikt_pairs.cu) and the fused column kernel (icikt_columns.cu), which runs the pass on the
+// column's own sorted ranks to get the per-column constant `cconst`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace icikt {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ uint32_t lanemask_le() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+  return m;
+}
+// lanes strictly below the highest set bit of `bits` (bits != 0)
+__device__ __forceinline__ uint32_t below_top(uint32_t bits) {
+  return (1u << (31 - __clz((int)bits))) - 1u;
+}
+
+// ---- memory-space accessors ----------------------------------------------------------------
+// The counting passes run either on shared memory (32-bit shared-window addresses, explicit
+// ld/st.shared) or, for vectors too long for one CTA's shared memory, on a per-CTA scratch in
+// global memory that stays L2-resident.  Offsets are in bytes.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// Constants handed over as kernel parameters so that the assembler keeps multiplications by
+// them as IMAD / IMAD.HI (FMA pipe) instead of strength-reducing them to integer-ALU shifts/adds.
+struct PipeConst {
+  uint32_t one, two, c64k;
+};
+
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (sm_90+) ---------------------
+// Used for the one contiguous bulk transfer of the pair kernel: y's dense-rank table into the
+// second sequence buffer.  One thread issues it; the copy engine moves the bytes while the CTA
+// does the bit-mask counting, then everybody waits on the barrier's phase.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  // earlier generic-proxy accesses to the destination are ordered before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <bool G>
+struct Mem;
+template <>
+struct Mem<false> {
+  typedef uint32_t ptr;
+  static __device__ __forceinline__ ptr add(ptr p, int32_t bytes) { return p + (uint32_t)bytes; }
+  static __device__ __forceinline__ uint32_t ld16(ptr p) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(p) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ uint32_t ld32(ptr p) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void ld128(ptr p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(p) : "memory");
+  }
+  // position of p for the inversion accumulator: any value that differs from the byte offset
+  // inside the buffer by a per-level constant (here the shared-window address itself)
+  static __device__ __forceinline__ uint32_t off(ptr p, ptr) { return p; }
+  // a + b on the FMA pipe (IMAD with a multiplier the assembler cannot fold): the integer ALU
+  // pipe is the binding one in pass A, both pipes issue one warp instruction per two cycles
+  static __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+  }
+  // high 16-bit key of a word on the FMA pipe (IMAD.HI by 65536)
+  static __device__ __forceinline__ uint32_t hi16(uint32_t w, uint32_t c64k) {
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(w), "r"(c64k));
+    return d;
+  }
+  // one key of pass A's scatter sweep (two bits per level, see count_pass): Q01/Q23 hold the
+  // next free slot (element index, 16 bits each) of digit classes 0|1 and 2|3, S the number of
+  // keys seen so far whose high bit is set.  `two` is a register holding 2 that the assembler
+  // cannot fold, so the slot address is an IMAD and not an LEA.  14 instructions per key.
+  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                               uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
+                                               uint32_t key, ptr base, uint32_t two) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred ph, pl;\n\t"
+        ".reg .b32 t, qs, sel, idx, ad, inc, up;\n\t"
+        "and.b32 t, %5, %7;\n\t"
+        "setp.ne.u32 ph, t, 0;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 pl, t, 0;\n\t"
+        "selp.b32 qs, %1, %0, ph;\n\t"
+        "selp.b32 sel, 0x4432, 0x4410, pl;\n\t"
+        "prmt.b32 idx, qs, 0, sel;\n\t"
+        "mad.lo.u32 ad, idx, %10, %9;\n\t"
+        "st.shared.u16 [ad], %8;\n\t"
+        "selp.b32 inc, 0x10000, 1, pl;\n\t"
+        "shr.u32 up, qs, 16;\n\t"
+        "@ph add.u32 %1, %1, inc;\n\t"
+        "@!ph add.u32 %0, %0, inc;\n\t"
+        "@!ph add.u32 %3, %3, %2;\n\t"
+        "@ph add.u32 %2, %2, 1;\n\t"
+        "@!pl add.u32 %4, %4, up;\n\t"
+        "}"
+        : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base), "r"(two)
+        : "memory");
+  }
+  // the same without the store: the last level only has to count
+  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred ph, pl;\n\t"
+        ".reg .b32 t, qs, inc, up;\n\t"
+        "and.b32 t, %5, %7;\n\t"
+        "setp.ne.u32 ph, t, 0;\n\t"
+        "and.b32 t, %5, %6;\n\t"
+        "setp.ne.u32 pl, t, 0;\n\t"
+        "selp.b32 qs, %1, %0, ph;\n\t"
+        "selp.b32 inc, 0x10000, 1, pl;\n\t"
+        "shr.u32 up, qs, 16;\n\t"
+        "@ph add.u32 %1, %1, inc;\n\t"
+        "@!ph add.u32 %0, %0, inc;\n\t"
+        "@!ph add.u32 %3, %3, %2;\n\t"
+        "@ph add.u32 %2, %2, 1;\n\t"
+        "@!pl add.u32 %4, %4, up;\n\t"
+        "}"
+        : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi));
+  }
+  static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ ptr from_shared(const void* q) { return smem_addr(q); }
+  static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(p), "h"((unsigned short)v) : "memory");
+  }
+  static __device__ __forceinline__ void st32(ptr p, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
+  }
+  static __device__ __forceinline__ void st128(ptr p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  }
+};
+template <>
+struct Mem<true> {
+  typedef unsigned char* ptr;
+  static __device__ __forceinline__ ptr add(ptr p, int32_t bytes) { return p + bytes; }
+  static __device__ __forceinline__ uint32_t ld16(ptr p) { return *reinterpret_cast<const unsigned short*>(p); }
+  static __device__ __forceinline__ uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t*>(p); }
+  static __device__ __forceinline__ void ld128(ptr p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    a = v.x; b = v.y; c = v.z; d = v.w;
+  }
+  static __device__ __forceinline__ uint32_t off(ptr p, ptr base) { return (uint32_t)(p - base); }
+  static __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t) { return a + b; }
+  static __device__ __forceinline__ uint32_t hi16(uint32_t w, uint32_t) { return w >> 16; }
+  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                               uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
+                                               uint32_t key, ptr base, uint32_t) {
+    const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
+    const uint32_t qs = ph ? Q23 : Q01;
+    const uint32_t idx = pl ? (qs >> 16) : (qs & 0xffffu);
+    *reinterpret_cast<unsigned short*>(base + 2 * (size_t)idx) = (unsigned short)key;
+    const uint32_t inc = pl ? 0x10000u : 1u;
+    if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
+    if (ph) S += 1;
+    if (!pl) acc2 += qs >> 16;
+  }
+  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
+                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi) {
+    const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
+    const uint32_t qs = ph ? Q23 : Q01;
+    const uint32_t inc = pl ? 0x10000u : 1u;
+    if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
+    if (ph) S += 1;
+    if (!pl) acc2 += qs >> 16;
+  }
+  static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) { atomicAdd(reinterpret_cast<uint32_t*>(p), v); }
+  // generic addressing reaches shared memory too
+  static __device__ __forceinline__ ptr from_shared(const void* q) { return (ptr) const_cast<void*>(q); }
+  static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
+    *reinterpret_cast<unsigned short*>(p) = (unsigned short)v;
+  }
+  static __device__ __forceinline__ void st32(ptr p, uint32_t v) { *reinterpret_cast<uint32_t*>(p) = v; }
+  static __device__ __forceinline__ void st128(ptr p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+  }
+};
+
+// Pass A: the bucket-free counting pass on 16-bit keys (see the file header), lane-sequential,
+// TWO bits per level.  Thread t of the CTA owns the contiguous range [t*R, (t+1)*R) of the
+// sequence, R = 8*kk keys, and walks it with 128-bit loads (kk must be ODD: the 16-byte accesses
+// of a quarter warp then fall into distinct bank groups).  A level on bits (s+1, s) is the fusion
+// of the two one-bit levels s+1 and s: a stable partition of the whole sequence into the digit
+// classes 0,1,2,3 (digit = 2*hi + lo), and the count
+//     sum over keys with hi = 0 of #(hi = 1 keys before it)                        [bit s+1]
+//   + sum over keys with lo = 0 of #(lo = 1 keys before it after the hi partition)  [bit s]
+// where the second term is, for a key of class 0, the class-1 keys before it, and for a key of
+// class 2 all N1 class-1 keys plus the class-3 keys before it.  Per level:
+//   sweep 1  counts the range's keys per class, two keys per 32-bit word at once
+//            ((w >> s) & 0x00010001 summed in two 16-bit fields);
+//   two packed warp scans + warp-total reductions give the class counts before the range;
+//   sweep 2  walks the range with four running slot indices (packed 2 x 16 bit in Q01, Q23),
+//            stores every key to its slot of the other buffer and accumulates the count.
+// No ballots, no per-key population counts: about 16 instructions per key and level of two bits.
+// With an odd number of bits the first level treats the missing top bit as zero.
+//   acc64 += the count over all levels (this thread's share)
+template <bool G>
+__device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
+                                           const int nwarps, const int L, uint32_t* descA, uint32_t* descB,
+                                           const int lane, const int warp, const PipeConst pc,
+                                           unsigned long long& acc64) {
+  typedef Mem<G> M;
+  const uint32_t tid = ((uint32_t)warp << 5) + (uint32_t)lane;
+  const uint32_t R = (uint32_t)kk << 3;                // keys per thread range
+  const uint32_t my_off = tid * (R << 1);              // bytes
+  const uint32_t my_pos = tid * R;
+  const uint32_t cap = ((uint32_t)nwarps << 5) * R;    // keys per buffer
+  for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
+    const typename M::ptr ra = M::add(a, (int32_t)my_off);
+    uint32_t cl = 0, ch = 0, cb = 0;
+#pragma unroll 1
+    for (int c = 0; c < kk; ++c) {
+      uint32_t w[4];
+      M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = (w[j] >> s) & 0x00010001u, hi = (w[j] >> (s + 1)) & 0x00010001u;
+        cl = M::fadd(cl, lo, pc.one);
+        ch = M::fadd(ch, hi, pc.one);
+        cb = M::fadd(cb, lo & hi, pc.one);
+      }
+    }
+    const uint32_t n3 = (cb & 0xffffu) + (cb >> 16);
+    const uint32_t n2 = (ch & 0xffffu) + (ch >> 16) - n3;
+    const uint32_t n1 = (cl & 0xffffu) + (cl >> 16) - n3;
+    const uint32_t A = n1 | (n2 << 16), B = n3;
+    uint32_t inclA = A, inclB = B;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t tA = __shfl_up_sync(FULL, inclA, d), tB = __shfl_up_sync(FULL, inclB, d);
+      if (lane >= d) {
+        inclA += tA;
+        inclB += tB;
+      }
+    }
+    if (lane == 31) {
+      descA[warp] = inclA;
+      descB[warp] = inclB;
+    }
+    __syncthreads();
+    const uint32_t vA = (lane < nwarps) ? descA[lane] : 0u, vB = (lane < nwarps) ? descB[lane] : 0u;
+    const uint32_t totA = __reduce_add_sync(FULL, vA), totB = __reduce_add_sync(FULL, vB);
+    const uint32_t exA = __reduce_add_sync(FULL, (lane < warp) ? vA : 0u) + inclA - A;
+    const uint32_t exB = __reduce_add_sync(FULL, (lane < warp) ? vB : 0u) + inclB - B;
+    const uint32_t e1 = exA & 0xffffu, e2 = exA >> 16, e3 = exB;           // class counts before my range
+    const uint32_t N1 = totA & 0xffffu, N2 = totA >> 16, N3 = totB;
+    const uint32_t N0 = cap - N1 - N2 - N3;
+    uint32_t Q01 = ((N0 + e1) << 16) | (my_pos - e1 - e2 - e3);
+    uint32_t Q23 = ((N0 + N1 + N2 + e3) << 16) | (N0 + N1 + e2);
+    uint32_t S = e2 + e3, acc = 0, acc2 = 0;
+    uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
+    asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));  // keep the bit tests single LOP3s
+    if (s > 0) {
+#pragma unroll 1
+      for (int c = 0; c < kk; ++c) {
+        uint32_t w[4];
+        M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          M::step4(Q01, Q23, S, acc, acc2, w[j], bLl, bHl, w[j], b, pc.two);
+          M::step4(Q01, Q23, S, acc, acc2, w[j], bLh, bHh, M::hi16(w[j], pc.c64k), b, pc.two);
+        }
+      }
+    } else {  // the sorted sequence itself is not needed: the last level only counts
+#pragma unroll 1
+      for (int c = 0; c < kk; ++c) {
+        uint32_t w[4];
+        M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          M::step4c(Q01, Q23, S, acc, acc2, w[j], bLl, bHl);
+          M::step4c(Q01, Q23, S, acc, acc2, w[j], bLh, bHh);
+        }
+      }
+    }
+    // acc2 summed absolute slot indices: take out the class bases (class 1 starts at N0, class 3
+    // at N0+N1+N2) and add the N1 class-1 keys that precede every class-2 key after the hi partition
+    const uint32_t n0 = R - n1 - n2 - n3;
+    acc64 += (unsigned long long)(acc + acc2 - n0 * N0 - n2 * (N0 + N2));
+    __syncthreads();  // also protects descA/descB for the next level
+    const typename M::ptr t = a;
+    a = b;
+    b = t;
+  }
+}
+
+}  // namespace
+}  // namespace icikt
