@@ -11,10 +11,10 @@ python bench.py --workload $wl --steps 3 --warmup 3 --cpu-budget 10 > gpurun_out
 done
 python bench.py --kernel naive --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${tag}_naive_config2.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}_config2.csv python bench.py --steps 2 --warmup 3 --quick > gpurun_out/ncu_launch.log 2>&1
-prof() { # name workload cols  (three pair-kernel launches per step, one per tier: the first of a step runs)
-ncu --set full --clock-control none --import-source on -k regex:pairs_tiled --launch-skip $4 --launch-count 1 -f -o gpurun_out/prof_${tag}_k2_$1 python bench.py --workload $2 --cols $3 --steps 1 --warmup 3 --quick > gpurun_out/ncu_$1.log 2>&1
+prof() { # name workload cols  (three pair-kernel launches per step, one per tier; all three of the timed step are captured, two of them exit at once)
+ncu --set full --clock-control none --import-source on -k regex:pairs_tiled --launch-skip 9 --launch-count 3 -f -o gpurun_out/prof_${tag}_k2_$1 python bench.py --workload $2 --cols $3 --steps 1 --warmup 3 --quick > gpurun_out/ncu_$1.log 2>&1
 }
-prof config2 config2 100 9
-prof target target 300 9
-prof config1 config1 96 10
+prof config2 config2 100
+prof target target 300
+prof config1 config1 96
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
