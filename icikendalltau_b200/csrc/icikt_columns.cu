@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         uint16_t* __restrict__ trun, uint16_t* __restrict__ tend, uint32_t* __restrict__ nabits,
                         uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
                         uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
-                        int32_t* __restrict__ max_tied, const PipeConst pc) {
+                        int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord, const PipeConst pc) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
   unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(sort_smem);           // [SORT_THREADS]
   uint16_t* gpos = reinterpret_cast<uint16_t*>(sort_smem + 8 * SORT_THREADS);                // [CAP + 2]
   uint32_t* bits = reinterpret_cast<uint32_t*>(sort_smem + 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15));  // [CAP/32]
+  uint32_t* whist = bits + ((CAP / 32 + 3) & ~3);                                            // [CAP]
   const int base = tid * ITEMS;  // blocked arrangement after the sort
   uint16_t* pm = perm + (size_t)col * nstride;
   uint16_t* rk = rank + (size_t)col * nstride;
@@ -289,6 +290,45 @@ __global__ void __launch_bounds__(SORT_THREADS)
       }
     }
   }
+  // ---- walk order for the pair kernel's direct comparison of small tie groups: a tied row is
+  // compared with the rows behind it in its group (`walk` of them), so consecutive rows of a group
+  // walk t-1, t-2, ... 0 steps and a warp taking them in list order idles half of the time.  Here the
+  // tied rows are sorted by walk length, longest first (counting sort), and listed as
+  // (list index << 16 | walk): the lanes of a warp then walk equally far.
+  if ((tot2 & 0xffff) > 0) {  // block-uniform
+    for (int w = tid; w < n; w += SORT_THREADS) whist[w] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i)
+      if ((tmask >> i) & 1u) {
+        const uint32_t walk = ((lmask >> i) & 1u) ? 0u : (uint32_t)(after[i] - 1);
+        after[i] = (int)(walk | (atomicAdd(&whist[walk], 1u) << 16));  // rank inside the walk class
+      }
+    __syncthreads();
+    {  // class offsets, longest walk first
+      const int per = (n + SORT_THREADS - 1) / SORT_THREADS;
+      const int hi = n - 1 - tid * per, lo = max(hi - per + 1, 0);
+      int sum = 0;
+      for (int v = hi; v >= lo; --v) sum += (int)whist[v];
+      int total;
+      int run = block_scan_excl(sum, warp_sums, total);
+      for (int v = hi; v >= lo; --v) {
+        const int c = (int)whist[v];
+        whist[v] = (uint32_t)run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    uint32_t* to = tord + (size_t)col * nstride;
+    int pos = excl2 & 0xffff;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i)
+      if ((tmask >> i) & 1u) {
+        const uint32_t walk = (uint32_t)after[i] & 0xffffu;
+        to[whist[walk] + ((uint32_t)after[i] >> 16)] = ((uint32_t)pos << 16) | walk;
+        ++pos;
+      }
+  }
   __syncthreads();  // bits complete
   for (int w = tid; w < nwords; w += SORT_THREADS) firstbits[(size_t)col * wstride + w] = bits[w];
   if (tid == 0) {
@@ -354,7 +394,7 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
                         ColumnTables& tab, cudaStream_t stream) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
-  const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * (CAP / 32);
+  const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * ((CAP / 32 + 3) & ~3) + 4 * (size_t)CAP;
   const size_t pass_a = 2 * 2 * (size_t)SORT_THREADS * 8;  // two u16 buffers of 8 keys per thread
   const size_t smem = std::max(std::max(sizeof(typename Sort::TempStorage), post), pass_a);
   PipeConst pc;
@@ -366,7 +406,7 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
                                                         tab.trow, tab.trun, tab.tend, tab.nabits, tab.firstbits, tab.gstart,
-                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, pc);
+                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, tab.tord, pc);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -535,6 +575,8 @@ size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride) {
   return bytes;
 }
 
+bool columns_fused(int64_t n) { return n <= 8192 && !getenv("ICIKT_NO_FUSED_COLUMNS"); }
+
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
                    int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
                    unsigned char* scratch, cudaStream_t stream) {
@@ -545,7 +587,8 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   // words up to wstride were zeroed once when the plan was created
   // short columns: 512 threads (more CTAs per SM when there are many columns), else 1024
   if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
-  if (n <= 8192 && !getenv("ICIKT_NO_FUSED_COLUMNS")) {
+  tab.tord_valid = columns_fused(n) && tab.tord != nullptr;
+  if (tab.tord_valid) {
     int l;
 #define ICIKT_FUSED(T, I) l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream)
     if (n <= 512) ICIKT_FUSED(512, 1);

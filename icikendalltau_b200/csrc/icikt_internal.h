@@ -21,6 +21,9 @@ struct ColumnTables {
   uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1), | kLargeFlag
   uint16_t* tend = nullptr;       // [C][nstride] index in the tied-row list one past the row's group
                                   //              (= the row's own index for rows of large groups)
+  uint32_t* tord = nullptr;       // [C][nstride] tied-row list indices sorted by walk length (index << 16 | walk), longest first;
+                                  //              null for long columns (n > 8192), whose rows are walked in list order
+  bool tord_valid = false;        // set by launch_columns: the last run filled tord
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
   uint16_t* lgrp = nullptr;       // [C][kLargeStride] (start position, size) of every large tie group
@@ -86,6 +89,7 @@ struct ColumnWork {
   size_t cub_bytes = 0;
 };
 size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride);
+bool columns_fused(int64_t n);  // short columns: one kernel per column does everything (and writes tord)
 
 // K1: data (device, column-major, ld) -> tables.  Returns number of kernel launches or <0.
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,

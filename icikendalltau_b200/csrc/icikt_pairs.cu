@@ -402,6 +402,7 @@ template <bool G, bool RG>
 __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, const int m,
                                                     const uint16_t* __restrict__ trow,
                                                     const uint16_t* __restrict__ tend,
+                                                    const uint32_t* __restrict__ tord,
                                                     typename Mem<G>::ptr rank_tbl,
                                                     const uint16_t* __restrict__ rank_g, uint32_t& inv,
                                                     uint32_t& ties) {
@@ -425,6 +426,24 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
     }
   }
   __syncthreads();
+  if (tord) {
+    // K1's walk order: (list index << 16 | rows behind it in its group), longest walk first, so the
+    // lanes of a warp walk equally far
+    for (int i = tid; i < m; i += T) {
+      const uint32_t e = __ldg(tord + i);
+      const int walk = (int)(e & 0xffffu), k = (int)(e >> 16);
+      if (walk == 0) break;  // sorted: nothing but rows without a walk from here on
+      const uint32_t mine = M::ld16(M::add(keys, k << 1));
+#pragma unroll 4
+      for (int j = k + 1; j <= k + walk; ++j) {
+        const uint32_t other = M::ld16(M::add(keys, j << 1));
+        inv += (other < mine);
+        ties += (other == mine);
+      }
+    }
+    __syncthreads();
+    return;
+  }
   for (int k = tid; k < m; k += T) {
     const int end = tend[k];
     if (end <= k + 1) continue;
@@ -582,6 +601,7 @@ struct TiledParams {
   const uint16_t* trow;
   const uint16_t* trun;
   const uint16_t* tend;
+  const uint32_t* tord;  // may be null
   const uint32_t* nabits;
   const uint32_t* firstbits;
   const ColStats* stats;
@@ -796,7 +816,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       uint32_t accB = 0;
       if (m > 0 && !by_pass_b)  // keys: 2 m <= 2 cap bytes, the still empty sequence buffer
         small_groups_direct<G, RG>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tend + (size_t)xcol * p.nstride,
-                                   rank_tbl, rankY_g, accB, ties);
+                                   p.tord ? p.tord + (size_t)xcol * p.nstride : nullptr, rank_tbl, rankY_g, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
       if (f > 0) {
         if (PW && XS.n_na > 0)
@@ -1199,6 +1219,7 @@ TiledParams make_params(const PairLaunch& pl) {
   p.trow = t.trow;
   p.trun = t.trun;
   p.tend = t.tend;
+  p.tord = t.tord_valid ? t.tord : nullptr;
   p.nabits = t.nabits;
   p.firstbits = t.firstbits;
   p.stats = t.stats;
