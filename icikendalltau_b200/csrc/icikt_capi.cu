@@ -420,7 +420,7 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(dmalloc(&t.trow, ne));
   PCK(dmalloc(&t.trun, ne));
   PCK(dmalloc(&t.tend, ne));
-  if (columns_fused(n)) PCK(dmalloc(&t.tord, ne));
+  PCK(dmalloc(&t.tord, ne));
   PCK(dmalloc(&t.nabits, nw));
   PCK(dmalloc(&t.firstbits, nw));
   t.gstride = t.nstride + 64;

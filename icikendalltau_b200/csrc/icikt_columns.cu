@@ -417,11 +417,16 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        uint32_t* __restrict__ firstbits,
                        uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
                        uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
-                       int32_t* __restrict__ max_tied) {
+                       int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord,
+                       uint16_t* __restrict__ wrank_all) {
+  // rows compared directly walk less than 2048 steps: groups below kLargeTie rows, or larger ones
+  // whose squares sum to at most kDirectBudget * n
+  static_assert(kLargeTie <= 2048 && (long long)kDirectBudget * 65535LL < 2048LL * 2048LL, "walk classes");
   __shared__ int n_large;
   __shared__ int warp_sums[32];
   __shared__ long long llbuf[128];
   __shared__ uint32_t bits[2048];
+  __shared__ uint32_t whist[2048];
   const int col = blockIdx.x;
   const int tid = threadIdx.x;
   const unsigned long long* sk = skeys + (size_t)col * nstride;
@@ -530,6 +535,44 @@ __global__ void __launch_bounds__(RANK_THREADS)
     gcarry += gtotal;
   }
 
+  // walk order of the tied rows for the pair kernel's direct comparison (see column_fused_kernel):
+  // counting sort by walk length, longest first; the rank inside a class is parked in the sort's
+  // value buffer, which is free by now
+  if (carry > 0) {  // block-uniform
+    const int m = carry;
+    uint16_t* wr = wrank_all + (size_t)col * nstride;
+    uint32_t* to = tord + (size_t)col * nstride;
+    for (int w = tid; w < 2048; w += RANK_THREADS) whist[w] = 0;
+    __syncthreads();  // also: te[] above was written by other threads
+    for (int k = tid; k < m; k += RANK_THREADS) {
+      const int e = te[k];
+      const int walk = e > k ? e - k - 1 : 0;
+      wr[k] = (uint16_t)atomicAdd(&whist[walk], 1u);
+    }
+    __syncthreads();
+    {
+      constexpr int PER = 2048 / RANK_THREADS;
+      const int hi = 2047 - tid * PER;
+      int sum = 0;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) sum += (int)whist[hi - q];
+      int total;
+      int run = block_scan_excl(sum, warp_sums, total);
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int c = (int)whist[hi - q];
+        whist[hi - q] = (uint32_t)run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < m; k += RANK_THREADS) {
+      const int e = te[k];
+      const uint32_t walk = e > k ? (uint32_t)(e - k - 1) : 0u;
+      to[whist[walk] + wr[k]] = ((uint32_t)k << 16) | walk;
+    }
+  }
+
   if (tid == 0) {
     ColStats s;
     s.n_na = a;
@@ -587,8 +630,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   // words up to wstride were zeroed once when the plan was created
   // short columns: 512 threads (more CTAs per SM when there are many columns), else 1024
   if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
-  tab.tord_valid = columns_fused(n) && tab.tord != nullptr;
-  if (tab.tord_valid) {
+  if (columns_fused(n)) {
     int l;
 #define ICIKT_FUSED(T, I) l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream)
     if (n <= 512) ICIKT_FUSED(512, 1);
@@ -621,7 +663,8 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                        tab.trow, tab.trun, tab.tend, tab.firstbits,
-                                                       wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied);
+                                                       wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied,
+                                                       tab.tord, wk.vals_in);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
   }

@@ -20,10 +20,9 @@ struct ColumnTables {
   uint16_t* trow = nullptr;       // [C][nstride] rows of tied (non-first-group) elements, sorted order
   uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1), | kLargeFlag
   uint16_t* tend = nullptr;       // [C][nstride] index in the tied-row list one past the row's group
-                                  //              (= the row's own index for rows of large groups)
-  uint32_t* tord = nullptr;       // [C][nstride] tied-row list indices sorted by walk length (index << 16 | walk), longest first;
-                                  //              null for long columns (n > 8192), whose rows are walked in list order
-  bool tord_valid = false;        // set by launch_columns: the last run filled tord
+                                  //              (= the row's own index for rows of large groups); K1-internal since tord
+  uint32_t* tord = nullptr;       // [C][nstride] the tied-row list in walk order: (list index << 16 | rows behind it in its
+                                  //              group, 0 for rows of large groups), longest walk first
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing
   uint32_t* firstbits = nullptr;  // [C][wstride] bit r: row r belongs to the first group (size > 1)
   uint16_t* lgrp = nullptr;       // [C][kLargeStride] (start position, size) of every large tie group

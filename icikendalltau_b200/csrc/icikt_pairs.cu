@@ -391,17 +391,17 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
   return ties;
 }
 
-// Small tie groups of x (fewer than kLargeTie rows, other than the first): the inversions and the
-// joint ties inside each group by direct comparison.  `keys` receives the y ranks (u16) of all m
-// tied rows of x in x order; every thread takes a row and walks forward to the end of its group
-// (tend[], from K1; rows of large groups end at themselves and are skipped) -- the lanes of a warp
-// read consecutive keys.  One comparison for the usual isolated tie; K1 bounds the total (groups of
-// kLargeTie rows or more are only left to this routine while the sum of their size^2 stays below
-// kDirectBudget * n).
+// Small tie groups of x (other than the first; large groups of a column in large-group mode are
+// sorted in place instead): the inversions and the joint ties inside each group by direct
+// comparison.  `keys` receives the y ranks (u16) of all m tied rows of x in x order; every thread
+// takes a row and compares it with the rows behind it in its group.  The rows come in K1's walk
+// order -- (list index << 16 | rows behind it), longest walk first -- so that the lanes of a warp
+// walk equally far (in list order a group's rows walk t-1, t-2, ... 0 steps and half of the warp
+// idles).  One comparison for the usual isolated tie; K1 bounds the total (groups of kLargeTie rows
+// or more are only left to this routine while the sum of their size^2 stays below kDirectBudget * n).
 template <bool G, bool RG>
 __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, const int m,
                                                     const uint16_t* __restrict__ trow,
-                                                    const uint16_t* __restrict__ tend,
                                                     const uint32_t* __restrict__ tord,
                                                     typename Mem<G>::ptr rank_tbl,
                                                     const uint16_t* __restrict__ rank_g, uint32_t& inv,
@@ -426,30 +426,13 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
     }
   }
   __syncthreads();
-  if (tord) {
-    // K1's walk order: (list index << 16 | rows behind it in its group), longest walk first, so the
-    // lanes of a warp walk equally far
-    for (int i = tid; i < m; i += T) {
-      const uint32_t e = __ldg(tord + i);
-      const int walk = (int)(e & 0xffffu), k = (int)(e >> 16);
-      if (walk == 0) break;  // sorted: nothing but rows without a walk from here on
-      const uint32_t mine = M::ld16(M::add(keys, k << 1));
-#pragma unroll 4
-      for (int j = k + 1; j <= k + walk; ++j) {
-        const uint32_t other = M::ld16(M::add(keys, j << 1));
-        inv += (other < mine);
-        ties += (other == mine);
-      }
-    }
-    __syncthreads();
-    return;
-  }
-  for (int k = tid; k < m; k += T) {
-    const int end = tend[k];
-    if (end <= k + 1) continue;
+  for (int i = tid; i < m; i += T) {
+    const uint32_t e = __ldg(tord + i);
+    const int walk = (int)(e & 0xffffu), k = (int)(e >> 16);
+    if (walk == 0) break;  // sorted: nothing but rows without a walk from here on
     const uint32_t mine = M::ld16(M::add(keys, k << 1));
 #pragma unroll 4
-    for (int j = k + 1; j < end; ++j) {
+    for (int j = k + 1; j <= k + walk; ++j) {
       const uint32_t other = M::ld16(M::add(keys, j << 1));
       inv += (other < mine);
       ties += (other == mine);
@@ -600,8 +583,7 @@ struct TiledParams {
   const uint16_t* rank;
   const uint16_t* trow;
   const uint16_t* trun;
-  const uint16_t* tend;
-  const uint32_t* tord;  // may be null
+  const uint32_t* tord;
   const uint32_t* nabits;
   const uint32_t* firstbits;
   const ColStats* stats;
@@ -815,8 +797,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const bool by_pass_b = nlg > 0 && p.tier == 2 && (long long)nlg * YS.n_groups > p.budget;
       uint32_t accB = 0;
       if (m > 0 && !by_pass_b)  // keys: 2 m <= 2 cap bytes, the still empty sequence buffer
-        small_groups_direct<G, RG>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tend + (size_t)xcol * p.nstride,
-                                   p.tord ? p.tord + (size_t)xcol * p.nstride : nullptr, rank_tbl, rankY_g, accB, ties);
+        small_groups_direct<G, RG>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tord + (size_t)xcol * p.nstride,
+                                   rank_tbl, rankY_g, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
       if (f > 0) {
         if (PW && XS.n_na > 0)
@@ -1218,8 +1200,7 @@ TiledParams make_params(const PairLaunch& pl) {
   p.rank = t.rank;
   p.trow = t.trow;
   p.trun = t.trun;
-  p.tend = t.tend;
-  p.tord = t.tord_valid ? t.tord : nullptr;
+  p.tord = t.tord;
   p.nabits = t.nabits;
   p.firstbits = t.firstbits;
   p.stats = t.stats;
