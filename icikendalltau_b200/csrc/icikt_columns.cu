@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         uint16_t* __restrict__ trun, uint16_t* __restrict__ tend, uint32_t* __restrict__ nabits,
                         uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
                         uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
-                        int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord, const PipeConst pc) {
+                        int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord, const PipeConst pc,
+                        const int large_tie, const int direct_budget) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
@@ -231,10 +232,10 @@ __global__ void __launch_bounds__(SORT_THREADS)
   long long s2 = 0, s3 = 0, s5 = 0, ntied = 0, lsq = 0;
   for (int g = tid + 1; g < K; g += SORT_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
-    if (t >= kLargeTie) lsq += t * t;
+    if (t >= large_tie) lsq += t * t;
   }
   lsq = block_sum_ll(lsq, llbuf);
-  const int large_from = lsq > (long long)kDirectBudget * n ? kLargeTie : 0x7fffffff;
+  const int large_from = lsq > (long long)direct_budget * n ? large_tie : 0x7fffffff;
   for (int g = tid; g < K; g += SORT_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
     if (g > 0 && t >= large_from) {  // large tie group: also listed by (start position, size)
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 
 template <int SORT_THREADS, int ITEMS>
 int launch_column_fused(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na, int na_inf,
-                        ColumnTables& tab, cudaStream_t stream) {
+                        ColumnTables& tab, cudaStream_t stream, int large_tie, int direct_budget) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * ((CAP / 32 + 3) & ~3) + 4 * (size_t)CAP;
@@ -406,7 +407,7 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
                                                         tab.trow, tab.trun, tab.tend, tab.nabits, tab.firstbits, tab.gstart,
-                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, tab.tord, pc);
+                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, tab.tord, pc, large_tie, direct_budget);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -418,10 +419,9 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
                        uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
                        int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord,
-                       uint16_t* __restrict__ wrank_all) {
-  // rows compared directly walk less than 2048 steps: groups below kLargeTie rows, or larger ones
-  // whose squares sum to at most kDirectBudget * n
-  static_assert(kLargeTie <= 2048 && (long long)kDirectBudget * 65535LL < 2048LL * 2048LL, "walk classes");
+                       uint16_t* __restrict__ wrank_all, const int large_tie, const int direct_budget) {
+  // rows compared directly walk less than 2048 steps: groups below large_tie (<= 2048) rows, or larger
+  // ones whose squares sum to at most direct_budget (<= 63) * n (launch_columns clamps both)
   __shared__ int n_large;
   __shared__ int warp_sums[32];
   __shared__ long long llbuf[128];
@@ -476,10 +476,10 @@ __global__ void __launch_bounds__(RANK_THREADS)
   long long s2 = 0, s3 = 0, s5 = 0, ntied = 0, lsq = 0;
   for (int g = tid + 1; g < K; g += RANK_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
-    if (t >= kLargeTie) lsq += t * t;
+    if (t >= large_tie) lsq += t * t;
   }
   lsq = block_sum_ll(lsq, llbuf);
-  const long long large_from = lsq > (long long)kDirectBudget * n ? kLargeTie : 0x7fffffff;
+  const long long large_from = lsq > (long long)direct_budget * n ? large_tie : 0x7fffffff;
   for (int g = tid; g < K; g += RANK_THREADS) {
     const long long t = (long long)gpos[g + 1] - (long long)gpos[g];
     if (g > 0 && t >= large_from) {  // large tie group: also listed by (start position, size)
@@ -626,13 +626,18 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   const int n = (int)tab.n, C = (int)tab.C;
   const int nstride = (int)tab.nstride, wstride = (int)tab.wstride;
   int launches = 0;
+  // tie-group thresholds (icikt_common.cuh); the environment overrides are for tuning sweeps
+  int large_tie = kLargeTie, direct_budget = kDirectBudget;
+  if (const char* e = getenv("ICIKT_LARGE_TIE")) large_tie = std::min(2048, std::max(2, atoi(e)));
+  if (const char* e = getenv("ICIKT_DIRECT_BUDGET")) direct_budget = std::min(63, std::max(0, atoi(e)));
   // the bit arrays are written in full (words below n32/32) by the kernels below; the padding
   // words up to wstride were zeroed once when the plan was created
   // short columns: 512 threads (more CTAs per SM when there are many columns), else 1024
   if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
   if (columns_fused(n)) {
     int l;
-#define ICIKT_FUSED(T, I) l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream)
+#define ICIKT_FUSED(T, I) \
+  l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream, large_tie, direct_budget)
     if (n <= 512) ICIKT_FUSED(512, 1);
     else if (n <= 1024) ICIKT_FUSED(512, 2);
     else if (n <= 2048) ICIKT_FUSED(512, 4);
@@ -664,7 +669,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                        tab.trow, tab.trun, tab.tend, tab.firstbits,
                                                        wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied,
-                                                       tab.tord, wk.vals_in);
+                                                       tab.tord, wk.vals_in, large_tie, direct_budget);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
   }
