@@ -408,6 +408,9 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
                                                     uint32_t& ties) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, T = blockDim.x;
+  // the first walk-order entry is fetched before the key gather, later ones one step ahead: the
+  // global-load latency would otherwise sit between the barrier and the first comparison
+  uint32_t e = (tid < m) ? __ldg(tord + tid) : 0u;
   {  // eight rows per thread and step (the list is readable up to nstride, a multiple of 64)
     const uint4* tr8 = reinterpret_cast<const uint4*>(trow);
     for (int t8 = tid; t8 < ((m + 7) >> 3); t8 += T) {
@@ -427,7 +430,7 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
   }
   __syncthreads();
   for (int i = tid; i < m; i += T) {
-    const uint32_t e = __ldg(tord + i);
+    const uint32_t e_next = (i + T < m) ? __ldg(tord + i + T) : 0u;
     const int walk = (int)(e & 0xffffu), k = (int)(e >> 16);
     if (walk == 0) break;  // sorted: nothing but rows without a walk from here on
     const uint32_t mine = M::ld16(M::add(keys, k << 1));
@@ -437,6 +440,7 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
       inv += (other < mine);
       ties += (other == mine);
     }
+    e = e_next;
   }
   __syncthreads();
 }
