@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
     return LIB
 
