@@ -55,13 +55,15 @@ class Timings(ctypes.Structure):
                 ("reserved", ctypes.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return dict(h2d_ms=self.h2d_ms, columns_ms=self.columns_ms, pairs_ms=self.pairs_ms,
+                    epilogue_ms=self.epilogue_ms, d2h_ms=self.d2h_ms, total_ms=self.total_ms,
+                    n_launches=self.n_launches)
 
 
 _lib = None
-_dp = ctypes.POINTER(ctypes.c_double)
-_ip = ctypes.POINTER(ctypes.c_int32)
-_lp = ctypes.POINTER(ctypes.c_int64)
+# array arguments travel as plain addresses (void*): building typed ctypes pointers from NumPy
+# arrays costs microseconds each, which shows in the one-shot call on small matrices
+_dp = _ip = _lp = ctypes.c_void_p
 
 
 def load():
@@ -146,27 +148,23 @@ def check(rc):
 
 def make_opts(perspective="global", alternative="two.sided", continuity=False, include_diag=False,
               na_inf=False, device=0, kernel=KERNEL_TILED, want_counts=False, pair_lo=0, pair_hi=0):
-    o = Opts()
-    load().icikt_default_opts(ctypes.byref(o))
-    o.perspective = PERSPECTIVE.get(perspective, 0)   # any other string behaves as global
-    o.alternative = ALTERNATIVE.get(alternative, 3)   # unknown alternative: p-value stays 0
-    o.continuity = int(bool(continuity))
-    o.include_diag = int(bool(include_diag))
-    o.na_inf = int(bool(na_inf))
-    o.device = int(device)
-    o.kernel = int(kernel)
-    o.want_counts = int(bool(want_counts))
-    o.pair_lo, o.pair_hi = int(pair_lo), int(pair_hi)
-    return o
+    # same values as icikt_default_opts() for everything not given (all zero)
+    return Opts(PERSPECTIVE.get(perspective, 0),   # any other string behaves as global
+                ALTERNATIVE.get(alternative, 3),   # unknown alternative: p-value stays 0
+                int(bool(continuity)), int(bool(include_diag)), int(bool(na_inf)), int(device), int(kernel),
+                int(bool(want_counts)), int(pair_lo), int(pair_hi))
 
 
 def _global_na_array(global_na):
+    if len(global_na) == 0:
+        return None, None, 0
     g = np.ascontiguousarray(np.asarray(list(global_na), dtype=np.float64))
-    return g, (g.ctypes.data_as(_dp) if g.size else None), int(g.size)
+    return g, _ptr(g), int(g.size)
 
 
-def _ptr(a, t):
-    return a.ctypes.data_as(t) if a is not None else None
+def _ptr(a, t=None):
+    """address of a NumPy array's buffer (None -> NULL); `t` names the element type for the reader"""
+    return a.__array_interface__["data"][0] if a is not None else None
 
 
 def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, devices=None, **opt_kw):
@@ -191,26 +189,28 @@ def run_pairs(data, global_na=(), pi=None, pj=None, want_counts=False, devices=N
         pi = np.ascontiguousarray(pi, dtype=np.int32)
         pj = np.ascontiguousarray(pj, dtype=np.int32)
         P = int(pi.size)
-    raw, pv, tm, comp = (np.empty(max(P, 0), dtype=np.float64) for _ in range(4))
-    status = np.empty(max(P, 0), dtype=np.int32)
-    counts = np.empty((max(P, 0), NCOUNTS), dtype=np.int64) if want_counts else None
+    # the five result arrays are views of one allocation: one address lookup instead of five
+    P = max(P, 0)
+    buf = np.empty(4 * P + (P + 1) // 2, dtype=np.float64)
+    raw, pv, tm, comp = buf[:P], buf[P:2 * P], buf[2 * P:3 * P], buf[3 * P:4 * P]
+    status = buf[4 * P:].view(np.int32)[:P]
+    counts = np.empty((P, NCOUNTS), dtype=np.int64) if want_counts else None
+    a_raw = _ptr(buf)
+    a_pv, a_tm, a_comp, a_status = a_raw + 8 * P, a_raw + 16 * P, a_raw + 24 * P, a_raw + 32 * P
     mx = ctypes.c_double(float("nan"))
     t = Timings()
     g, gp, ng = _global_na_array(global_na)
     if pi is None and devices is not None:
         dev = np.ascontiguousarray(list(devices), dtype=np.int32)
         rc = L.icikt_all_pairs_multi(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), _ptr(dev, _ip),
-                                     int(dev.size), _ptr(raw, _dp), _ptr(pv, _dp), _ptr(tm, _dp),
-                                     _ptr(comp, _dp), _ptr(status, _ip), _ptr(counts, _lp),
+                                     int(dev.size), a_raw, a_pv, a_tm, a_comp, a_status, _ptr(counts, _lp),
                                      ctypes.byref(mx), ctypes.byref(t))
     elif pi is None:
-        rc = L.icikt_all_pairs(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), _ptr(raw, _dp),
-                               _ptr(pv, _dp), _ptr(tm, _dp), _ptr(comp, _dp), _ptr(status, _ip),
-                               _ptr(counts, _lp), ctypes.byref(mx), ctypes.byref(t))
+        rc = L.icikt_all_pairs(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), a_raw, a_pv, a_tm, a_comp,
+                               a_status, _ptr(counts, _lp), ctypes.byref(mx), ctypes.byref(t))
     else:
         rc = L.icikt_pair_list(_ptr(data, _dp), n, C, n, gp, ng, _ptr(pi, _ip), _ptr(pj, _ip), P,
-                               ctypes.byref(o), _ptr(raw, _dp), _ptr(pv, _dp), _ptr(tm, _dp),
-                               _ptr(comp, _dp), _ptr(status, _ip), _ptr(counts, _lp),
+                               ctypes.byref(o), a_raw, a_pv, a_tm, a_comp, a_status, _ptr(counts, _lp),
                                ctypes.byref(mx), ctypes.byref(t))
     check(rc)
     out = dict(raw=raw, pvalue=pv, taumax=tm, completeness=comp, status=status,
