@@ -330,9 +330,10 @@ class HostBarrier {
   int n_, count_ = 0, gen_ = 0;
 };
 
+// elapsed time between two completed events; 0 if one of them was never recorded
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, a, b);
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) ms = 0.f;
   return ms;
 }
 
@@ -785,13 +786,13 @@ int icikt_plan_timings(icikt_plan* p, icikt_timings* t) {
   const int launches = (p->tm.n_launches & 0xffff) + (p->tm.n_launches >> 16);
   std::memset(t, 0, sizeof(*t));
   t->n_launches = launches;
-  if (cudaEventQuery(p->ev[1]) == cudaSuccess) t->h2d_ms = ev_ms(p->ev[0], p->ev[1]);
-  if (cudaEventQuery(p->ev[3]) == cudaSuccess) t->columns_ms = ev_ms(p->ev[2], p->ev[3]);
-  if (cudaEventQuery(p->ev[8]) == cudaSuccess) t->pairs_ms = ev_ms(p->ev[4], p->ev[8]);
-  if (cudaEventQuery(p->ev[5]) == cudaSuccess) t->epilogue_ms = ev_ms(p->ev[8], p->ev[5]);
-  if (cudaEventQuery(p->ev[7]) == cudaSuccess) t->d2h_ms = ev_ms(p->ev[6], p->ev[7]);
-  if (cudaEventQuery(p->ev[0]) == cudaSuccess && cudaEventQuery(p->ev[7]) == cudaSuccess)
-    t->total_ms = ev_ms(p->ev[0], p->ev[7]);
+  // the stream is idle, so every recorded event has completed
+  t->h2d_ms = ev_ms(p->ev[0], p->ev[1]);
+  t->columns_ms = ev_ms(p->ev[2], p->ev[3]);
+  t->pairs_ms = ev_ms(p->ev[4], p->ev[8]);
+  t->epilogue_ms = ev_ms(p->ev[8], p->ev[5]);
+  t->d2h_ms = ev_ms(p->ev[6], p->ev[7]);
+  t->total_ms = ev_ms(p->ev[0], p->ev[7]);
   cudaGetLastError();
   return ICIKT_OK;
 }
