@@ -80,6 +80,12 @@ struct Mem<false> {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(p) : "memory");
     return v;
   }
+  // 16-bit load zero-extended straight into a 32-bit register (no conversion afterwards)
+  static __device__ __forceinline__ uint32_t ld16w(ptr p) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(p) : "memory");
+    return v;
+  }
   static __device__ __forceinline__ uint32_t ld32(ptr p) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p) : "memory");
@@ -178,6 +184,7 @@ struct Mem<true> {
   typedef unsigned char* ptr;
   static __device__ __forceinline__ ptr add(ptr p, int32_t bytes) { return p + bytes; }
   static __device__ __forceinline__ uint32_t ld16(ptr p) { return *reinterpret_cast<const unsigned short*>(p); }
+  static __device__ __forceinline__ uint32_t ld16w(ptr p) { return *reinterpret_cast<const unsigned short*>(p); }
   static __device__ __forceinline__ uint32_t ld32(ptr p) { return *reinterpret_cast<const uint32_t*>(p); }
   static __device__ __forceinline__ void ld128(ptr p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     const uint4 v = *reinterpret_cast<const uint4*>(p);

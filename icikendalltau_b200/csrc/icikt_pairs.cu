@@ -433,13 +433,19 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
     const uint32_t e_next = (i + T < m) ? __ldg(tord + i + T) : 0u;
     const int walk = (int)(e & 0xffffu), k = (int)(e >> 16);
     if (walk == 0) break;  // sorted: nothing but rows without a walk from here on
-    const uint32_t mine = M::ld16(M::add(keys, k << 1));
+    // sign bits instead of compare-and-select: (mine - 1 - other) is negative iff other >= mine,
+    // (other - mine - 1) iff other <= mine (16-bit keys); one add and one shift-add each
+    const uint32_t mine = M::ld16w(M::add(keys, k << 1));
+    const uint32_t m1 = mine - 1u, nm = ~mine;
+    uint32_t ge = 0, le = 0;
 #pragma unroll 4
     for (int j = k + 1; j <= k + walk; ++j) {
-      const uint32_t other = M::ld16(M::add(keys, j << 1));
-      inv += (other < mine);
-      ties += (other == mine);
+      const uint32_t other = M::ld16w(M::add(keys, j << 1));
+      ge += (m1 - other) >> 31;
+      le += (other + nm) >> 31;
     }
+    inv += (uint32_t)walk - ge;        // other < mine
+    ties += ge + le - (uint32_t)walk;  // other == mine
     e = e_next;
   }
   __syncthreads();
