@@ -107,3 +107,37 @@ def test_setup_missing_matrix_matches_oracle():
     x[5, 1] = -2.0
     for g in ((np.nan, np.inf, 0), (np.nan,), (0,), (np.nan, np.inf, -2), ()):
         assert np.array_equal(api.setup_missing_matrix(x, g), O.setup_missing_matrix(x, g))
+
+
+def test_run_pairs_result_views_match_the_addresses_handed_to_the_library(monkeypatch):
+    """run_pairs hands the library plain addresses into ONE result allocation; the arrays it
+    returns must be exactly those ranges (checked with a stand-in that writes through them)."""
+    import ctypes
+    real = _lib.load()
+    seen = {}
+
+    def fake_all_pairs(data, n, C, ld, gna, ngna, opts, raw, pv, tm, comp, status, counts, mx, timings):
+        P = C * (C - 1) // 2
+        seen.update(n=n, C=C, ld=ld, ngna=ngna, gna=gna)
+        for k, addr in enumerate((raw, pv, tm, comp)):
+            (ctypes.c_double * P).from_address(addr)[:] = [100.0 * k + i for i in range(P)]
+        (ctypes.c_int32 * P).from_address(status)[:] = list(range(P))
+        assert counts is None
+        return 0
+
+    class Stub:
+        icikt_all_pairs = staticmethod(fake_all_pairs)
+
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+    monkeypatch.setattr(_lib, "_lib", Stub())
+    x = np.asfortranarray(np.arange(35, dtype=np.float64).reshape(5, 7))
+    r = _lib.run_pairs(x, (), perspective="local")
+    P = 21
+    for k, name in enumerate(("raw", "pvalue", "taumax", "completeness")):
+        assert r[name].dtype == np.float64 and r[name].shape == (P,)
+        assert np.array_equal(r[name], 100.0 * k + np.arange(P)), name
+    assert r["status"].dtype == np.int32 and np.array_equal(r["status"], np.arange(P))
+    assert (seen["n"], seen["C"], seen["ld"], seen["ngna"], seen["gna"]) == (5, 7, 5, 0, None)
+    r["status"][3] = 0  # the views are writable (kt_fast clears status 9 in place)
