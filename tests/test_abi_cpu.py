@@ -141,3 +141,52 @@ def test_run_pairs_result_views_match_the_addresses_handed_to_the_library(monkey
     assert r["status"].dtype == np.int32 and np.array_equal(r["status"], np.arange(P))
     assert (seen["n"], seen["C"], seen["ld"], seen["ngna"], seen["gna"]) == (5, 7, 5, 0, None)
     r["status"][3] = 0  # the views are writable (kt_fast clears status 9 in place)
+
+
+def test_ici_kendalltau_matrix_path_host_logic(monkeypatch):
+    """ici_kendalltau(return_matrix=True) hands scale_and_reshape to icikt_matrices: what the host
+    layer passes (n_good of setup_missing_matrix, diag_good, scale_max, the include_only pair list)
+    and what it does with the answer (warnings from the status counts, keep, names)."""
+    import ctypes
+    import warnings
+    real = _lib.load()
+    calls = []
+
+    def fake_matrices(data, n, C, ld, gna, ngna, pi, pj, P, opts, scale_max, diag_good, n_good, cor, raw, pv, tm,
+                      comp, hist, mx, timings):
+        ng = list((ctypes.c_int32 * C).from_address(n_good)) if n_good else None
+        pairs = None
+        if pi:
+            pairs = list(zip((ctypes.c_int32 * P).from_address(pi), (ctypes.c_int32 * P).from_address(pj)))
+        calls.append(dict(n=n, C=C, scale_max=scale_max, diag_good=diag_good, n_good=ng, pairs=pairs,
+                          literals=list((ctypes.c_double * ngna).from_address(gna)) if ngna else []))
+        for k, addr in enumerate((cor, raw, pv, tm, comp)):
+            (ctypes.c_double * (C * C)).from_address(addr)[:] = [float(k)] * (C * C)
+        counts = (ctypes.c_int64 * _lib.NSTATUS).from_address(hist)
+        counts[0], counts[3] = C * (C - 1) // 2 - 2, 2  # two pairs with a single unique value
+        return 0
+
+    class Stub:
+        icikt_matrices = staticmethod(fake_matrices)
+
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+    monkeypatch.setattr(_lib, "_lib", Stub())
+    x = np.array([[1.0, 0.0, 3.0], [2.0, 5.0, np.nan], [0.0, 6.0, 7.0], [4.0, np.inf, 8.0]])
+    names = ["a", "b", "c"]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        out = ik.ici_kendalltau(x, colnames=names, scale_max=False, diag_good=True)
+    assert any("single unique value" in str(v.message) and "2 pairs" in str(v.message) for v in w)
+    c = calls[-1]
+    assert (c["n"], c["C"], c["scale_max"], c["diag_good"], c["pairs"]) == (4, 3, 0, 1, None)
+    assert c["n_good"] == [3, 2, 3]  # zeros, NaN and Inf are missing by default (R/utils.R:1-23)
+    assert sorted(v for v in c["literals"] if v == v and abs(v) != np.inf) == [0.0]
+    assert out["raw"].shape == (3, 3) and np.all(out["cor"] == 0.0) and np.all(out["completeness"] == 4.0)
+    assert out["keep"].shape == (3, 4) and out["keep"].sum() == 8 and out["names"] == names
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ik.ici_kendalltau(x, colnames=names, include_only="b", diag_good=False)
+    c = calls[-1]
+    assert c["diag_good"] == 0 and sorted(c["pairs"]) == [(0, 1), (1, 1), (1, 2)]
