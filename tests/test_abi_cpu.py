@@ -190,3 +190,54 @@ def test_ici_kendalltau_matrix_path_host_logic(monkeypatch):
         ik.ici_kendalltau(x, colnames=names, include_only="b", diag_good=False)
     c = calls[-1]
     assert c["diag_good"] == 0 and sorted(c["pairs"]) == [(0, 1), (1, 1), (1, 2)]
+
+
+def test_kt_fast_pairwise_host_logic(monkeypatch):
+    """kt_fast(use = "pairwise.complete.obs") on data with missing values: one all-pairs call in
+    the complete-observations mode; pairs the device flags with status 9 are filtered on the host
+    (R/kendalltau.R:323-331) and re-run as two-column problems."""
+    import ctypes
+    real = _lib.load()
+    log = []
+
+    def fake_all_pairs(data, n, C, ld, gna, ngna, opts, raw, pv, tm, comp, status, counts, mx, timings):
+        o = ctypes.cast(opts, ctypes.POINTER(_lib.Opts)).contents
+        P = C * (C - 1) // 2 + (C if o.include_diag else 0)
+        log.append(("all", n, C, o.perspective, o.include_diag, P))
+        (ctypes.c_double * P).from_address(raw)[:] = [0.5] * P
+        (ctypes.c_double * P).from_address(pv)[:] = [0.25] * P
+        st = (ctypes.c_int32 * P).from_address(status)
+        st[:] = [0] * P
+        st[1] = 9  # pair (0, 2): not supported on the device
+        return 0
+
+    def fake_pair_list(data, n, C, ld, gna, ngna, pi, pj, P, opts, raw, pv, tm, comp, status, counts, mx, timings):
+        o = ctypes.cast(opts, ctypes.POINTER(_lib.Opts)).contents
+        rows = np.ctypeslib.as_array((ctypes.c_double * (n * C)).from_address(data)).reshape(C, n).T.copy()
+        log.append(("list", n, C, o.perspective, rows))
+        (ctypes.c_double * P).from_address(raw)[:] = [-1.0] * P
+        (ctypes.c_double * P).from_address(pv)[:] = [0.75] * P
+        (ctypes.c_int32 * P).from_address(status)[:] = [0] * P
+        return 0
+
+    class Stub:
+        icikt_all_pairs = staticmethod(fake_all_pairs)
+        icikt_pair_list = staticmethod(fake_pair_list)
+
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+    monkeypatch.setattr(_lib, "_lib", Stub())
+    x = np.array([[1.0, 4.0, 9.0], [2.0, np.nan, 8.0], [3.0, 6.0, np.nan], [5.0, 7.0, 6.0], [np.nan, 1.0, 5.0]])
+    out = ik.kt_fast(x, use="pairwise.complete.obs", colnames=["a", "b", "c"], return_matrix=False)
+    assert log[0] == ("all", 5, 3, _lib.PERSPECTIVE["complete"], 1, 6)
+    kind, n, C, persp, rows = log[1]
+    assert (kind, n, C, persp) == ("list", 3, 2, _lib.PERSPECTIVE["local"])  # rows present in both a and c
+    assert np.array_equal(rows, np.array([[1.0, 9.0], [2.0, 8.0], [5.0, 6.0]]))
+    tau = out["tau"]
+    assert list(tau["s1"]) == ["a", "a", "b", "a", "b", "c"] and list(tau["s2"]) == ["b", "c", "c", "a", "b", "c"]
+    assert list(tau["tau"]) == [0.5, -1.0, 0.5, 0.5, 0.5, 0.5] and tau["pvalue"][1] == 0.75
+    # no missing value: the plain local perspective is enough
+    log.clear()
+    ik.kt_fast(np.nan_to_num(x, nan=0.5), use="pairwise.complete.obs", colnames=["a", "b", "c"])
+    assert log[0][3] == _lib.PERSPECTIVE["local"] and len(log) == 1
