@@ -29,7 +29,8 @@ EXPORTS = [
     "icikt_plan_column_info", "icikt_plan_stream", "icikt_plan_timings", "icikt_plan_destroy",
     "icikt_pnorm_device", "icikt_release_workspace", "icikt_measure_smem_bandwidth",
     "icikt_pair_from_index", "icikt_all_pairs_multi", "icikt_matrices", "icikt_plan_download_matrices",
-    "icikt_pairwise_completeness",
+    "icikt_pairwise_completeness", "icikt_plan_upload_columns", "icikt_plan_columns_range",
+    "icikt_plan_tables", "icikt_plan_columns_finish",
 ]
 NSTATUS = 10
 
@@ -59,6 +60,12 @@ class Timings(ctypes.Structure):
                     epilogue_ms=self.epilogue_ms, d2h_ms=self.d2h_ms, total_ms=self.total_ms,
                     n_launches=self.n_launches)
 
+
+class Table(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("bytes_per_column", ctypes.c_int64)]
+
+
+MAX_TABLES = 16
 
 _lib = None
 # array arguments travel as plain addresses (void*): building typed ctypes pointers from NumPy
@@ -104,6 +111,14 @@ def load():
     L.icikt_plan_set_device_matrix.restype = ctypes.c_int
     L.icikt_plan_columns.argtypes = [vp, _dp, ctypes.c_int32]
     L.icikt_plan_columns.restype = ctypes.c_int
+    L.icikt_plan_upload_columns.argtypes = [vp, _dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]
+    L.icikt_plan_upload_columns.restype = ctypes.c_int
+    L.icikt_plan_columns_range.argtypes = [vp, _dp, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64]
+    L.icikt_plan_columns_range.restype = ctypes.c_int
+    L.icikt_plan_tables.argtypes = [vp, ctypes.POINTER(Table), ctypes.c_int32]
+    L.icikt_plan_tables.restype = ctypes.c_int
+    L.icikt_plan_columns_finish.argtypes = [vp]
+    L.icikt_plan_columns_finish.restype = ctypes.c_int
     L.icikt_plan_pairs.argtypes = [vp]
     L.icikt_plan_pairs.restype = ctypes.c_int
     L.icikt_plan_sync.argtypes = [vp]
@@ -306,6 +321,28 @@ class Plan:
     def columns(self, global_na=()):
         g, gp, ng = _global_na_array(global_na)
         check(self._L.icikt_plan_columns(self._h, gp, ng))
+
+    # ---- sharded K1 (one rank per GPU): upload + preprocess a slice of the columns, exchange the
+    # table slices (sharding.exchange_tables), then columns_finish() releases pairs()
+    def upload_columns(self, data, col_lo, col_hi):
+        """`data` is the whole (n, C) Fortran-ordered host matrix; only the slice is copied."""
+        assert data.flags["F_CONTIGUOUS"] and data.dtype == np.float64 and data.shape == (self.n, self.C)
+        check(self._L.icikt_plan_upload_columns(self._h, _ptr(data, _dp), self.n, int(col_lo), int(col_hi)))
+
+    def columns_range(self, global_na, col_lo, col_hi):
+        g, gp, ng = _global_na_array(global_na)
+        check(self._L.icikt_plan_columns_range(self._h, gp, ng, int(col_lo), int(col_hi)))
+
+    def tables(self):
+        """[(device pointer of column 0, bytes per column)] of the per-column tables to exchange."""
+        arr = (Table * MAX_TABLES)()
+        n = self._L.icikt_plan_tables(self._h, arr, MAX_TABLES)
+        if n < 0:
+            check(n)
+        return [(int(arr[k].ptr), int(arr[k].bytes_per_column)) for k in range(n)]
+
+    def columns_finish(self):
+        check(self._L.icikt_plan_columns_finish(self._h))
 
     def pairs(self):
         check(self._L.icikt_plan_pairs(self._h))

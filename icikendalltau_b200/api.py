@@ -60,10 +60,6 @@ def _warn_status_counts(counts):
             warnings.warn(text if cnt == 1 else f"{text} ({cnt} pairs)", RuntimeWarning, stacklevel=3)
 
 
-def _arg_name(default):
-    return default
-
-
 def _colnames_of(x, colnames, arg):
     """check_if_colnames_null + transform_to_matrix + check_if_numeric (R/utils.R:25-66)."""
     names = colnames
@@ -126,6 +122,11 @@ def setup_comparisons(samples, include_only=None, diag_good=True, include_arg="i
             pass
         if isinstance(include_only, dict):
             include_only = list(include_only.values())
+        # a list mixing scalars and vectors, the documented list(g1 = "s1", g2 = c("s2", "s3")) form
+        # (R/kendalltau.R:86-91): scalars are vectors of length one and paste0 recycles them
+        if isinstance(include_only, (list, tuple)) and \
+                any(isinstance(v, (list, tuple, np.ndarray)) for v in include_only):
+            include_only = [list(v) if isinstance(v, (list, tuple, np.ndarray)) else [v] for v in include_only]
         is_list_of_vectors = isinstance(include_only, (list, tuple)) and len(include_only) > 0 and \
             all(isinstance(v, (list, tuple, np.ndarray)) for v in include_only)
         if is_list_of_vectors:

@@ -302,9 +302,11 @@ int upload_columns(icikt_plan* p, const double* data, int64_t ld, int64_t c_lo, 
     CK(cudaMemcpy2DAsync(p->d_data_own + (size_t)c_lo * p->n, sizeof(double) * p->n, data + (size_t)c_lo * ld,
                          sizeof(double) * ld, sizeof(double) * p->n, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice,
                          p->stream));
+  CK(cudaEventRecord(p->ev[1], p->stream));
   p->d_data = p->d_data_own;
   p->ld = p->n;
   p->columns_done = false;
+  p->pairs_done = false;
   return ICIKT_OK;
 }
 
@@ -506,15 +508,20 @@ int icikt_plan_set_device_matrix(icikt_plan* p, const double* d_data, int64_t ld
   p->d_data = d_data;
   p->ld = ld;
   p->columns_done = false;
+  p->pairs_done = false;
   CK(cudaSetDevice(p->device));
   CK(cudaEventRecord(p->ev[0], p->stream));
   CK(cudaEventRecord(p->ev[1], p->stream));
   return ICIKT_OK;
 }
 
-int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_na) {
+// K1 over columns [col_lo, col_hi); `finish`: the statistics of every column are in place afterwards
+// (a full run), so the pair kernel may be launched
+static int plan_columns_impl(icikt_plan* p, const double* global_na, int32_t n_global_na, int64_t col_lo,
+                             int64_t col_hi, bool finish) {
   if (!p || !p->d_data) return fail(ICIKT_ERR_BAD_ARG, "no matrix set on the plan");
   if (n_global_na < 0 || (n_global_na > 0 && !global_na)) return fail(ICIKT_ERR_BAD_ARG, "bad global_na");
+  if (col_lo < 0 || col_hi > p->C || col_lo > col_hi) return fail(ICIKT_ERR_BAD_ARG, "column range out of bounds");
   CK(cudaSetDevice(p->device));
   // R/utils.R:6-15: NA and Inf entries of global_na select classes, the rest are literals
   double lit[64];
@@ -537,23 +544,77 @@ int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_
   const TiledShape& worst = p->shape_heavy;
   const int slot_bytes = std::max(worst.region_bytes, worst.const_region_bytes);
   const int slot_ctas = std::max(std::max(worst.max_ctas, p->shape.max_ctas), std::max(p->shape_mid.max_ctas, p->n_sm * 2));
-  if ((worst.gmem || worst.const_gmem) && !p->d_scratch) {
-    p->scratch_bytes = (size_t)slot_ctas * (size_t)slot_bytes;
-    CK(cudaMalloc(reinterpret_cast<void**>(&p->d_scratch), p->scratch_bytes));
+  const bool any_gmem = worst.gmem || worst.const_gmem || p->shape.gmem || p->shape_mid.gmem;
+  const size_t need = (size_t)slot_ctas * (size_t)slot_bytes;
+  if (any_gmem && need > p->scratch_bytes) {
+    // the shape depends on the perspective class and on tuning knobs in the environment, so a cached
+    // plan may need a larger scratch than the one it was given first
+    CK(cudaStreamSynchronize(p->stream));
+    if (p->d_scratch) { cudaFree(p->d_scratch); p->d_scratch = nullptr; p->scratch_bytes = 0; }
+    if (cudaMalloc(reinterpret_cast<void**>(&p->d_scratch), need) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ICIKT_ERR_ALLOC, "device allocation of the pair kernel's global scratch failed");
+    }
+    p->scratch_bytes = need;
   }
   for (TiledShape* sh : {&p->shape, &p->shape_mid, &p->shape_heavy}) {
     sh->scratch_stride = p->d_scratch ? slot_bytes : 0;
-    sh->scratch_ctas = p->d_scratch ? slot_ctas : 0;
+    sh->scratch_ctas = p->d_scratch ? (int)std::min<size_t>((size_t)slot_ctas, p->scratch_bytes / (size_t)slot_bytes) : 0;
   }
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
-                               p->d_scratch, p->stream);
+                               p->d_scratch, p->stream, col_lo, col_hi);
   if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
   CK(cudaEventRecord(p->ev[3], p->stream));
   // no synchronisation: `lit` is pageable host memory, so the copy above was staged before
   // cudaMemcpyAsync returned
   p->tm.n_launches = l;
+  p->columns_done = finish;
+  p->pairs_done = false;
+  return ICIKT_OK;
+}
+
+int icikt_plan_columns(icikt_plan* p, const double* global_na, int32_t n_global_na) {
+  if (!p) return fail(ICIKT_ERR_BAD_ARG, "plan is NULL");
+  return plan_columns_impl(p, global_na, n_global_na, 0, p->C, true);
+}
+
+int icikt_plan_columns_range(icikt_plan* p, const double* global_na, int32_t n_global_na, int64_t col_lo,
+                             int64_t col_hi) {
+  if (!p) return fail(ICIKT_ERR_BAD_ARG, "plan is NULL");
+  return plan_columns_impl(p, global_na, n_global_na, col_lo, col_hi, false);
+}
+
+int icikt_plan_columns_finish(icikt_plan* p) {
+  if (!p || !p->d_data) return fail(ICIKT_ERR_BAD_ARG, "no matrix set on the plan");
+  CK(cudaSetDevice(p->device));
+  const int l = launch_max_tied(p->tab, p->stream);
+  if (l < 0) return cuda_fail(cudaGetLastError(), "tier maxima kernel");
+  CK(cudaEventRecord(p->ev[3], p->stream));  // the exchange of the tables counts as column time
+  p->tm.n_launches += l;
   p->columns_done = true;
   return ICIKT_OK;
+}
+
+int icikt_plan_upload_columns(icikt_plan* p, const double* data, int64_t ld, int64_t col_lo, int64_t col_hi) {
+  if (!p || !data || ld < p->n || col_lo < 0 || col_hi > p->C || col_lo > col_hi)
+    return fail(ICIKT_ERR_BAD_ARG, "bad upload arguments");
+  return upload_columns(p, data, ld, col_lo, col_hi);
+}
+
+int icikt_plan_tables(icikt_plan* p, icikt_table* out, int32_t cap) {
+  if (!p) return fail(ICIKT_ERR_BAD_ARG, "plan is NULL");
+  const ColumnTables& t = p->tab;
+  const bool complete = p->opts.perspective == ICIKT_PERSPECTIVE_COMPLETE;
+  const icikt_table all[] = {
+      {t.perm, (int64_t)(2 * t.nstride)},       {t.rank, (int64_t)(2 * t.nstride)},
+      {t.trow, (int64_t)(2 * t.nstride)},       {t.trun, (int64_t)(2 * t.nstride)},
+      {t.tord, (int64_t)(4 * t.nstride)},       {t.nabits, (int64_t)(4 * t.wstride)},
+      {t.firstbits, (int64_t)(4 * t.wstride)},  {t.lgrp, (int64_t)(2 * kLargeStride)},
+      {t.stats, (int64_t)sizeof(ColStats)},     {t.gstart, (int64_t)(2 * t.gstride)},
+  };
+  const int n_all = (int)(sizeof(all) / sizeof(all[0])) - (complete ? 0 : 1);  // gstart: that mode only
+  for (int k = 0; k < n_all && out && k < cap; ++k) out[k] = all[k];
+  return n_all;
 }
 
 int icikt_plan_pairs(icikt_plan* p) {
@@ -685,14 +746,13 @@ int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_
   CK(cudaSetDevice(p->device));
   const size_t C = (size_t)p->C, cc = C * C;
   double* outs[5] = {cor, raw, pvalue, taumax, completeness};
-  if (!p->d_mat) {
-    if (dmalloc(&p->d_mat, 5 * cc) != cudaSuccess) {
-      cudaGetLastError();
-      return fail(ICIKT_ERR_ALLOC, "device allocation of the result matrices failed");
-    }
-    CK(dmalloc(&p->d_hist, 16));
-    CK(dmalloc(&p->d_ngood, C));
+  if (!p->d_mat && dmalloc(&p->d_mat, 5 * cc) != cudaSuccess) {
+    cudaGetLastError();
+    p->d_mat = nullptr;
+    return fail(ICIKT_ERR_ALLOC, "device allocation of the result matrices failed");
   }
+  if (!p->d_hist) CK(dmalloc(&p->d_hist, 16));
+  if (!p->d_ngood) CK(dmalloc(&p->d_ngood, C));
   CK(cudaEventRecord(p->ev[6], p->stream));
   // entries no pair writes stay 0 (R/kendalltau.R:389-396 start from matrix(0, ...)); with every pair
   // and the diagonal present nothing needs clearing
@@ -1005,10 +1065,11 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
   base.want_counts = counts ? 1 : 0;
   const int64_t ptot = tri_pairs(C) + (base.include_diag ? C : 0);
   std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached plans are not re-entrant
-  // Input distribution: if every pair of devices can reach each other directly (NVLink /
-  // NVSwitch), each device uploads only its slice of the columns over its own PCIe link and pulls
-  // the other slices from its peers (an all-gather of the matrix by peer copies); otherwise every
-  // device uploads the whole matrix.
+  // Sharded preprocessing: if every pair of devices can reach each other directly (NVLink /
+  // NVSwitch), device k uploads only its slice of the columns over its own PCIe link, runs K1 on
+  // that slice and pulls the other slices of the per-column TABLES from its peers (an all-gather
+  // by peer copies: K1 is not replicated and the raw matrix never travels between devices);
+  // otherwise every device uploads the whole matrix and preprocesses all columns.
   bool gather = n_devices >= 2 && C >= n_devices && ptot >= n_devices && !std::getenv("ICIKT_NO_PEER_GATHER");
   for (int a = 0; gather && a < n_devices; ++a)
     for (int b = 0; gather && b < n_devices; ++b) {
@@ -1019,7 +1080,7 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
     }
   cudaGetLastError();
   HostBarrier barrier(n_devices);
-  std::vector<double*> dev_matrix((size_t)n_devices, nullptr);
+  std::vector<icikt_plan*> peer_plan((size_t)n_devices, nullptr);
   struct Work {
     int rc = ICIKT_OK;
     std::string err;
@@ -1036,7 +1097,6 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
       o.pair_lo = ptot * k / n_devices;  // contiguous slices that differ by at most one pair
       o.pair_hi = ptot * (k + 1) / n_devices;
       const int64_t lo = o.pair_lo, cnt = o.pair_hi - o.pair_lo;
-      if (cnt <= 0) return;
       // one cached plan per slot, like the one-shot entry points: repeated calls of the same
       // shape do not pay the device allocations again
       icikt_plan*& slot = g_cached_multi[k];
@@ -1053,35 +1113,45 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
         if (w.rc == ICIKT_OK) slot = p;
       }
       if (!gather) {
+        if (cnt <= 0) return;
         if (w.rc == ICIKT_OK) w.rc = icikt_plan_upload(p, data, ld);
+        if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns(p, global_na, n_global_na);
       } else {
         // every worker passes both barriers whatever happened to it, so nobody is left waiting
         const auto col_lo = [&](int j) { return C * j / n_devices; };
         if (w.rc == ICIKT_OK) w.rc = upload_columns(p, data, ld, col_lo(k), col_lo(k + 1));
-        if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "slice upload");
-        dev_matrix[(size_t)k] = (w.rc == ICIKT_OK) ? p->d_data_own : nullptr;
-        barrier.wait();  // all slices are on their devices
+        if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns_range(p, global_na, n_global_na, col_lo(k), col_lo(k + 1));
+        if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "column slice");
+        peer_plan[(size_t)k] = (w.rc == ICIKT_OK) ? p : nullptr;
+        barrier.wait();  // every slice of the tables is complete on its device
         bool all_ok = true;
-        for (int j = 0; j < n_devices; ++j) all_ok = all_ok && dev_matrix[(size_t)j] != nullptr;
-        if (w.rc == ICIKT_OK && !all_ok) w.rc = fail(ICIKT_ERR_CUDA, "a peer device failed to upload its slice");
+        for (int j = 0; j < n_devices; ++j) all_ok = all_ok && peer_plan[(size_t)j] != nullptr;
+        if (w.rc == ICIKT_OK && !all_ok) w.rc = fail(ICIKT_ERR_CUDA, "a peer device failed to preprocess its slice");
         if (w.rc == ICIKT_OK) {
+          icikt_table mine[ICIKT_MAX_TABLES], theirs[ICIKT_MAX_TABLES];
+          const int nt = icikt_plan_tables(p, mine, ICIKT_MAX_TABLES);
           for (int j = 0; j < n_devices && w.rc == ICIKT_OK; ++j) {
             if (j == k) continue;
             const int dj = devices ? devices[j] : j;
             const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { w.rc = cuda_fail(e, "cudaDeviceEnablePeerAccess"); break; }
             cudaGetLastError();
-            const size_t off = (size_t)col_lo(j) * (size_t)n, cnt_el = (size_t)(col_lo(j + 1) - col_lo(j)) * (size_t)n;
-            if (cudaMemcpyPeerAsync(p->d_data_own + off, o.device, dev_matrix[(size_t)j] + off, dj, sizeof(double) * cnt_el,
-                                    p->stream) != cudaSuccess)
-              w.rc = cuda_fail(cudaGetLastError(), "cudaMemcpyPeerAsync");
+            icikt_plan_tables(peer_plan[(size_t)j], theirs, ICIKT_MAX_TABLES);
+            for (int t = 0; t < nt && w.rc == ICIKT_OK; ++t) {
+              const size_t off = (size_t)col_lo(j) * (size_t)mine[t].bytes_per_column;
+              const size_t len = (size_t)(col_lo(j + 1) - col_lo(j)) * (size_t)mine[t].bytes_per_column;
+              if (len && cudaMemcpyPeerAsync(static_cast<unsigned char*>(mine[t].ptr) + off, o.device,
+                                             static_cast<const unsigned char*>(theirs[t].ptr) + off, dj, len,
+                                             p->stream) != cudaSuccess)
+                w.rc = cuda_fail(cudaGetLastError(), "cudaMemcpyPeerAsync");
+            }
           }
-          if (w.rc == ICIKT_OK && cudaEventRecord(p->ev[1], p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "event");
+          if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns_finish(p);
           if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "peer gather");
         }
-        barrier.wait();  // nobody's matrix is touched (or freed) before every pull has finished
+        barrier.wait();  // nobody's tables are touched (or freed) before every pull has finished
+        if (cnt <= 0) return;
       }
-      if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns(p, global_na, n_global_na);
       if (w.rc == ICIKT_OK) w.rc = icikt_plan_pairs(p);
       if (w.rc == ICIKT_OK)
         w.rc = icikt_plan_download(p, raw + lo, pvalue ? pvalue + lo : nullptr, taumax ? taumax + lo : nullptr,

@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(256)
     build_keys_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
                       const double* __restrict__ global_na, int n_global_na, int na_inf,
                       unsigned long long* __restrict__ keys, uint16_t* __restrict__ vals,
-                      uint32_t* __restrict__ nabits) {
-  const int col = blockIdx.y;
+                      uint32_t* __restrict__ nabits, const int col0) {
+  const int col = blockIdx.y + col0;
   const int r = blockIdx.x * 256 + threadIdx.x;
   bool miss = false;
   if (r < n) {
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         uint32_t* __restrict__ firstbits, uint16_t* __restrict__ gstart, int gstride,
                         uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
                         int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord, const PipeConst pc,
-                        const int large_tie, const int direct_budget) {
+                        const int large_tie, const int direct_budget, const int col0) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
   __shared__ int n_large;
   __shared__ uint32_t descA[32], descB[32];
   typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
-  const int col = blockIdx.x, tid = threadIdx.x;
+  const int col = blockIdx.x + col0, tid = threadIdx.x;
   if (tid == 0) n_large = 0;
   unsigned long long keys[ITEMS];
   uint16_t vals[ITEMS];
@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
 
 template <int SORT_THREADS, int ITEMS>
 int launch_column_fused(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na, int na_inf,
-                        ColumnTables& tab, cudaStream_t stream, int large_tie, int direct_budget) {
+                        ColumnTables& tab, cudaStream_t stream, int large_tie, int direct_budget, int col0,
+                        int ncols) {
   using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * ((CAP / 32 + 3) & ~3) + 4 * (size_t)CAP;
@@ -404,10 +405,10 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
   pc.c64k = 65536u;
   auto kern = column_fused_kernel<SORT_THREADS, ITEMS>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  kern<<<(unsigned)tab.C, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
+  kern<<<(unsigned)ncols, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
                                                         tab.trow, tab.trun, tab.tend, tab.nabits, tab.firstbits, tab.gstart,
-                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, tab.tord, pc, large_tie, direct_budget);
+                                                        (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, tab.tord, pc, large_tie, direct_budget, col0);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -419,7 +420,8 @@ __global__ void __launch_bounds__(RANK_THREADS)
                        uint32_t* __restrict__ gpos_all, uint16_t* __restrict__ gstart_tab, int gstride,
                        uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
                        int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord,
-                       uint16_t* __restrict__ wrank_all, const int large_tie, const int direct_budget) {
+                       uint16_t* __restrict__ wrank_all, const int large_tie, const int direct_budget,
+                       const int col0) {
   // rows compared directly walk less than 2048 steps: groups below large_tie (<= 2048) rows, or larger
   // ones whose squares sum to at most direct_budget (<= 63) * n (launch_columns clamps both)
   __shared__ int n_large;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
   __shared__ long long llbuf[128];
   __shared__ uint32_t bits[2048];
   __shared__ uint32_t whist[2048];
-  const int col = blockIdx.x;
+  const int col = blockIdx.x + col0;
   const int tid = threadIdx.x;
   const unsigned long long* sk = skeys + (size_t)col * nstride;
   uint16_t* pm = perm + (size_t)col * nstride;
@@ -598,15 +600,44 @@ __global__ void __launch_bounds__(RANK_THREADS)
   }
 }
 
-__global__ void seg_offsets_kernel(long long* begin, long long* end, int C, long long nstride, long long n) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
+__global__ void seg_offsets_kernel(long long* begin, long long* end, int c0, int c1, long long nstride, long long n) {
+  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < c1) {
     begin[c] = c * nstride;
     end[c] = c * nstride + n;
   }
 }
 
+// tier maxima from the statistics of all columns (what the column kernels raise with atomicMax in a
+// full run): [0] any large tie group, [1] most large groups, [2] most distinct values of a column
+__global__ void max_tied_kernel(const ColStats* __restrict__ stats, int C, int32_t* __restrict__ max_tied) {
+  int nl = 0, k = 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    nl = max(nl, stats[c].flags >> 8);
+    k = max(k, stats[c].n_groups);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    nl = max(nl, __shfl_xor_sync(FULL, nl, d));
+    k = max(k, __shfl_xor_sync(FULL, k, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nl > 0) {
+      atomicMax(max_tied + 0, 1);
+      atomicMax(max_tied + 1, nl);
+    }
+    atomicMax(max_tied + 2, k);
+  }
+}
+
 }  // namespace
+
+int launch_max_tied(ColumnTables& tab, cudaStream_t stream) {
+  if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
+  const int C = (int)tab.C;
+  max_tied_kernel<<<std::min(64, (C + 255) / 256), 256, 0, stream>>>(tab.stats, C, tab.max_tied);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 
 size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride) {
   size_t bytes = 0;
@@ -622,8 +653,10 @@ bool columns_fused(int64_t n) { return n <= 8192 && !getenv("ICIKT_NO_FUSED_COLU
 
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
                    int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
-                   unsigned char* scratch, cudaStream_t stream) {
-  const int n = (int)tab.n, C = (int)tab.C;
+                   unsigned char* scratch, cudaStream_t stream, int64_t col_lo, int64_t col_hi) {
+  const int n = (int)tab.n;
+  const int col0 = (int)col_lo, C = (int)(col_hi - col_lo);  // the columns of this call
+  if (C <= 0) return 0;
   const int nstride = (int)tab.nstride, wstride = (int)tab.wstride;
   int launches = 0;
   // tie-group thresholds (icikt_common.cuh); the environment overrides are for tuning sweeps
@@ -633,11 +666,13 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
   // the bit arrays are written in full (words below n32/32) by the kernels below; the padding
   // words up to wstride were zeroed once when the plan was created
   // short columns: 512 threads (more CTAs per SM when there are many columns), else 1024
-  if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
+  // full runs reset the tier maxima here and the kernels below raise them; a partial run (sharded
+  // preprocessing) is followed by launch_max_tied once the statistics of every column are in place
+  if (col0 == 0 && C == (int)tab.C && cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
   if (columns_fused(n)) {
     int l;
 #define ICIKT_FUSED(T, I) \
-  l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream, large_tie, direct_budget)
+  l = launch_column_fused<T, I>(d_data, ld, d_global_na, n_global_na, na_inf, tab, stream, large_tie, direct_budget, col0, C)
     if (n <= 512) ICIKT_FUSED(512, 1);
     else if (n <= 1024) ICIKT_FUSED(512, 2);
     else if (n <= 2048) ICIKT_FUSED(512, 4);
@@ -650,30 +685,30 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     if (l < 0) return -1;
     return launches + l;  // the fused kernel computes the pass-A constants itself
   } else {
-    seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, C, nstride, n);
+    seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, col0, col0 + C, nstride, n);
     ++launches;
     const int n32 = (n + 31) & ~31;
     dim3 grid((n32 + 255) / 256, C);
     build_keys_kernel<<<grid, 256, 0, stream>>>(d_data, ld, n, nstride, wstride, d_global_na, n_global_na,
-                                                na_inf, wk.keys_in, wk.vals_in, tab.nabits);
+                                                na_inf, wk.keys_in, wk.vals_in, tab.nabits, col0);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
     size_t bytes = wk.cub_bytes;
     if (cub::DeviceSegmentedSort::SortPairs(wk.cub_temp, bytes, (const unsigned long long*)wk.keys_in,
                                             wk.keys_out, (const uint16_t*)wk.vals_in, tab.perm,
-                                            (long long)nstride * C, (long long)C,
-                                            (const long long*)wk.seg_begin, (const long long*)wk.seg_end,
+                                            (long long)nstride * tab.C, (long long)C,
+                                            (const long long*)wk.seg_begin + col0, (const long long*)wk.seg_end + col0,
                                             stream) != cudaSuccess)
       return -1;
     launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                        tab.trow, tab.trun, tab.tend, tab.firstbits,
                                                        wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied,
-                                                       tab.tord, wk.vals_in, large_tie, direct_budget);
+                                                       tab.tord, wk.vals_in, large_tie, direct_budget, col0);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
   }
-  const int cl = launch_column_consts(tab, sh, scratch, stream);
+  const int cl = launch_column_consts(tab, sh, scratch, stream, col_lo, col_hi);
   if (cl < 0) return -1;
   return launches + cl;
 }

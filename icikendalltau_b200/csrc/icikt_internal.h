@@ -90,13 +90,19 @@ struct ColumnWork {
 size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride);
 bool columns_fused(int64_t n);  // short columns: one kernel per column does everything (and writes tord)
 
-// K1: data (device, column-major, ld) -> tables.  Returns number of kernel launches or <0.
+// K1: data (device, column-major, ld) -> tables of columns [col_lo, col_hi).  Does not touch
+// tab.max_tied (launch_max_tied derives it from the statistics of all columns).  Returns the
+// number of kernel launches or <0.
 int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na,
                    int na_inf, ColumnTables& tab, ColumnWork& wk, const TiledShape& sh,
-                   unsigned char* scratch, cudaStream_t stream);
+                   unsigned char* scratch, cudaStream_t stream, int64_t col_lo, int64_t col_hi);
+
+// the device-side tier selection of the pair kernel: maxima over the statistics of ALL columns
+int launch_max_tied(ColumnTables& tab, cudaStream_t stream);
 
 // pass-A correction constant per column (needs the pair kernel's code path)
-int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream);
+int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream,
+                         int64_t col_lo, int64_t col_hi);
 
 // K2 (tiled) and K2-naive; both fill raw[P].
 // runs only if the device-side maxima written by K1 select `tier`; unit_counter must be zero

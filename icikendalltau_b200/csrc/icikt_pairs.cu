@@ -8,26 +8,30 @@
 //
 // Counting scheme (one CTA per pair, all integer, bit-exact):
 //   x := the streamed column (its sorted order `perm` defines the positions), y := the
-//   staged column (dense ranks in shared memory).  seq[p] = rank_y[perm_x[p]].
+//   staged column (dense ranks in shared memory, one TMA bulk copy per pair).
+//   seq[p] = rank_y[perm_x[p]], 16-bit keys (n <= 65 535).
 //   dis = #{p<q : x-group(p) != x-group(q), seq[p] > seq[q]}
 //       = INV(seq) - sum over x-groups INV(seq restricted to the group)
-//   INV is counted by an MSB-first stable bit partition of the whole sequence (a wavelet-matrix
-//   construction): at the level of bit s every element with bit 0 adds the number of
-//   1-elements that precede it inside its bucket (= elements agreeing on the higher bits).
-//   Pass A runs over all n rows.  Because every row is present, the bucket layout and the
-//   number of ones before each bucket are properties of column y alone, so the per-bucket
-//   offsets collapse into one per-column constant `cconst` (the raw count of the sorted
-//   sequence, which has no inversions): INV = sum_levels sum_{zero q} ones_before(q) - cconst.
-//   No bucket boundaries are tracked in pass A.
-//   The first x-group (the missing rows, usually the only large tie group) is written into
-//   the sequence already ordered by y (stream compaction of y's sorted order through x's
-//   membership bitmask), so it contributes no inversions and its joint ties fall out of the
-//   compaction.  The remaining tied x-groups go through pass B: the same partition on the
-//   composite key (x-group << 16 | y-rank) with explicit bucket boundaries (ballot + clz),
-//   which yields their internal inversions and their joint ties.
-//   Each level is two warp-synchronous sweeps over register-resident chunks (ballot/popc
-//   prefix sums), one cross-warp scan of W per-warp totals, and an in-place scatter in
-//   shared memory; two __syncthreads per level.
+//   INV is counted by an MSB-first stable partition of the whole sequence (a wavelet-matrix
+//   construction) -- NOT the bottom-up merge sort BASELINE.json's north_star sketches; DESIGN.md
+//   section 2 states the deviation and why (same counts, fewer instructions per key).
+//   Pass A (icikt_count.cuh: count_pass, count_pass_inplace) runs over all n rows, TWO bits per
+//   level, lane-sequential: thread t owns a contiguous range of the sequence, counts its keys per
+//   digit class with SIMD-in-a-word adds, two packed warp scans give the class offsets, then the
+//   thread walks its range with four running slot indices and scatters the keys (STS.U16).  No
+//   ballots and no per-key popc.  Because every row is present, the bucket layout (keys agreeing
+//   on the higher bits) and the number of ones before each bucket are properties of column y
+//   alone, so the per-bucket offsets collapse into one per-column constant `cconst` (the raw
+//   count of y's own sorted sequence, which has no inversions; computed by K1):
+//       INV = sum_levels sum_{zero keys} ones_before - cconst.
+//   The first x-group (the missing rows, usually the only large tie group) is written into the
+//   sequence already ordered by y from a RANK HISTOGRAM (group_hist: 16-bit counters by
+//   shared-memory atomics, one block scan, every thread writes `count` copies of its ranks), so it
+//   contributes no inversions and its joint ties are sum C(count, 2).  Small tie groups of x are
+//   compared directly in K1's walk order (small_groups_direct), large ones are rewritten in place
+//   in ascending y order by the same histogram technique (large_groups_sorted).  Pass B
+//   (bucket_pass: one-bit levels on the composite key with explicit bucket boundaries, ballot +
+//   clz) survives only as tier 2, for columns with very many large groups x distinct values.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -959,7 +963,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
 // cconst of every column: the raw pass-A count of the column's own sorted rank sequence
 // (no inversions), evaluated by the same code path as the pair kernel.  Grid-stride over columns.
 template <bool G>
-__global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams p, ColStats* stats, int C) {
+__global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams p, ColStats* stats, int c0, int C) {
   typedef Mem<G> M;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -968,7 +972,7 @@ __global__ void __launch_bounds__(1024, 1) column_const_kernel(const TiledParams
   const int cap = (nwarps * kk) << 8;
   Carve sm(smem_raw, p.wstride, fmask_words(nwarps, kk << 3));
   const typename M::ptr bufA = region_base<G>(sm, p), bufB = M::add(bufA, 2 * cap);
-  for (int col = blockIdx.x; col < C; col += gridDim.x) {
+  for (int col = c0 + blockIdx.x; col < C; col += gridDim.x) {
     const ColStats CS = stats[col];
     if (CS.n_groups < 2) {
       if (tid == 0) stats[col].cconst = 0;
@@ -1442,7 +1446,8 @@ int launch_pairs_tiled(const PairLaunch& pl, const TiledShape& sh, int n_sm, int
   return launch_tiled_g<false>(p, sh, tiled_smem_bytes(sh.region_bytes, p.wstride, fw), n_sm, stream);
 }
 
-int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream) {
+int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char* scratch, cudaStream_t stream,
+                         int64_t col_lo, int64_t col_hi) {
   PairLaunch pl{};
   pl.tab = &tab;
   TiledParams p = make_params(pl);
@@ -1452,7 +1457,8 @@ int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char*
   const int region = (2 * 2 * cap + 15) & ~15;
   const int fw = fmask_words(W, p.kk << 3);
   const bool g = tiled_smem_bytes(region, p.wstride, fw) > 227 * 1024 || getenv("ICIKT_FORCE_GMEM") != nullptr;
-  long long grid = tab.C;
+  long long grid = col_hi - col_lo;
+  if (grid <= 0) return 0;
   if (g) {
     if (!scratch || sh.scratch_stride < region) return -2;  // the plan sizes the slot as max(region, const region)
     p.scratch = scratch;
@@ -1460,11 +1466,11 @@ int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char*
     grid = std::min<long long>(grid, sh.scratch_ctas);
     const size_t smem = tiled_smem_bytes(0, p.wstride, fw);
     if (cudaFuncSetAttribute(column_const_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    column_const_kernel<true><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)tab.C);
+    column_const_kernel<true><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)col_lo, (int)col_hi);
   } else {
     const size_t smem = tiled_smem_bytes(region, p.wstride, fw);
     if (cudaFuncSetAttribute(column_const_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    column_const_kernel<false><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)tab.C);
+    column_const_kernel<false><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)col_lo, (int)col_hi);
   }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

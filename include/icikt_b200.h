@@ -185,6 +185,24 @@ int icikt_plan_upload(icikt_plan* plan, const double* data, int64_t ld);
 int icikt_plan_set_device_matrix(icikt_plan* plan, const double* d_data, int64_t ld);
 /* K1: missing marking, sort, dense ranks, tie sums, per-column tables               */
 int icikt_plan_columns(icikt_plan* plan, const double* global_na, int32_t n_global_na);
+/* Sharded K1 (one process or worker per GPU): the per-column work of columns
+ * [col_lo, col_hi) only.  A rank uploads and preprocesses its slice of the columns, the ranks
+ * exchange the table slices icikt_plan_tables describes (column c of table k lives at
+ * ptr + c * bytes_per_column, on the plan's device; any transport: NCCL all-gather, peer
+ * copies), then icikt_plan_columns_finish derives the launch tier from the statistics of all
+ * columns and releases icikt_plan_pairs.  `data`/`ld` address the whole matrix.            */
+typedef struct icikt_table {
+  void* ptr;                /* device pointer to column 0 of the table */
+  int64_t bytes_per_column;
+} icikt_table;
+#define ICIKT_MAX_TABLES 16
+int icikt_plan_upload_columns(icikt_plan* plan, const double* data, int64_t ld, int64_t col_lo,
+                              int64_t col_hi);
+int icikt_plan_columns_range(icikt_plan* plan, const double* global_na, int32_t n_global_na,
+                             int64_t col_lo, int64_t col_hi);
+/* fills out[0..min(cap, n)) and returns n, the number of tables to exchange (<= ICIKT_MAX_TABLES) */
+int icikt_plan_tables(icikt_plan* plan, icikt_table* out, int32_t cap);
+int icikt_plan_columns_finish(icikt_plan* plan);
 /* K2+K3 over the plan's pairs; results stay on the device                           */
 int icikt_plan_pairs(icikt_plan* plan);
 /* block until the plan's stream is idle                                             */

@@ -484,11 +484,13 @@ double icikt_oracle_pnorm(double x, int lower_tail) { return pnorm_std(x, lower_
 // (missing already marked NaN, R/kendalltau.R:119-121).  One std::thread per chunk
 // stands in for one furrr worker.  pi/pj are 0-based column indices.  Outputs have
 // length P; counts (7 int64 per pair: dis, ntie, xtie, ytie, tot, n_entry, b) may be NULL.
-int icikt_oracle_pair_loop(const double* data, int64_t n, int64_t C, const int32_t* pi,
-                           const int32_t* pj, int64_t P, int perspective, int alternative,
-                           int continuity, int emulate_int32, int ncore, double* raw,
-                           double* pvalue, double* taumax, double* completeness, int32_t* status,
-                           int64_t* counts) {
+// z != NULL: also the normal deviate of every pair (src/kendallc.cpp:321), which the parity
+// tests need for the z^2-aware p-value tolerance
+int icikt_oracle_pair_loop_z(const double* data, int64_t n, int64_t C, const int32_t* pi,
+                             const int32_t* pj, int64_t P, int perspective, int alternative,
+                             int continuity, int emulate_int32, int ncore, double* raw,
+                             double* pvalue, double* taumax, double* completeness, int32_t* status,
+                             int64_t* counts, double* z) {
   (void)C;
   if (ncore < 1) ncore = 1;
   const int64_t n_each = (P + ncore - 1) / ncore;
@@ -502,6 +504,7 @@ int icikt_oracle_pair_loop(const double* data, int64_t n, int64_t C, const int32
       taumax[k] = r.tau_max;
       completeness[k] = r.completeness;
       if (status) status[k] = r.status;
+      if (z) z[k] = r.z;
       if (counts) {
         int64_t* c = counts + 7 * k;
         c[0] = r.dis; c[1] = r.ntie; c[2] = r.xtie; c[3] = r.ytie; c[4] = r.tot; c[5] = r.n_entry;
@@ -521,6 +524,15 @@ int icikt_oracle_pair_loop(const double* data, int64_t n, int64_t C, const int32
   }
   for (auto& t : th) t.join();
   return 0;
+}
+
+int icikt_oracle_pair_loop(const double* data, int64_t n, int64_t C, const int32_t* pi,
+                           const int32_t* pj, int64_t P, int perspective, int alternative,
+                           int continuity, int emulate_int32, int ncore, double* raw,
+                           double* pvalue, double* taumax, double* completeness, int32_t* status,
+                           int64_t* counts) {
+  return icikt_oracle_pair_loop_z(data, n, C, pi, pj, P, perspective, alternative, continuity, emulate_int32,
+                                  ncore, raw, pvalue, taumax, completeness, status, counts, nullptr);
 }
 
 }  // extern "C"

@@ -75,6 +75,8 @@ def lib():
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              dp, dp, dp, dp, ip, lp]
         L.icikt_oracle_pair_loop.restype = ctypes.c_int
+        L.icikt_oracle_pair_loop_z.argtypes = L.icikt_oracle_pair_loop.argtypes + [dp]
+        L.icikt_oracle_pair_loop_z.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -202,8 +204,9 @@ def setup_comparisons(n_sample, include_only=None, diag_good=True):
 
 
 def pair_loop(exclude_data, pi, pj, perspective="global", alternative="two.sided",
-              continuity=False, ncore=1, emulate_int32=False, want_counts=False):
-    """ici_split over split_comparisons, R/kendalltau.R:158,280-308."""
+              continuity=False, ncore=1, emulate_int32=False, want_counts=False, want_z=False):
+    """ici_split over split_comparisons, R/kendalltau.R:158,280-308.
+    want_z: also return the normal deviate z of every pair (src/kendallc.cpp:321)."""
     data = np.asfortranarray(exclude_data, dtype=np.float64)
     n, C = data.shape
     pi = np.ascontiguousarray(pi, dtype=np.int32)
@@ -213,13 +216,17 @@ def pair_loop(exclude_data, pi, pj, perspective="global", alternative="two.sided
     status = np.empty(P, dtype=np.int32)
     counts = np.empty((P, 7), dtype=np.int64) if want_counts else None
     ip = ctypes.POINTER(ctypes.c_int32)
-    lib().icikt_oracle_pair_loop(
+    z = np.empty(P) if want_z else None
+    lib().icikt_oracle_pair_loop_z(
         _dptr(data), n, C, pi.ctypes.data_as(ip), pj.ctypes.data_as(ip), P,
         PERSPECTIVE.get(perspective, 0), ALTERNATIVE.get(alternative, 3), int(bool(continuity)),
         int(bool(emulate_int32)), int(ncore), _dptr(raw), _dptr(pv), _dptr(tm), _dptr(comp),
         status.ctypes.data_as(ip),
-        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if want_counts else None)
+        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if want_counts else None,
+        _dptr(z) if want_z else None)
     out = dict(raw=raw, pvalue=pv, taumax=tm, completeness=comp, status=status)
+    if want_z:
+        out["z"] = z
     if want_counts:
         out["counts"] = counts
     return out

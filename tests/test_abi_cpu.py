@@ -37,6 +37,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Opts) == 8 * 4 + 2 * 8
     assert ctypes.sizeof(_lib.Timings) == 6 * 4 + 2 * 4
+    assert ctypes.sizeof(_lib.Table) == 16 and _lib.MAX_TABLES == 16  # icikt_table, ICIKT_MAX_TABLES
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
@@ -81,6 +82,13 @@ def test_setup_comparisons_matches_oracle():
         opi, opj = O.setup_comparisons(100, inc_idx, diag)
         assert np.array_equal(pi, opi) and np.array_equal(pj, opj)
         assert allp == (inc_names is None)
+    # the documented list(g1 = "s1", g2 = c("s2", "s3")) form (R/kendalltau.R:86-91): a scalar member is
+    # a vector of length one, as a list, a tuple or a dict
+    want = api.setup_comparisons(names, (["s1"], ["s2", "s3"]), True)
+    for form in (["s1", ["s2", "s3"]], ("s1", ("s2", "s3")), {"g1": "s1", "g2": ["s2", "s3"]},
+                 [np.array(["s2", "s3"]), "s1"]):
+        got = api.setup_comparisons(names, form, True)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] is False
     # test-kendall-tau.R:102-136: zero counts of the C x C result follow from the pair counts
     for inc, zeros in (("s1", 9702), (["s1", "s3"], 9506), ((["s1"], ["s2", "s3"]), 9896)):
         pi, pj, _ = api.setup_comparisons(names, inc, True)

@@ -36,6 +36,21 @@ def test_pair_ranges_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_column_ranges_cover_and_table_slices():
+    for C in (1, 7, 100, 2000, 5001):
+        for world in (1, 2, 3, 8):
+            r = [sharding.column_range(C, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == C
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+    sl = sharding.table_slices([(1000, 40), (5000, 64)], 10, 4)
+    assert len(sl) == 8
+    for t, bpc in ((0, 40), (1, 64)):
+        mine = [(off, ln) for (tt, r, off, ln) in sl if tt == t]
+        assert mine[0][0] == 0 and sum(ln for _, ln in mine) == 10 * bpc
+        assert all(mine[k][0] + mine[k][1] == mine[k + 1][0] for k in range(3))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -62,12 +77,25 @@ def _worker(rank, world, port, q):
     dist.all_gather_object(gathered, mine)
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # the table exchange of the sharded K1 (bench.py runs it over NCCL on device memory): every rank
+    # fills its own column slice of a table, afterwards every rank holds every column -- equal
+    # slices (one in-place all-gather) and ragged ones (one broadcast per rank)
+    tables_ok = True
+    for C, bpc in ((8, 24), (9, 10)):
+        want = torch.arange(C * bpc, dtype=torch.int64).remainder(251).to(torch.uint8)
+        tbl = torch.zeros(C * bpc, dtype=torch.uint8)
+        c0, c1 = sharding.column_range(C, rank, world)
+        tbl[c0 * bpc:c1 * bpc] = want[c0 * bpc:c1 * bpc]
+        calls = sharding.all_gather_columns(tbl, bpc, C, rank, world)
+        tables_ok = tables_ok and bool(torch.equal(tbl, want)) and calls == (1 if C % world == 0 else world)
+    flags = [None] * world
+    dist.all_gather_object(flags, tables_ok)
     if rank == 0:
         full = O.pair_loop(x, pi, pj, perspective="local")
         got = sharding.gather_results(gathered, P)
         ok = all(np.array_equal(got[k], full[k], equal_nan=True) for k in ("raw", "pvalue", "taumax",
                                                                           "completeness", "status"))
-        ok = ok and got["max_taumax"] == float(np.nanmax(full["taumax"])) and t.item() == world
+        ok = ok and got["max_taumax"] == float(np.nanmax(full["taumax"])) and t.item() == world and all(flags)
         q.put(ok)
     dist.destroy_process_group()
 
