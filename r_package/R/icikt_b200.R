@@ -41,13 +41,33 @@
   out
 }
 
+# All pairs in utils::combn(n, 2) order as 1-based column indices, vectorised (utils::combn is an
+# R-level loop over 12.5 M pairs at 5 000 samples); the diagonal is appended when !diag_good.
+.all_pair_indices = function(n_sample, diag_good) {
+  cnt = if (n_sample > 1) (n_sample - 1L):1L else integer(0)
+  i = rep.int(seq_len(n_sample - 1L), cnt)
+  j = i + sequence(cnt)
+  if (!diag_good) { i = c(i, seq_len(n_sample)); j = c(j, seq_len(n_sample)) }
+  list(i = as.integer(i), j = as.integer(j))
+}
+
 # Pair plan in utils::combn order (+ the diagonal when !diag_good) as 1-based column indices.
 # `all_pairs` tells the caller that the list is exactly what icikt_all_pairs enumerates itself.
-.plan_pairs = function(samples, include_only = NULL, diag_good = TRUE, include_arg = "include_only") {
+# need_indices = FALSE: the caller hands the all-pairs case to the library without ever looking at
+# the index vectors (matrix outputs), so none are built -- only their number, `n_todo`.
+.plan_pairs = function(samples, include_only = NULL, diag_good = TRUE, include_arg = "include_only",
+                       need_indices = TRUE) {
   n_sample = length(samples)
-  idx = utils::combn(n_sample, 2)
-  i = idx[1, ]; j = idx[2, ]
-  if (!diag_good) { i = c(i, seq_len(n_sample)); j = c(j, seq_len(n_sample)) }
+  if (is.null(include_only) && !need_indices) {
+    n_todo = n_sample * (n_sample - 1) / 2 + if (diag_good) 0 else n_sample
+    if (n_todo == 0) {
+      stop(sprintf("No comparisons to do. Check the list of column names in `%s` vs those in the samples.",
+                   include_arg), call. = FALSE)
+    }
+    return(list(i = NULL, j = NULL, all_pairs = TRUE, n_todo = n_todo))
+  }
+  idx = .all_pair_indices(n_sample, diag_good)
+  i = idx$i; j = idx$j
   all_pairs = TRUE
   if (!is.null(include_only)) {
     all_pairs = FALSE
@@ -70,7 +90,7 @@
     stop(sprintf("No comparisons to do. Check the list of column names in `%s` vs those in the samples.",
                  include_arg), call. = FALSE)
   }
-  list(i = as.integer(i), j = as.integer(j), all_pairs = all_pairs)
+  list(i = as.integer(i), j = as.integer(j), all_pairs = all_pairs, n_todo = length(i))
 }
 
 .run_pairs = function(data, global_na, plan, include_diag, perspective, alternative, continuity, device) {
@@ -124,8 +144,10 @@ ici_kendalltau = function(data_matrix, global_na = c(NA, Inf, 0), perspective = 
   data_matrix = .as_numeric_matrix(data_matrix, arg)
   samples = colnames(data_matrix)
   exclude_loc = .missing_matrix(data_matrix, global_na)
-  plan = .plan_pairs(samples, include_only, diag_good, include_arg)
-  n_todo = length(plan$i)
+  # the all-pairs matrix path never needs the 1-based index vectors (12.5 M pairs at 5 000 samples)
+  on_device = return_matrix && length(device) == 1L
+  plan = .plan_pairs(samples, include_only, diag_good, include_arg, need_indices = !on_device || check_timing)
+  n_todo = plan$n_todo
 
   if (check_timing) {   # R/kendalltau.R:141-148,633-669: time five random pairs, extrapolate
     pick = sample(n_todo, min(5L, n_todo))
@@ -140,7 +162,7 @@ ici_kendalltau = function(data_matrix, global_na = c(NA, Inf, 0), perspective = 
                                 t_all / 60, t_all / 3600, t_all / 216000)))
   }
 
-  if (return_matrix && length(device) == 1L) {
+  if (on_device) {
     # scale_and_reshape (R/kendalltau.R:357-421) on the device: the five matrices come back filled,
     # degenerate pairs already NA; only the dimnames and `keep` are added here
     t1 = Sys.time()
@@ -239,7 +261,8 @@ pairwise_completeness = function(data_matrix, global_na = c(NA, Inf, 0), include
   # masks and popc(x | y) on the device, no pair kernel
   data_matrix = .as_numeric_matrix(data_matrix, deparse(substitute(data_matrix)))
   samples = colnames(data_matrix)
-  plan = .plan_pairs(samples, include_only, diag_good = FALSE, deparse(substitute(include_only)))
+  plan = .plan_pairs(samples, include_only, diag_good = FALSE, deparse(substitute(include_only)),
+                     need_indices = !return_matrix)
   r = .Call(C_icikt_pairwise_completeness, data_matrix, as.double(global_na),
             if (plan$all_pairs) NULL else plan$i, if (plan$all_pairs) NULL else plan$j,
             as.integer(device), return_matrix && plan$all_pairs)
