@@ -288,6 +288,7 @@ def main():
 
     smem32, smem128 = _lib.measure_smem_bandwidth(local_rank)
     smem_peak = max(smem32, smem128)
+    issue_alu, issue_fma, issue_mixed = _lib.measure_issue_rate(local_rank)  # G warp-instructions/s
 
     plan = ik.Plan(n, C, perspective=persp, device=local_rank, kernel=kernel, pair_lo=lo, pair_hi=hi)
     plan.upload(x_pinned)
@@ -379,6 +380,20 @@ def main():
             traffic = json.load(open(prof)).get(args.workload)
         except Exception:
             traffic = None
+    # INT/issue roofline: the pair kernel's executed warp instructions per pair come from the ncu
+    # capture of the same workload (smsp__inst_executed.sum / pairs, profiles/k2_inst_per_pair.json);
+    # the denominator is measured live (LOP3 and IMAD interleaved, both integer-capable pipes busy)
+    issue = None
+    try:
+        ent = json.load(open(os.path.join(ROOT, "profiles", "k2_inst_per_pair.json"))).get(args.workload)
+        if ent and args.kernel == "tiled":
+            ach = ent["warp_inst_per_pair"] * P_rank / (k2_avg_ms * 1e-3) / 1e9
+            issue = {"achieved": ach, "peak": issue_mixed, "unit": "G warp-inst/s", "frac": ach / issue_mixed,
+                     "warp_inst_per_pair": ent["warp_inst_per_pair"], "inst_source": ent["source"],
+                     "peak_source": f"measured on this GPU by icikt_measure_issue_rate: LOP3 only {issue_alu:.0f}, "
+                                    f"IMAD only {issue_fma:.0f}, interleaved {issue_mixed:.0f} G warp-inst/s"}
+    except Exception:
+        issue = None
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -408,6 +423,7 @@ def main():
                      "peak_source": f"measured on this GPU by icikt_measure_smem_bandwidth: "
                                     f"{smem32:.0f} GB/s (32-bit), {smem128:.0f} GB/s (128-bit); "
                                     "MEASURED_PEAKS.json has no shared-memory figure",
+                     "issue": issue,
                      "k2_ms": k2_avg_ms, "k1_ms": float(np.mean(k1_ms)), "k3_ms": float(np.mean(k3_ms)),
                      "k2_share_of_step": k2_avg_ms * args.steps / dev_ms if world == 1 else None,
                      "k1_hbm": {"achieved_gbs": (8.0 + 4.2) * n * (c_hi - c_lo if shard_k1 else C) /

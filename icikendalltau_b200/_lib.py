@@ -30,7 +30,8 @@ EXPORTS = [
     "icikt_pnorm_device", "icikt_release_workspace", "icikt_measure_smem_bandwidth",
     "icikt_pair_from_index", "icikt_all_pairs_multi", "icikt_matrices", "icikt_plan_download_matrices",
     "icikt_pairwise_completeness", "icikt_plan_upload_columns", "icikt_plan_columns_range",
-    "icikt_plan_tables", "icikt_plan_columns_finish",
+    "icikt_plan_tables", "icikt_plan_columns_finish", "icikt_measure_issue_rate",
+    "icikt_matrices_multi",
 ]
 NSTATUS = 10
 
@@ -132,6 +133,10 @@ def load():
                                  _ip, _ip, ctypes.c_int64, ctypes.POINTER(Opts), ctypes.c_int32, ctypes.c_int32,
                                  _ip, _dp, _dp, _dp, _dp, _dp, _lp, _dp, ctypes.POINTER(Timings)]
     L.icikt_matrices.restype = ctypes.c_int
+    L.icikt_matrices_multi.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp, ctypes.c_int32,
+                                       ctypes.POINTER(Opts), _ip, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       _ip, _dp, _dp, _dp, _dp, _dp, _lp, _dp, ctypes.POINTER(Timings)]
+    L.icikt_matrices_multi.restype = ctypes.c_int
     L.icikt_pairwise_completeness.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _dp,
                                               ctypes.c_int32, ctypes.c_int32, _ip, _ip, ctypes.c_int64, _ip,
                                               _dp, _dp]
@@ -152,6 +157,8 @@ def load():
     L.icikt_release_workspace.restype = None
     L.icikt_measure_smem_bandwidth.argtypes = [ctypes.c_int32, _dp, _dp]
     L.icikt_measure_smem_bandwidth.restype = ctypes.c_int
+    L.icikt_measure_issue_rate.argtypes = [ctypes.c_int32, _dp, _dp, _dp]
+    L.icikt_measure_issue_rate.restype = ctypes.c_int
     _lib = L
     return L
 
@@ -239,10 +246,12 @@ MATRIX_NAMES = ("cor", "raw", "pvalue", "taumax", "completeness")
 
 
 def run_matrices(data, global_na=(), scale_max=True, diag_good=True, n_good=None, pi=None, pj=None,
-                 want=MATRIX_NAMES, **opt_kw):
+                 want=MATRIX_NAMES, devices=None, **opt_kw):
     """icikt_matrices: the pair results as symmetric C x C matrices filled on the device
     (scale_and_reshape, R/kendalltau.R:357-421).  Returns the requested matrices plus
-    status_counts (pairs per status class), max_taumax and timings."""
+    status_counts (pairs per status class), max_taumax and timings.
+    devices: list of CUDA ordinals -> icikt_matrices_multi (all pairs only): the pair order is sliced
+    over the devices and every device returns its own block of columns of each matrix."""
     L = load()
     data = np.asfortranarray(data, dtype=np.float64)
     if data.ndim != 2:
@@ -258,6 +267,17 @@ def run_matrices(data, global_na=(), scale_max=True, diag_good=True, n_good=None
         pi = np.ascontiguousarray(pi, dtype=np.int32)
         pj = np.ascontiguousarray(pj, dtype=np.int32)
     ngood = None if n_good is None else np.ascontiguousarray(n_good, dtype=np.int32)
+    if devices is not None:
+        if pi is not None:
+            raise ValueError("several devices: all pairs only")
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        check(L.icikt_matrices_multi(_ptr(data, _dp), n, C, n, gp, ng, ctypes.byref(o), _ptr(dev, _ip), int(dev.size),
+                                     int(bool(scale_max)), int(bool(diag_good)), _ptr(ngood, _ip),
+                                     *(_ptr(mats[k], _dp) for k in MATRIX_NAMES), _ptr(hist, _lp), ctypes.byref(mx),
+                                     ctypes.byref(t)))
+        out = {k: v for k, v in mats.items() if v is not None}
+        out.update(status_counts=hist, max_taumax=mx.value, timings=t.as_dict())
+        return out
     check(L.icikt_matrices(_ptr(data, _dp), n, C, n, gp, ng, _ptr(pi, _ip), _ptr(pj, _ip),
                            0 if pi is None else int(pi.size), ctypes.byref(o), int(bool(scale_max)),
                            int(bool(diag_good)), _ptr(ngood, _ip), *(_ptr(mats[k], _dp) for k in MATRIX_NAMES),
@@ -405,6 +425,13 @@ def measure_smem_bandwidth(device=0):
     a, b = ctypes.c_double(0), ctypes.c_double(0)
     check(load().icikt_measure_smem_bandwidth(device, ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
+
+
+def measure_issue_rate(device=0):
+    """(LOP3 only, IMAD only, interleaved) sustained issue rate in G warp-instructions/s over the GPU."""
+    a, f, m = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+    check(load().icikt_measure_issue_rate(device, ctypes.byref(a), ctypes.byref(f), ctypes.byref(m)))
+    return a.value, f.value, m.value
 
 
 def pair_from_index(C, index, include_diag=False):

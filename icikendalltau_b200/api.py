@@ -209,7 +209,7 @@ def ici_kendalltau(data_matrix, global_na=(np.nan, np.inf, 0), perspective="glob
     global_na = [float(v) for v in global_na]
     exclude_loc = setup_missing_matrix(data, global_na)
     log.info("Figuring out comparisons to do ...")
-    if include_only is None and return_matrix and n_gpus <= 1 and not check_timing:
+    if include_only is None and return_matrix and not check_timing:
         # every pair, in the library's own order, straight into matrices: no pair list on the host
         pi = pj = None
         all_pairs = True
@@ -236,10 +236,12 @@ def ici_kendalltau(data_matrix, global_na=(np.nan, np.inf, 0), perspective="glob
 
     log.info("Running correlations ...")
     t1 = time.perf_counter()
-    if return_matrix and n_gpus <= 1:
+    if return_matrix and (n_gpus <= 1 or all_pairs):
         # scale_and_reshape on the device: the five C x C matrices come back filled (:357-421)
         n_good = (~exclude_loc).sum(axis=0)
-        if all_pairs:
+        if all_pairs and n_gpus > 1:  # every GPU fills and returns its own block of columns
+            r = _lib.run_matrices(data, global_na, scale_max, diag_good, n_good, devices=range(n_gpus), **kw)
+        elif all_pairs:
             r = _lib.run_matrices(data, global_na, scale_max, diag_good, n_good, **kw)
         else:
             r = _lib.run_matrices(data, global_na, scale_max, diag_good, n_good, pi=pi, pj=pj, **kw)

@@ -30,6 +30,15 @@ int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return ICIKT_ERR_CUDA;
 }
+// failure of one of the launchers in icikt_columns.cu / icikt_pairs.cu / icikt_reshape.cu
+int launch_fail(const char* what) {
+  cudaError_t e = g_launch_error;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  g_err = std::string(what) + ": " + (g_launch_note ? g_launch_note : "") + ": " + cudaGetErrorString(e);
+  g_launch_error = cudaSuccess;
+  g_launch_note = "";
+  return ICIKT_ERR_CUDA;
+}
 #define CK(call)                                         \
   do {                                                   \
     cudaError_t e_ = (call);                             \
@@ -101,7 +110,8 @@ struct icikt_plan {
   uint32_t* d_naive = nullptr;
   int64_t naive_threads = 0;
   // matrix output (icikt_plan_download_matrices), allocated on first use
-  double* d_mat = nullptr;          // 5 x [C][C]: cor, raw, pvalue, taumax, completeness
+  double* d_mat = nullptr;          // 5 x [C][C]: cor, raw, pvalue, taumax, completeness (multi-GPU: 5 blocks of columns)
+  size_t mat_elems = 0;             // doubles allocated at d_mat
   unsigned char* h_mat = nullptr;   // pinned copy of all five (small C only)
   unsigned long long* d_hist = nullptr;  // [16] pairs per status class
   int32_t* d_ngood = nullptr;       // [C] caller-supplied n_good
@@ -134,9 +144,6 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->wk.keys_out);
   cudaFree(p->wk.vals_in);
   cudaFree(p->wk.gpos);
-  cudaFree(p->wk.seg_begin);
-  cudaFree(p->wk.seg_end);
-  cudaFree(p->wk.cub_temp);
   cudaFree(p->d_units);
   cudaFree(p->d_pj);
   cudaFree(p->d_raw);
@@ -436,14 +443,12 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   PCK(cudaMemsetAsync(t.firstbits, 0, sizeof(uint32_t) * nw, p->stream));
   PCK(cudaMemsetAsync(t.max_tied, 0, 4 * sizeof(int32_t), p->stream));
   p->shape = tiled_shape(n, 0, t.wstride, p->n_sm);
-  PCK(dmalloc(&p->wk.keys_in, ne));
-  PCK(dmalloc(&p->wk.keys_out, ne));
-  PCK(dmalloc(&p->wk.vals_in, ne));
-  PCK(dmalloc(&p->wk.gpos, (size_t)(t.nstride + 64) * C));
-  PCK(dmalloc(&p->wk.seg_begin, (size_t)C));
-  PCK(dmalloc(&p->wk.seg_end, (size_t)C));
-  p->wk.cub_bytes = columns_cub_bytes(n, C, t.nstride);
-  PCK(cudaMalloc(&p->wk.cub_temp, std::max<size_t>(p->wk.cub_bytes, 16)));
+  if (!columns_fused(n)) {  // scratch of the multi-kernel column path (long columns)
+    PCK(dmalloc(&p->wk.keys_in, ne));
+    PCK(dmalloc(&p->wk.keys_out, ne));
+    PCK(dmalloc(&p->wk.vals_in, ne));
+    PCK(dmalloc(&p->wk.gpos, (size_t)(t.nstride + 64) * C));
+  }
   PCK(dmalloc(&p->d_global_na, 64));
 
   const size_t np = (size_t)std::max<int64_t>(p->P, 1);
@@ -563,7 +568,7 @@ static int plan_columns_impl(icikt_plan* p, const double* global_na, int32_t n_g
   }
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
                                p->d_scratch, p->stream, col_lo, col_hi);
-  if (l < 0) return cuda_fail(cudaGetLastError(), "column kernels");
+  if (l < 0) return launch_fail("column kernels");
   CK(cudaEventRecord(p->ev[3], p->stream));
   // no synchronisation: `lit` is pageable host memory, so the copy above was staged before
   // cudaMemcpyAsync returned
@@ -588,7 +593,7 @@ int icikt_plan_columns_finish(icikt_plan* p) {
   if (!p || !p->d_data) return fail(ICIKT_ERR_BAD_ARG, "no matrix set on the plan");
   CK(cudaSetDevice(p->device));
   const int l = launch_max_tied(p->tab, p->stream);
-  if (l < 0) return cuda_fail(cudaGetLastError(), "tier maxima kernel");
+  if (l < 0) return launch_fail("tier maxima kernel");
   CK(cudaEventRecord(p->ev[3], p->stream));  // the exchange of the tables counts as column time
   p->tm.n_launches += l;
   p->columns_done = true;
@@ -654,7 +659,7 @@ int icikt_plan_pairs(icikt_plan* p) {
     if (l == -2)
       return fail(ICIKT_ERR_TOO_LONG, "the tied-value lists of this matrix do not fit the pair kernel's "
                                       "shared memory (long vectors with heavy ties)");
-    if (l < 0) return cuda_fail(cudaGetLastError(), "pair kernel");
+    if (l < 0) return launch_fail("pair kernel");
     launches += l;
     CK(cudaEventRecord(p->ev[8], p->stream));
     EpilogueLaunch el;
@@ -676,7 +681,7 @@ int icikt_plan_pairs(icikt_plan* p) {
     el.counts = p->d_counts;
     el.max_taumax_bits = p->d_maxbits;
     l = launch_epilogue(el, p->stream);
-    if (l < 0) return cuda_fail(cudaGetLastError(), "epilogue kernel");
+    if (l < 0) return launch_fail("epilogue kernel");
     launches += l;
   }
   CK(cudaEventRecord(p->ev[5], p->stream));
@@ -746,10 +751,15 @@ int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_
   CK(cudaSetDevice(p->device));
   const size_t C = (size_t)p->C, cc = C * C;
   double* outs[5] = {cor, raw, pvalue, taumax, completeness};
-  if (!p->d_mat && dmalloc(&p->d_mat, 5 * cc) != cudaSuccess) {
-    cudaGetLastError();
+  if (p->mat_elems < 5 * cc) {
+    cudaFree(p->d_mat);
     p->d_mat = nullptr;
-    return fail(ICIKT_ERR_ALLOC, "device allocation of the result matrices failed");
+    p->mat_elems = 0;
+    if (dmalloc(&p->d_mat, 5 * cc) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ICIKT_ERR_ALLOC, "device allocation of the result matrices failed");
+    }
+    p->mat_elems = 5 * cc;
   }
   if (!p->d_hist) CK(dmalloc(&p->d_hist, 16));
   if (!p->d_ngood) CK(dmalloc(&p->d_ngood, C));
@@ -783,7 +793,7 @@ int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_
   mf.diag_good = diag_good != 0;
   mf.hist = p->d_hist;
   if (p->P <= 0) mf.n_units = 0;
-  if (launch_matrix_fill(mf, p->stream) < 0) return cuda_fail(cudaGetLastError(), "matrix fill kernel");
+  if (launch_matrix_fill(mf, p->stream) < 0) return launch_fail("matrix fill kernel");
   const size_t all_bytes = 5 * cc * sizeof(double);
   if (all_bytes <= stage_all()) {
     if (!p->h_mat) CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_mat), all_bytes));
@@ -953,9 +963,20 @@ int icikt_measure_smem_bandwidth(int32_t device, double* g32, double* g128) {
   int rc = select_device(device);
   if (rc != ICIKT_OK) return rc;
   double a = 0, b = 0;
-  if (measure_smem_bandwidth(&a, &b) < 0) return cuda_fail(cudaGetLastError(), "smem bandwidth kernel");
+  if (measure_smem_bandwidth(&a, &b) < 0) return launch_fail("smem bandwidth kernel");
   if (g32) *g32 = a;
   if (g128) *g128 = b;
+  return ICIKT_OK;
+}
+
+int icikt_measure_issue_rate(int32_t device, double* alu, double* fma, double* mixed) {
+  int rc = select_device(device);
+  if (rc != ICIKT_OK) return rc;
+  double a = 0, f = 0, m = 0;
+  if (measure_issue_rate(&a, &f, &m) < 0) return launch_fail("issue-rate kernel");
+  if (alu) *alu = a;
+  if (fma) *fma = f;
+  if (mixed) *mixed = m;
   return ICIKT_OK;
 }
 
@@ -1027,7 +1048,7 @@ int icikt_pairwise_completeness(const double* data, int64_t n, int64_t C, int64_
                        cudaMemcpyHostToDevice, b.stream));
   if (nlit) CK(cudaMemcpyAsync(b.lit, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, b.stream));
   if (launch_missing_bits(b.data, n, n, C, b.lit, nlit, na_nan, na_inf, b.bits, words, b.stream) < 0)
-    return cuda_fail(cudaGetLastError(), "missing-mask kernel");
+    return launch_fail("missing-mask kernel");
   if (per_pair) {
     if (pi) {
       CK(dmalloc(&b.pi, (size_t)P));
@@ -1038,136 +1059,151 @@ int icikt_pairwise_completeness(const double* data, int64_t n, int64_t C, int64_
     if (missing) CK(dmalloc(&b.miss, (size_t)P));
     if (completeness) CK(dmalloc(&b.comp, (size_t)P));
     if (launch_pair_missing(b.bits, words, n, C, b.pi, b.pj, P, b.miss, b.comp, b.stream) < 0)
-      return cuda_fail(cudaGetLastError(), "pair completeness kernel");
+      return launch_fail("pair completeness kernel");
     if (missing) CK(cudaMemcpyAsync(missing, b.miss, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, b.stream));
     if (completeness) CK(cudaMemcpyAsync(completeness, b.comp, sizeof(double) * P, cudaMemcpyDeviceToHost, b.stream));
   }
   if (matrix) {
     CK(dmalloc(&b.mat, (size_t)C * C));
     if (launch_missing_matrix(b.bits, words, n, C, b.mat, b.stream) < 0)
-      return cuda_fail(cudaGetLastError(), "completeness matrix kernel");
+      return launch_fail("completeness matrix kernel");
     CK(cudaMemcpyAsync(matrix, b.mat, sizeof(double) * C * C, cudaMemcpyDeviceToHost, b.stream));
   }
   CK(cudaStreamSynchronize(b.stream));
   return ICIKT_OK;
 }
 
-int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
-                          int32_t n_global_na, const icikt_opts* opts, const int32_t* devices,
-                          int32_t n_devices, double* raw, double* pvalue, double* taumax,
-                          double* completeness, int32_t* status, int64_t* counts, double* max_taumax,
-                          icikt_timings* timings) {
-  if (!data || !raw) return fail(ICIKT_ERR_BAD_ARG, "data and raw must not be NULL");
-  if (n_devices < 1 || n_devices > 64) return fail(ICIKT_ERR_BAD_ARG, "n_devices must be 1..64");
-  if (n < 1 || C < 1) return fail(ICIKT_ERR_BAD_ARG, "n and C must be >= 1");
+}  // extern "C"
+
+namespace {
+
+// One multi-device job: worker k (one host thread per device) owns the k-th contiguous slice of the
+// pair order.  Sharded preprocessing: if every pair of devices can reach each other directly (NVLink /
+// NVSwitch), device k uploads only its slice of the columns over its own PCIe link, runs K1 on that
+// slice and pulls the other slices of the per-column TABLES from its peers (an all-gather by peer
+// copies: K1 is not replicated and the raw matrix never travels between devices); otherwise every
+// device uploads the whole matrix and preprocesses all columns.
+struct MultiJob {
+  const double* data;
+  int64_t n, C, ld;
+  const double* global_na;
+  int32_t n_global_na;
   icikt_opts base;
-  if (opts) base = *opts; else icikt_default_opts(&base);
-  base.want_counts = counts ? 1 : 0;
-  const int64_t ptot = tri_pairs(C) + (base.include_diag ? C : 0);
-  std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached plans are not re-entrant
-  // Sharded preprocessing: if every pair of devices can reach each other directly (NVLink /
-  // NVSwitch), device k uploads only its slice of the columns over its own PCIe link, runs K1 on
-  // that slice and pulls the other slices of the per-column TABLES from its peers (an all-gather
-  // by peer copies: K1 is not replicated and the raw matrix never travels between devices);
-  // otherwise every device uploads the whole matrix and preprocesses all columns.
-  bool gather = n_devices >= 2 && C >= n_devices && ptot >= n_devices && !std::getenv("ICIKT_NO_PEER_GATHER");
-  for (int a = 0; gather && a < n_devices; ++a)
-    for (int b = 0; gather && b < n_devices; ++b) {
-      const int da = devices ? devices[a] : a, db = devices ? devices[b] : b;
+  const int32_t* devices;
+  int n_devices;
+  int64_t ptot;
+  bool peers_ok = false;  // every pair of distinct ordinals has peer access
+  bool gather = false;    // sharded K1 + peer gather of the tables
+  HostBarrier barrier;
+  std::vector<icikt_plan*> peer_plan;
+  explicit MultiJob(int nd) : n_devices(nd), barrier(nd), peer_plan((size_t)nd, nullptr) {}
+  int device_of(int k) const { return devices ? devices[k] : k; }
+  int64_t pair_lo(int k) const { return ptot * k / n_devices; }  // slices differ by at most one pair
+  int64_t col_lo(int k) const { return C * k / n_devices; }
+};
+
+void multi_probe_peers(MultiJob& J) {
+  bool distinct = true;
+  J.peers_ok = true;
+  for (int a = 0; a < J.n_devices; ++a)
+    for (int b = 0; b < J.n_devices; ++b) {
       if (a == b) continue;
+      const int da = J.device_of(a), db = J.device_of(b);
+      if (da == db) { distinct = false; continue; }
       int ok = 0;
-      if (da == db || cudaDeviceCanAccessPeer(&ok, da, db) != cudaSuccess || !ok) gather = false;
+      if (cudaDeviceCanAccessPeer(&ok, da, db) != cudaSuccess || !ok) J.peers_ok = false;
     }
   cudaGetLastError();
-  HostBarrier barrier(n_devices);
-  std::vector<icikt_plan*> peer_plan((size_t)n_devices, nullptr);
-  struct Work {
-    int rc = ICIKT_OK;
-    std::string err;
-    double mx = std::nan("");
-    icikt_timings tm{};
-  };
-  std::vector<Work> work((size_t)n_devices);
-  std::vector<std::thread> threads;
-  for (int k = 0; k < n_devices; ++k) {
-    threads.emplace_back([&, k]() {
-      Work& w = work[(size_t)k];
-      icikt_opts o = base;
-      o.device = devices ? devices[k] : k;
-      o.pair_lo = ptot * k / n_devices;  // contiguous slices that differ by at most one pair
-      o.pair_hi = ptot * (k + 1) / n_devices;
-      const int64_t lo = o.pair_lo, cnt = o.pair_hi - o.pair_lo;
-      // one cached plan per slot, like the one-shot entry points: repeated calls of the same
-      // shape do not pay the device allocations again
-      icikt_plan*& slot = g_cached_multi[k];
-      icikt_plan* p = nullptr;
-      if (cache_matches(slot, n, C, o) && (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || slot->d_pw)) {
-        p = slot;
-        p->opts.perspective = o.perspective;
-        p->opts.alternative = o.alternative;
-        p->opts.continuity = o.continuity;
-        p->opts.na_inf = o.na_inf;
-      } else {
-        if (slot) { icikt_plan_destroy(slot); slot = nullptr; }
-        w.rc = icikt_plan_create(&p, n, C, nullptr, nullptr, 0, &o);
-        if (w.rc == ICIKT_OK) slot = p;
-      }
-      if (!gather) {
-        if (cnt <= 0) return;
-        if (w.rc == ICIKT_OK) w.rc = icikt_plan_upload(p, data, ld);
-        if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns(p, global_na, n_global_na);
-      } else {
-        // every worker passes both barriers whatever happened to it, so nobody is left waiting
-        const auto col_lo = [&](int j) { return C * j / n_devices; };
-        if (w.rc == ICIKT_OK) w.rc = upload_columns(p, data, ld, col_lo(k), col_lo(k + 1));
-        if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns_range(p, global_na, n_global_na, col_lo(k), col_lo(k + 1));
-        if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "column slice");
-        peer_plan[(size_t)k] = (w.rc == ICIKT_OK) ? p : nullptr;
-        barrier.wait();  // every slice of the tables is complete on its device
-        bool all_ok = true;
-        for (int j = 0; j < n_devices; ++j) all_ok = all_ok && peer_plan[(size_t)j] != nullptr;
-        if (w.rc == ICIKT_OK && !all_ok) w.rc = fail(ICIKT_ERR_CUDA, "a peer device failed to preprocess its slice");
-        if (w.rc == ICIKT_OK) {
-          icikt_table mine[ICIKT_MAX_TABLES], theirs[ICIKT_MAX_TABLES];
-          const int nt = icikt_plan_tables(p, mine, ICIKT_MAX_TABLES);
-          for (int j = 0; j < n_devices && w.rc == ICIKT_OK; ++j) {
-            if (j == k) continue;
-            const int dj = devices ? devices[j] : j;
-            const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { w.rc = cuda_fail(e, "cudaDeviceEnablePeerAccess"); break; }
-            cudaGetLastError();
-            icikt_plan_tables(peer_plan[(size_t)j], theirs, ICIKT_MAX_TABLES);
-            for (int t = 0; t < nt && w.rc == ICIKT_OK; ++t) {
-              const size_t off = (size_t)col_lo(j) * (size_t)mine[t].bytes_per_column;
-              const size_t len = (size_t)(col_lo(j + 1) - col_lo(j)) * (size_t)mine[t].bytes_per_column;
-              if (len && cudaMemcpyPeerAsync(static_cast<unsigned char*>(mine[t].ptr) + off, o.device,
-                                             static_cast<const unsigned char*>(theirs[t].ptr) + off, dj, len,
-                                             p->stream) != cudaSuccess)
-                w.rc = cuda_fail(cudaGetLastError(), "cudaMemcpyPeerAsync");
-            }
-          }
-          if (w.rc == ICIKT_OK) w.rc = icikt_plan_columns_finish(p);
-          if (w.rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) w.rc = cuda_fail(cudaGetLastError(), "peer gather");
-        }
-        barrier.wait();  // nobody's tables are touched (or freed) before every pull has finished
-        if (cnt <= 0) return;
-      }
-      if (w.rc == ICIKT_OK) w.rc = icikt_plan_pairs(p);
-      if (w.rc == ICIKT_OK)
-        w.rc = icikt_plan_download(p, raw + lo, pvalue ? pvalue + lo : nullptr, taumax ? taumax + lo : nullptr,
-                                   completeness ? completeness + lo : nullptr, status ? status + lo : nullptr,
-                                   counts ? counts + lo * ICIKT_NCOUNTS : nullptr, &w.mx);
-      if (w.rc == ICIKT_OK) w.rc = icikt_plan_timings(p, &w.tm);
-      if (w.rc != ICIKT_OK) {
-        w.err = g_err;  // thread-local message of this worker
-        if (slot) { icikt_plan_destroy(slot); slot = nullptr; }
-      }
-    });
+  J.gather = J.n_devices >= 2 && distinct && J.peers_ok && J.C >= J.n_devices && J.ptot >= J.n_devices &&
+             !std::getenv("ICIKT_NO_PEER_GATHER");
+}
+
+int enable_peers(const MultiJob& J, int k) {
+  for (int j = 0; j < J.n_devices; ++j) {
+    if (J.device_of(j) == J.device_of(k)) continue;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(J.device_of(j), 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    cudaGetLastError();
   }
-  for (auto& t : threads) t.join();
+  return ICIKT_OK;
+}
+
+// Worker k up to and including the pair kernel + epilogue (results stay on its device).  In gather mode
+// every worker passes both barriers whatever happened to it, so nobody is left waiting.
+int multi_worker_pairs(MultiJob& J, int k, icikt_plan** out) {
+  int rc = ICIKT_OK;
+  icikt_opts o = J.base;
+  o.device = J.device_of(k);
+  o.pair_lo = J.pair_lo(k);
+  o.pair_hi = J.pair_lo(k + 1);
+  const int64_t cnt = o.pair_hi - o.pair_lo;
+  // one cached plan per slot, like the one-shot entry points: repeated calls of the same shape do not
+  // pay the device allocations again
+  icikt_plan*& slot = g_cached_multi[k];
+  icikt_plan* p = nullptr;
+  if (cache_matches(slot, J.n, J.C, o) && (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || slot->d_pw)) {
+    p = slot;
+    p->opts.perspective = o.perspective;
+    p->opts.alternative = o.alternative;
+    p->opts.continuity = o.continuity;
+    p->opts.na_inf = o.na_inf;
+  } else {
+    if (slot) { icikt_plan_destroy(slot); slot = nullptr; }
+    rc = icikt_plan_create(&p, J.n, J.C, nullptr, nullptr, 0, &o);
+    if (rc == ICIKT_OK) slot = p;
+  }
+  *out = p;
+  if (!J.gather) {
+    if (cnt <= 0) return rc;
+    if (rc == ICIKT_OK) rc = icikt_plan_upload(p, J.data, J.ld);
+    if (rc == ICIKT_OK) rc = icikt_plan_columns(p, J.global_na, J.n_global_na);
+  } else {
+    if (rc == ICIKT_OK) rc = upload_columns(p, J.data, J.ld, J.col_lo(k), J.col_lo(k + 1));
+    if (rc == ICIKT_OK) rc = icikt_plan_columns_range(p, J.global_na, J.n_global_na, J.col_lo(k), J.col_lo(k + 1));
+    if (rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "column slice");
+    J.peer_plan[(size_t)k] = (rc == ICIKT_OK) ? p : nullptr;
+    J.barrier.wait();  // every slice of the tables is complete on its device
+    bool all_ok = true;
+    for (int j = 0; j < J.n_devices; ++j) all_ok = all_ok && J.peer_plan[(size_t)j] != nullptr;
+    if (rc == ICIKT_OK && !all_ok) rc = fail(ICIKT_ERR_CUDA, "a peer device failed to preprocess its slice");
+    if (rc == ICIKT_OK) rc = enable_peers(J, k);
+    if (rc == ICIKT_OK) {
+      icikt_table mine[ICIKT_MAX_TABLES], theirs[ICIKT_MAX_TABLES];
+      const int nt = icikt_plan_tables(p, mine, ICIKT_MAX_TABLES);
+      for (int j = 0; j < J.n_devices && rc == ICIKT_OK; ++j) {
+        if (j == k) continue;
+        icikt_plan_tables(J.peer_plan[(size_t)j], theirs, ICIKT_MAX_TABLES);
+        for (int t = 0; t < nt && rc == ICIKT_OK; ++t) {
+          const size_t off = (size_t)J.col_lo(j) * (size_t)mine[t].bytes_per_column;
+          const size_t len = (size_t)(J.col_lo(j + 1) - J.col_lo(j)) * (size_t)mine[t].bytes_per_column;
+          if (len && cudaMemcpyPeerAsync(static_cast<unsigned char*>(mine[t].ptr) + off, o.device,
+                                         static_cast<const unsigned char*>(theirs[t].ptr) + off, J.device_of(j), len,
+                                         p->stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "cudaMemcpyPeerAsync");
+        }
+      }
+      if (rc == ICIKT_OK) rc = icikt_plan_columns_finish(p);
+      if (rc == ICIKT_OK && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "peer gather");
+    }
+    J.barrier.wait();  // nobody's tables are touched (or freed) before every pull has finished
+    if (cnt <= 0) return rc;
+  }
+  if (rc == ICIKT_OK) rc = icikt_plan_pairs(p);
+  return rc;
+}
+
+struct MultiWork {
+  int rc = ICIKT_OK;
+  std::string err;
+  double mx = std::nan("");
+  icikt_timings tm{};
+  unsigned long long hist[16] = {};
+};
+
+int multi_collect(const std::vector<MultiWork>& work, double* max_taumax, icikt_timings* timings) {
   double mx = std::nan("");
   icikt_timings slowest{};
-  for (const Work& w : work) {
+  for (const MultiWork& w : work) {
     if (w.rc != ICIKT_OK) return fail(w.rc, w.err);
     if (w.mx == w.mx && !(mx >= w.mx)) mx = w.mx;
     if (w.tm.total_ms >= slowest.total_ms) {
@@ -1180,6 +1216,188 @@ int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, 
   }
   if (max_taumax) *max_taumax = mx;
   if (timings) *timings = slowest;
+  return ICIKT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int icikt_all_pairs_multi(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                          int32_t n_global_na, const icikt_opts* opts, const int32_t* devices,
+                          int32_t n_devices, double* raw, double* pvalue, double* taumax,
+                          double* completeness, int32_t* status, int64_t* counts, double* max_taumax,
+                          icikt_timings* timings) {
+  if (!data || !raw) return fail(ICIKT_ERR_BAD_ARG, "data and raw must not be NULL");
+  if (n_devices < 1 || n_devices > 64) return fail(ICIKT_ERR_BAD_ARG, "n_devices must be 1..64");
+  if (n < 1 || C < 1) return fail(ICIKT_ERR_BAD_ARG, "n and C must be >= 1");
+  MultiJob J(n_devices);
+  J.data = data; J.n = n; J.C = C; J.ld = ld; J.global_na = global_na; J.n_global_na = n_global_na;
+  J.devices = devices;
+  if (opts) J.base = *opts; else icikt_default_opts(&J.base);
+  J.base.want_counts = counts ? 1 : 0;
+  J.ptot = tri_pairs(C) + (J.base.include_diag ? C : 0);
+  std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached plans are not re-entrant
+  multi_probe_peers(J);
+  std::vector<MultiWork> work((size_t)n_devices);
+  std::vector<std::thread> threads;
+  for (int k = 0; k < n_devices; ++k) {
+    threads.emplace_back([&, k]() {
+      MultiWork& w = work[(size_t)k];
+      icikt_plan* p = nullptr;
+      w.rc = multi_worker_pairs(J, k, &p);
+      const int64_t lo = J.pair_lo(k), cnt = J.pair_lo(k + 1) - lo;
+      if (w.rc == ICIKT_OK && cnt > 0)
+        w.rc = icikt_plan_download(p, raw + lo, pvalue ? pvalue + lo : nullptr, taumax ? taumax + lo : nullptr,
+                                   completeness ? completeness + lo : nullptr, status ? status + lo : nullptr,
+                                   counts ? counts + lo * ICIKT_NCOUNTS : nullptr, &w.mx);
+      if (w.rc == ICIKT_OK && cnt > 0) w.rc = icikt_plan_timings(p, &w.tm);
+      if (w.rc != ICIKT_OK) {
+        w.err = g_err;  // thread-local message of this worker
+        if (g_cached_multi[k]) { icikt_plan_destroy(g_cached_multi[k]); g_cached_multi[k] = nullptr; }
+      }
+    });
+  }
+  for (auto& t : threads) t.join();
+  return multi_collect(work, max_taumax, timings);
+}
+
+int icikt_matrices_multi(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                         int32_t n_global_na, const icikt_opts* opts, const int32_t* devices, int32_t n_devices,
+                         int32_t scale_max, int32_t diag_good, const int32_t* n_good, double* cor, double* raw,
+                         double* pvalue, double* taumax, double* completeness, int64_t* status_counts,
+                         double* max_taumax, icikt_timings* timings) {
+  if (!data) return fail(ICIKT_ERR_BAD_ARG, "data must not be NULL");
+  if (n_devices < 1 || n_devices > kMaxMatrixDevices) return fail(ICIKT_ERR_BAD_ARG, "n_devices must be 1..16");
+  if (n < 1 || C < 1) return fail(ICIKT_ERR_BAD_ARG, "n and C must be >= 1");
+  icikt_opts base;
+  if (opts) base = *opts; else icikt_default_opts(&base);
+  base.include_diag = diag_good ? 0 : 1;  // setup_comparisons, R/kendalltau.R:191-194
+  base.pair_lo = base.pair_hi = 0;
+  const int64_t ptot = tri_pairs(C) + (base.include_diag ? C : 0);
+  MultiJob J(n_devices);
+  J.data = data; J.n = n; J.C = C; J.ld = ld; J.global_na = global_na; J.n_global_na = n_global_na;
+  J.devices = devices; J.base = base; J.base.want_counts = 0; J.ptot = ptot;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    multi_probe_peers(J);
+  }
+  if (n_devices == 1 || !J.peers_ok || ptot < n_devices || C < n_devices) {
+    // one device, or devices that cannot read each other's results: the single-device path
+    base.device = J.device_of(0);
+    return icikt_matrices(data, n, C, ld, global_na, n_global_na, nullptr, nullptr, 0, &base, scale_max, diag_good, n_good,
+                          cor, raw, pvalue, taumax, completeness, status_counts, max_taumax, timings);
+  }
+  std::lock_guard<std::mutex> lock(g_cache_mu);  // the cached plans are not re-entrant
+  double* outs[5] = {cor, raw, pvalue, taumax, completeness};
+  std::vector<MultiWork> work((size_t)n_devices);
+  std::vector<int32_t> good((size_t)C, 0);
+  if (n_good) std::copy(n_good, n_good + C, good.begin());
+  std::vector<icikt_plan*> plans((size_t)n_devices, nullptr);
+  std::vector<std::thread> threads;
+  for (int k = 0; k < n_devices; ++k) {
+    threads.emplace_back([&, k]() {
+      MultiWork& w = work[(size_t)k];
+      icikt_plan* p = nullptr;
+      w.rc = multi_worker_pairs(J, k, &p);
+      unsigned long long bits = 0;
+      if (w.rc == ICIKT_OK) {
+        if (cudaMemcpyAsync(&bits, p->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess ||
+            cudaStreamSynchronize(p->stream) != cudaSuccess)
+          w.rc = cuda_fail(cudaGetLastError(), "pair kernel");
+      }
+      if (w.rc == ICIKT_OK && bits) std::memcpy(&w.mx, &bits, sizeof(bits));
+      if (w.rc == ICIKT_OK && k == 0 && diag_good && !n_good) {  // n_good = n - missing rows (R/kendalltau.R:165)
+        w.rc = icikt_plan_column_info(p, good.data());
+        for (int64_t c = 0; c < C && w.rc == ICIKT_OK; ++c) good[(size_t)c] = (int32_t)n - good[(size_t)c];
+      }
+      plans[(size_t)k] = (w.rc == ICIKT_OK) ? p : nullptr;
+      J.barrier.wait();  // every slice of the pair results is complete on its device
+      bool all_ok = true;
+      double mx = std::nan("");
+      for (int j = 0; j < n_devices; ++j) {
+        all_ok = all_ok && plans[(size_t)j] != nullptr;
+        if (work[(size_t)j].mx == work[(size_t)j].mx && !(mx >= work[(size_t)j].mx)) mx = work[(size_t)j].mx;
+      }
+      if (w.rc == ICIKT_OK && !all_ok) w.rc = fail(ICIKT_ERR_CUDA, "a peer device failed to compute its pairs");
+      if (w.rc == ICIKT_OK) w.rc = enable_peers(J, k);
+      if (w.rc == ICIKT_OK) w.rc = [&]() -> int {
+        const int64_t c_lo = J.col_lo(k), c_hi = J.col_lo(k + 1);
+        const size_t blk = (size_t)C * (size_t)(c_hi - c_lo);
+        CK(cudaSetDevice(p->device));
+        if (p->mat_elems < 5 * blk) {
+          cudaFree(p->d_mat);
+          p->d_mat = nullptr;
+          p->mat_elems = 0;
+          if (dmalloc(&p->d_mat, 5 * blk) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ICIKT_ERR_ALLOC, "device allocation of the result matrix block failed");
+          }
+          p->mat_elems = 5 * blk;
+        }
+        if (!p->d_hist) CK(dmalloc(&p->d_hist, 16));
+        if (!p->d_ngood) CK(dmalloc(&p->d_ngood, (size_t)C));
+        if (!p->h_stage[0]) {
+          p->stage_bytes = stage_chunk();
+          for (int i = 0; i < 2; ++i) {
+            CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_stage[i]), p->stage_bytes));
+            CK(cudaEventCreateWithFlags(&p->stage_ev[i], cudaEventDisableTiming));
+          }
+        }
+        CK(cudaEventRecord(p->ev[6], p->stream));
+        CK(cudaMemsetAsync(p->d_hist, 0, 16 * sizeof(unsigned long long), p->stream));
+        BlockFill f{};
+        f.n_dev = n_devices;
+        for (int j = 0; j < n_devices; ++j) {
+          const icikt_plan* q = plans[(size_t)j];
+          f.tau[j] = q->d_tau; f.pvalue[j] = q->d_p; f.taumax[j] = q->d_tm; f.completeness[j] = q->d_comp;
+          f.status[j] = q->d_status;
+          f.pair_lo[j] = J.pair_lo(j);
+        }
+        f.pair_lo[n_devices] = ptot;
+        f.n = n; f.C = C; f.c_lo = c_lo; f.c_hi = c_hi;
+        f.scale_max = scale_max != 0; f.diag_good = diag_good != 0;
+        f.max_taumax = mx;
+        f.n_good = p->d_ngood;
+        int best = 1;
+        if (diag_good) {
+          CK(cudaMemcpyAsync(p->d_ngood, good.data(), sizeof(int32_t) * (size_t)C, cudaMemcpyHostToDevice, p->stream));
+          best = 0;
+          for (int64_t c = 0; c < C; ++c) best = std::max(best, good[(size_t)c]);
+        }
+        f.best_good = best;
+        for (int q = 0; q < 5; ++q) f.m[q] = outs[q] ? p->d_mat + (size_t)q * blk : nullptr;
+        f.hist = p->d_hist;
+        if (launch_matrix_block_fill(f, p->stream) < 0) return launch_fail("matrix block fill kernel");
+        for (int q = 0; q < 5; ++q)
+          if (outs[q] && blk) {
+            const int r2 = staged_copy_out(p, outs[q] + (size_t)c_lo * (size_t)C, f.m[q], sizeof(double) * blk);
+            if (r2 != ICIKT_OK) return r2;
+          }
+        CK(cudaMemcpyAsync(w.hist, p->d_hist, sizeof(w.hist), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaEventRecord(p->ev[7], p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        return icikt_plan_timings(p, &w.tm);
+      }();
+      J.barrier.wait();  // nobody's results are freed before every block has been filled
+      if (w.rc != ICIKT_OK) {
+        w.err = g_err;
+        if (g_cached_multi[k]) { icikt_plan_destroy(g_cached_multi[k]); g_cached_multi[k] = nullptr; }
+      }
+    });
+  }
+  for (auto& t : threads) t.join();
+  const int rc = multi_collect(work, max_taumax, timings);
+  if (rc != ICIKT_OK) return rc;
+  if (status_counts) {
+    int64_t bad = 0;
+    for (int q = 1; q < ICIKT_NSTATUS; ++q) {
+      status_counts[q] = 0;
+      for (const MultiWork& w : work) status_counts[q] += (int64_t)w.hist[q];
+      bad += status_counts[q];
+    }
+    status_counts[0] = ptot - bad;
+  }
   return ICIKT_OK;
 }
 

@@ -1,19 +1,23 @@
 // icikt_columns.cu -- K1: per-column preprocessing, done once per column instead of twice per
 // pair as in the reference.
 //
-//   build_keys_kernel   setup_missing_matrix (R/utils.R:1-23) + the NA -> "below the minimum"
+//   keys                setup_missing_matrix (R/utils.R:1-23) + the NA -> "below the minimum"
 //                       substitution of src/kendallc.cpp:214-219, expressed as a sort key:
 //                       missing rows get key 0, every other value an order-preserving 64-bit
 //                       image of the double (-0.0 == +0.0, as compare_self :15-31 sees them).
-//   segmented sort      sortedIndex (src/kendallc.cpp:6-12), one segment per column
-//                       (cub::DeviceSegmentedSort; stability is irrelevant because rows of a
-//                       tie group are interchangeable for every downstream count).
-//   column_rank_kernel  compare_self + cumsum (:15-31, :250-251) -> dense ranks; tie-group
+//   sort                sortedIndex (src/kendallc.cpp:6-12): a CTA-wide LSD radix ARGSORT written
+//                       here (radix_pass below): 4-bit digits, the rows' keys stay where they are
+//                       and only the 16-bit row ids move; every thread counts the digits of its own
+//                       contiguous slice of the current order in byte counters, one flat scan over
+//                       the [digit][thread] counters makes the pass stable.  Stability itself is
+//                       irrelevant downstream (rows of a tie group are interchangeable for every
+//                       count) but is what makes LSD passes compose.
+//   ranks and tables    compare_self + cumsum (:15-31, :250-251) -> dense ranks; tie-group
 //                       sizes -> count_rank_tie sums (:103-118) in exact int64; the bit masks
 //                       and the tied-row list (rows + dense group index) the pair kernel needs.
-#include <cub/block/block_merge_sort.cuh>
-#include <cub/device/device_segmented_sort.cuh>
-
+//   Three shapes: n <= 8192 one fused kernel per column (keys in shared memory, everything else in
+//   registers); n <= 22528 sort kernel with the keys' 32-bit halves and both row-id buffers in
+//   shared memory + rank kernel; longer columns the same sort on global (L2-resident) buffers.
 #include <algorithm>
 #include <cstdlib>
 
@@ -33,25 +37,6 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
 __device__ __forceinline__ double key_value(unsigned long long k) {
   const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
   return __longlong_as_double((long long)b);
-}
-
-__global__ void __launch_bounds__(256)
-    build_keys_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
-                      const double* __restrict__ global_na, int n_global_na, int na_inf,
-                      unsigned long long* __restrict__ keys, uint16_t* __restrict__ vals,
-                      uint32_t* __restrict__ nabits, const int col0) {
-  const int col = blockIdx.y + col0;
-  const int r = blockIdx.x * 256 + threadIdx.x;
-  bool miss = false;
-  if (r < n) {
-    const double v = data[(size_t)col * ld + r];
-    miss = (v != v) || (na_inf && isinf(v));
-    for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
-    keys[(size_t)col * nstride + r] = miss ? 0ull : order_key(v);
-    vals[(size_t)col * nstride + r] = (uint16_t)r;
-  }
-  const uint32_t m = __ballot_sync(FULL, miss);
-  if ((threadIdx.x & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
 }
 
 // block-wide exclusive scan of one int per thread; returns the exclusive prefix, sets total
@@ -122,17 +107,162 @@ __device__ __forceinline__ void block_sum_ll4(long long& a, long long& b, long l
   __syncthreads();
 }
 
+// ---- CTA-wide LSD radix argsort (sortedIndex, src/kendallc.cpp:6-12) ------------------------
+// One pass on one 4-bit digit of the keys.  The keys stay in place: `src + (row << stride_shift)`
+// addresses the key of a row (shared or global memory, generic loads), `shift` is the digit's bit
+// position; `in` is the current order of the 16-bit row ids (nullptr = identity), `out` receives the
+// order refined by this digit.  Thread t owns the contiguous positions [t*I, (t+1)*I) of the current
+// order (I = ceil(n / T)), so "digit-major, thread-minor, position inside the thread" is the stable
+// output order and no warp-level cooperation (match / ballot) is needed:
+//   sweep 1  cnt8[d][t]++ for the thread's keys (one byte per digit and thread; the row [d][.] of a
+//            warp is 32 consecutive bytes: conflict-free);
+//   scan     the counters in memory order ARE the output order: every thread folds 16 consecutive
+//            bytes (one 128-bit load), one block scan, 16 exclusive prefixes go to pre16;
+//   sweep 2  a key goes to pre16[d][t]++.
+// Returns false without writing `out` when every key has the same digit (the order is unchanged):
+// count data and other low-entropy columns skip most of their passes.
+// cnt8: 16*T bytes, pre16: 16*T u16, misc: 64 words.  I <= 255.
+__device__ __forceinline__ bool radix_pass(const unsigned char* src, const int stride_shift,
+                                           const int shift, const uint16_t* in, uint16_t* out, const int n,
+                                           unsigned char* cnt8, uint16_t* pre16, uint32_t* misc, const int T) {
+  // T sorting threads (a multiple of 32, <= blockDim.x): a pass costs every thread a fixed ~300
+  // instructions on top of ~25 per key, so short columns are sorted by fewer threads with more keys
+  // each; the other threads only keep the barriers
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+  const bool on = tid < T;
+  const int I = (n + T - 1) / T;
+  const int p0 = on ? min(tid * I, n) : n, p1 = min(p0 + I, n);
+  const int boff = shift >> 3, bsh = shift & 4;
+  if (on) {  // zero this thread's 16 counters' worth of the array (128 bits per thread)
+    uint4* z = reinterpret_cast<uint4*>(cnt8);
+    z[tid] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (tid == 0) misc[8] = 0u;
+  __syncthreads();
+  const uint32_t d0 = (src[((size_t)(in ? (uint32_t)in[0] : 0u) << stride_shift) + boff] >> bsh) & 15u;
+  bool differs = false;
+  unsigned char* mycnt = cnt8 + tid;
+  for (int p = p0; p < p1; p += 4) {
+    uint32_t d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      d[u] = 16u;
+      if (p + u < p1) {
+        const uint32_t row = in ? (uint32_t)in[p + u] : (uint32_t)(p + u);
+        d[u] = (src[((size_t)row << stride_shift) + boff] >> bsh) & 15u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (d[u] < 16u) {
+        differs = differs || d[u] != d0;
+        mycnt[d[u] * T] += 1;
+      }
+  }
+  if (__any_sync(FULL, differs) && lane == 0) misc[8] = 1u;
+  __syncthreads();
+  if (misc[8] == 0u) {  // a single digit value
+    __syncthreads();    // misc is rewritten by the next pass
+    return false;
+  }
+  {
+    const uint4 c = on ? reinterpret_cast<const uint4*>(cnt8)[tid] : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t h = (w[j] & 0x00ff00ffu) + ((w[j] >> 8) & 0x00ff00ffu);
+      sum += (h & 0xffffu) + (h >> 16);
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int s2 = 1; s2 < 32; s2 <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, s2);
+      if (lane >= s2) incl += t;
+    }
+    if (on && lane == 31) misc[16 + warp] = incl;
+    __syncthreads();
+    const uint32_t wv = lane < W ? misc[16 + lane] : 0u;
+    uint32_t wincl = wv;
+#pragma unroll
+    for (int s2 = 1; s2 < 32; s2 <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, wincl, s2);
+      if (lane >= s2) wincl += t;
+    }
+    uint32_t run = __shfl_sync(FULL, wincl - wv, warp & 31) + incl - sum;
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int b = 0; b < 4; b += 2) {
+        const uint32_t lo = run;
+        run += (w[j] >> (8 * b)) & 0xffu;
+        const uint32_t hi = run;
+        run += (w[j] >> (8 * b + 8)) & 0xffu;
+        o[2 * j + (b >> 1)] = lo | (hi << 16);
+      }
+    }
+    if (on) {
+      uint4* pr = reinterpret_cast<uint4*>(pre16) + 2 * tid;
+      pr[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      pr[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  __syncthreads();
+  uint16_t* mypre = pre16 + tid;
+  for (int p = p0; p < p1; p += 4) {
+    uint32_t d[4], row[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      d[u] = 16u;
+      row[u] = 0u;
+      if (p + u < p1) {
+        row[u] = in ? (uint32_t)in[p + u] : (uint32_t)(p + u);
+        d[u] = (src[((size_t)row[u] << stride_shift) + boff] >> bsh) & 15u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (d[u] < 16u) {
+        const uint32_t slot = mypre[d[u] * T];
+        mypre[d[u] * T] = (uint16_t)(slot + 1u);
+        out[slot] = (uint16_t)row[u];
+      }
+  }
+  __syncthreads();
+  return true;
+}
+
+// Sorts the rows of one column by the `nbits` key bits starting at bit0 (least significant digit
+// first); bufA / bufB ping-pong.  `cur` carries the order between calls (nullptr = identity).
+__device__ __forceinline__ const uint16_t* radix_argsort(const unsigned char* src, int stride_shift, int bit0,
+                                                         int nbits, const uint16_t* cur, uint16_t* bufA,
+                                                         uint16_t* bufB, int n, unsigned char* cnt8,
+                                                         uint16_t* pre16, uint32_t* misc, int T) {
+  for (int b = bit0; b < bit0 + nbits; b += 4) {
+    uint16_t* out = (cur == bufA) ? bufB : bufA;
+    if (radix_pass(src, stride_shift, b, cur, out, n, cnt8, pre16, misc, T)) cur = out;
+  }
+  return cur;
+}
+
+// sorting threads for a column of n rows in a CTA of `threads`: about 16 keys per thread
+__host__ __device__ inline int sort_threads(int n, int threads) {
+  int t = 128;
+  while (t < threads && t * 16 < n) t <<= 1;
+  return t < threads ? t : threads;
+}
+
+// counters of the sort: cnt8 [16][T] bytes, pre16 [16][T] u16, misc 64 words
+__host__ __device__ inline size_t sort_counter_bytes(int threads) { return 48 * (size_t)threads + 256; }
+
 // Short columns (n <= 8192): the WHOLE per-column preprocessing in one kernel, one CTA per
 // column, every sorted position held in registers (thread t owns positions t*ITEMS ..).
-//   missing marking + order-preserving keys   (build_keys_kernel)
-//   sort                                      (cub::BlockMergeSort in shared memory)
-//   dense ranks, tie sums, first-group mask, tied-row list, statistics   (column_rank_kernel)
-// Replaces six launches (~150 us for 100 columns of 5 000 rows, two thirds of it in
-// cub::DeviceSegmentedSort) where the per-column work is a visible share of the whole job.
-// Each phase is one pass over the registers plus one block scan.
-struct KeyLess {
-  __device__ __forceinline__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
-};
+//   missing marking + order-preserving keys   (64-bit keys parked in shared memory)
+//   sort                                      (radix_argsort on the row ids, up to 8 byte passes)
+//   dense ranks, tie sums, first-group mask, tied-row list, statistics   (as column_rank_kernel)
+// One launch instead of three where the per-column work is a visible share of the whole job.
+// Each phase after the sort is one pass over the registers plus one block scan.
 template <int SORT_THREADS, int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS)
     column_fused_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
@@ -143,7 +273,6 @@ __global__ void __launch_bounds__(SORT_THREADS)
                         uint16_t* __restrict__ lgrp, ColStats* __restrict__ stats,
                         int32_t* __restrict__ max_tied, uint32_t* __restrict__ tord, const PipeConst pc,
                         const int large_tie, const int direct_budget, const int col0) {
-  using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char sort_smem[];
   __shared__ int warp_sums[32];
@@ -151,28 +280,44 @@ __global__ void __launch_bounds__(SORT_THREADS)
   __shared__ unsigned long long mnkey;
   __shared__ int n_large;
   __shared__ uint32_t descA[32], descB[32];
-  typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(sort_smem);
   const int col = blockIdx.x + col0, tid = threadIdx.x;
   if (tid == 0) n_large = 0;
   unsigned long long keys[ITEMS];
   uint16_t vals[ITEMS];
+  {
+    // sort-time layout: [CAP] 64-bit keys by row, two [CAP] row-id buffers, the pass counters
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sort_smem);
+    uint16_t* idA = reinterpret_cast<uint16_t*>(sort_smem + 8 * (size_t)CAP);
+    uint16_t* idB = idA + CAP;
+    unsigned char* cnt8 = sort_smem + 12 * (size_t)CAP;
+    uint16_t* pre16 = reinterpret_cast<uint16_t*>(cnt8 + 16 * SORT_THREADS);
+    uint32_t* smisc = reinterpret_cast<uint32_t*>(cnt8 + 48 * SORT_THREADS);
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {  // striped: a warp reads 32 consecutive rows
-    const int r = i * SORT_THREADS + tid;
-    bool miss = false;
-    unsigned long long k = ~0ull;  // padding sorts last; no value maps to all-ones (NaN is missing)
-    if (r < n) {
-      const double v = data[(size_t)col * ld + r];
-      miss = (v != v) || (na_inf && isinf(v));
-      for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
-      k = miss ? 0ull : order_key(v);
+    for (int i = 0; i < ITEMS; ++i) {  // striped: a warp reads 32 consecutive rows
+      const int r = i * SORT_THREADS + tid;
+      bool miss = false;
+      if (r < n) {
+        const double v = data[(size_t)col * ld + r];
+        miss = (v != v) || (na_inf && isinf(v));
+        for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
+        skey[r] = miss ? 0ull : order_key(v);
+      }
+      const uint32_t m = __ballot_sync(FULL, miss);
+      if ((tid & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
     }
-    keys[i] = k;
-    vals[i] = (uint16_t)r;
-    const uint32_t m = __ballot_sync(FULL, miss);
-    if ((tid & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
+    __syncthreads();
+    const uint16_t* cur = radix_argsort(reinterpret_cast<const unsigned char*>(skey), 3, 0, 64, nullptr, idA, idB, n,
+                                        cnt8, pre16, smisc, sort_threads(n, SORT_THREADS));
+    // blocked arrangement: thread t takes sorted positions t*ITEMS .. (padding sorts last; no value
+    // maps to the all-ones key, NaN being missing)
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const int t = tid * ITEMS + i;
+      const uint32_t row = (t < n) ? (cur ? (uint32_t)cur[t] : (uint32_t)t) : 0u;
+      vals[i] = (uint16_t)row;
+      keys[i] = (t < n) ? skey[row] : ~0ull;
+    }
   }
-  Sort(temp).Sort(keys, vals, KeyLess());
   __syncthreads();  // the sort's shared memory is reused below
   unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(sort_smem);           // [SORT_THREADS]
   uint16_t* gpos = reinterpret_cast<uint16_t*>(sort_smem + 8 * SORT_THREADS);                // [CAP + 2]
@@ -394,22 +539,85 @@ template <int SORT_THREADS, int ITEMS>
 int launch_column_fused(const double* d_data, int64_t ld, const double* d_global_na, int n_global_na, int na_inf,
                         ColumnTables& tab, cudaStream_t stream, int large_tie, int direct_budget, int col0,
                         int ncols) {
-  using Sort = cub::BlockMergeSort<unsigned long long, SORT_THREADS, ITEMS, uint16_t>;
   constexpr int CAP = SORT_THREADS * ITEMS;
+  const size_t sort_bytes = 12 * (size_t)CAP + sort_counter_bytes(SORT_THREADS);  // keys, two row-id buffers, counters
   const size_t post = 8 * SORT_THREADS + ((2 * (CAP + 2) + 15) & ~15) + 4 * ((CAP / 32 + 3) & ~3) + 4 * (size_t)CAP;
   const size_t pass_a = 2 * 2 * (size_t)SORT_THREADS * 8;  // two u16 buffers of 8 keys per thread
-  const size_t smem = std::max(std::max(sizeof(typename Sort::TempStorage), post), pass_a);
-  PipeConst pc;
-  pc.one = 1u;
-  pc.two = 2u;
-  pc.c64k = 65536u;
+  const size_t smem = std::max(std::max(sort_bytes, post), pass_a);
+  const PipeConst pc = make_pipe_const();
   auto kern = column_fused_kernel<SORT_THREADS, ITEMS>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  // the architectural maximum less the kernel's static shared memory (a fixed value, so that host
+  // threads driving different shapes on one device cannot shrink it under each other)
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) return -1;
   kern<<<(unsigned)ncols, SORT_THREADS, smem, stream>>>(d_data, ld, (int)tab.n, (int)tab.nstride, (int)tab.wstride,
                                                         d_global_na, n_global_na, na_inf, tab.perm, tab.rank,
                                                         tab.trow, tab.trun, tab.tend, tab.nabits, tab.firstbits, tab.gstart,
                                                         (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied, tab.tord, pc, large_tie, direct_budget, col0);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
+}
+
+// Long columns (n > 8192): keys + sort in one kernel, one 1024-thread CTA per column.
+//   SM = true  (n <= kSortSmemRows): the keys' 32-bit halves (low half first, then the high half:
+//              4 + 4 byte passes) and both row-id buffers live in shared memory, 8 bytes per row;
+//   SM = false (longer): the same passes on global memory -- digits are read from the column's key
+//              array (480 KB at n = 60 000, L2 resident), the row ids ping-pong between `perm` and a
+//              scratch column.  Such shapes spend < 2 % of a job here.
+// Writes the keys by row (keys_in), the sorted order (perm), the keys in sorted order (keys_out, what
+// column_rank_kernel walks) and the missing-row bit mask.
+constexpr int kSortThreads = 1024;
+constexpr int kSortSmemRows = 22528;  // 8 bytes per row + 48 KB of counters within 227 KB
+template <bool SM>
+__global__ void __launch_bounds__(kSortThreads)
+    column_sort_kernel(const double* __restrict__ data, long long ld, int n, int nstride, int wstride,
+                       const double* __restrict__ global_na, int n_global_na, int na_inf,
+                       unsigned long long* keys_in, unsigned long long* __restrict__ keys_out, uint16_t* perm,
+                       uint16_t* vals, uint32_t* __restrict__ nabits, const int col0) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  const int col = blockIdx.x + col0, tid = threadIdx.x;
+  unsigned long long* kin = keys_in + (size_t)col * nstride;
+  uint16_t* pm = perm + (size_t)col * nstride;
+  uint32_t* part = reinterpret_cast<uint32_t*>(sort_smem);  // SM: [nstride] one half of every key, by row
+  uint16_t* idA = SM ? reinterpret_cast<uint16_t*>(sort_smem + 4 * (size_t)nstride) : pm;
+  uint16_t* idB = SM ? idA + nstride : vals + (size_t)col * nstride;
+  unsigned char* cnt8 = sort_smem + (SM ? 8 * (size_t)nstride : 0);
+  uint16_t* pre16 = reinterpret_cast<uint16_t*>(cnt8 + 16 * kSortThreads);
+  uint32_t* smisc = reinterpret_cast<uint32_t*>(cnt8 + 48 * kSortThreads);
+  const int n32 = (n + 31) & ~31;
+  for (int r = tid; r < n32; r += kSortThreads) {  // whole warps: the ballot needs every lane
+    bool miss = false;
+    if (r < n) {
+      const double v = data[(size_t)col * ld + r];
+      miss = (v != v) || (na_inf && isinf(v));
+      for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
+      const unsigned long long k = miss ? 0ull : order_key(v);
+      kin[r] = k;
+      if (SM) part[r] = (uint32_t)k;
+    }
+    const uint32_t m = __ballot_sync(FULL, miss);
+    if ((tid & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
+  }
+  __syncthreads();
+  const uint16_t* cur = nullptr;
+  if (SM) {
+    cur = radix_argsort(reinterpret_cast<const unsigned char*>(part), 2, 0, 32, cur, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+    __syncthreads();
+    for (int r = tid; r < n; r += kSortThreads) part[r] = (uint32_t)(kin[r] >> 32);  // written by this thread above
+    __syncthreads();
+    cur = radix_argsort(reinterpret_cast<const unsigned char*>(part), 2, 0, 32, cur, idA, idB, n, cnt8, pre16, smisc,
+                        kSortThreads);
+  } else {
+    cur = radix_argsort(reinterpret_cast<const unsigned char*>(kin), 3, 0, 64, cur, idA, idB, n, cnt8, pre16, smisc,
+                        kSortThreads);
+  }
+  __syncthreads();
+  unsigned long long* ko = keys_out + (size_t)col * nstride;
+  for (int t = tid; t < n; t += kSortThreads) {
+    const uint32_t row = cur ? (uint32_t)cur[t] : (uint32_t)t;
+    ko[t] = kin[row];
+    if (cur != pm) pm[t] = (uint16_t)row;
+  }
 }
 
 __global__ void __launch_bounds__(RANK_THREADS)
@@ -600,14 +808,6 @@ __global__ void __launch_bounds__(RANK_THREADS)
   }
 }
 
-__global__ void seg_offsets_kernel(long long* begin, long long* end, int c0, int c1, long long nstride, long long n) {
-  const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < c1) {
-    begin[c] = c * nstride;
-    end[c] = c * nstride + n;
-  }
-}
-
 // tier maxima from the statistics of all columns (what the column kernels raise with atomicMax in a
 // full run): [0] any large tie group, [1] most large groups, [2] most distinct values of a column
 __global__ void max_tied_kernel(const ColStats* __restrict__ stats, int C, int32_t* __restrict__ max_tied) {
@@ -636,17 +836,7 @@ int launch_max_tied(ColumnTables& tab, cudaStream_t stream) {
   if (cudaMemsetAsync(tab.max_tied, 0, 4 * sizeof(int32_t), stream) != cudaSuccess) return -1;
   const int C = (int)tab.C;
   max_tied_kernel<<<std::min(64, (C + 255) / 256), 256, 0, stream>>>(tab.stats, C, tab.max_tied);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride) {
-  size_t bytes = 0;
-  cub::DeviceSegmentedSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr,
-                                      (unsigned long long*)nullptr, (const uint16_t*)nullptr,
-                                      (uint16_t*)nullptr, (long long)(nstride * C), (long long)C,
-                                      (const long long*)nullptr, (const long long*)nullptr);
-  (void)n;
-  return bytes;
+  return launch_status(1);
 }
 
 bool columns_fused(int64_t n) { return n <= 8192 && !getenv("ICIKT_NO_FUSED_COLUMNS"); }
@@ -685,22 +875,21 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     if (l < 0) return -1;
     return launches + l;  // the fused kernel computes the pass-A constants itself
   } else {
-    seg_offsets_kernel<<<(C + 255) / 256, 256, 0, stream>>>(wk.seg_begin, wk.seg_end, col0, col0 + C, nstride, n);
-    ++launches;
-    const int n32 = (n + 31) & ~31;
-    dim3 grid((n32 + 255) / 256, C);
-    build_keys_kernel<<<grid, 256, 0, stream>>>(d_data, ld, n, nstride, wstride, d_global_na, n_global_na,
-                                                na_inf, wk.keys_in, wk.vals_in, tab.nabits, col0);
+    const bool sm = n <= kSortSmemRows && !getenv("ICIKT_SORT_GLOBAL");
+    const size_t smem = (sm ? 8 * (size_t)nstride : 0) + sort_counter_bytes(kSortThreads);
+    if (sm) {
+      if (cudaFuncSetAttribute(column_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+      column_sort_kernel<true><<<C, kSortThreads, smem, stream>>>(d_data, ld, n, nstride, wstride, d_global_na, n_global_na,
+                                                                 na_inf, wk.keys_in, wk.keys_out, tab.perm, wk.vals_in,
+                                                                 tab.nabits, col0);
+    } else {
+      if (cudaFuncSetAttribute(column_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+      column_sort_kernel<false><<<C, kSortThreads, smem, stream>>>(d_data, ld, n, nstride, wstride, d_global_na,
+                                                                  n_global_na, na_inf, wk.keys_in, wk.keys_out, tab.perm,
+                                                                  wk.vals_in, tab.nabits, col0);
+    }
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
-    size_t bytes = wk.cub_bytes;
-    if (cub::DeviceSegmentedSort::SortPairs(wk.cub_temp, bytes, (const unsigned long long*)wk.keys_in,
-                                            wk.keys_out, (const uint16_t*)wk.vals_in, tab.perm,
-                                            (long long)nstride * tab.C, (long long)C,
-                                            (const long long*)wk.seg_begin + col0, (const long long*)wk.seg_end + col0,
-                                            stream) != cudaSuccess)
-      return -1;
-    launches += 3;  // cub partitions the segments into size classes: up to three sort kernels
     column_rank_kernel<<<C, RANK_THREADS, 0, stream>>>(wk.keys_out, n, nstride, wstride, tab.perm, tab.rank,
                                                        tab.trow, tab.trun, tab.tend, tab.firstbits,
                                                        wk.gpos, tab.gstart, (int)tab.gstride, tab.lgrp, tab.stats, tab.max_tied,

@@ -38,7 +38,17 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) {
 // them as IMAD / IMAD.HI (FMA pipe) instead of strength-reducing them to integer-ALU shifts/adds.
 struct PipeConst {
   uint32_t one, two, c64k;
+  uint32_t c4410, c4432;  // PRMT selectors: low / high 16-bit half of a register, zero-extended
 };
+__host__ __device__ inline PipeConst make_pipe_const() {
+  PipeConst pc;
+  pc.one = 1u;
+  pc.two = 2u;
+  pc.c64k = 65536u;
+  pc.c4410 = 0x4410u;
+  pc.c4432 = 0x4432u;
+  return pc;
+}
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (sm_90+) ---------------------
 // Used for the one contiguous bulk transfer of the pair kernel: y's dense-rank table into the
@@ -111,59 +121,56 @@ struct Mem<false> {
     return d;
   }
   // one key of pass A's scatter sweep (two bits per level, see count_pass): Q01/Q23 hold the
-  // next free slot (element index, 16 bits each) of digit classes 0|1 and 2|3, S the number of
-  // keys seen so far whose high bit is set.  `two` is a register holding 2 that the assembler
-  // cannot fold, so the slot address is an IMAD and not an LEA.  14 instructions per key.
-  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
-                                               uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
-                                               uint32_t key, ptr base, uint32_t two) {
+  // next free slot (element index, 16 bits each) of digit classes 0|1 and 2|3.  acc2 sums, over
+  // ALL keys, the running slot of the key's lo = 1 sibling class (one IMAD.HI on the FMA pipe, no
+  // predicate); count_pass takes the lo = 1 keys' own share back out in closed form.  `two` and the
+  // other constants are registers the assembler cannot fold, so the slot address is an IMAD and
+  // not an LEA.  11 instructions per key.
+  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& acc2, uint32_t w,
+                                               uint32_t bit_lo, uint32_t bit_hi, uint32_t key, ptr base,
+                                               const PipeConst& pc) {
     asm volatile(
         "{\n\t"
         ".reg .pred ph, pl;\n\t"
-        ".reg .b32 t, qs, sel, idx, ad, inc, up;\n\t"
-        "and.b32 t, %5, %7;\n\t"
+        ".reg .b32 t, qs, sel, idx, ad, inc;\n\t"
+        "and.b32 t, %3, %5;\n\t"
         "setp.ne.u32 ph, t, 0;\n\t"
-        "and.b32 t, %5, %6;\n\t"
+        "and.b32 t, %3, %4;\n\t"
         "setp.ne.u32 pl, t, 0;\n\t"
         "selp.b32 qs, %1, %0, ph;\n\t"
-        "selp.b32 sel, 0x4432, 0x4410, pl;\n\t"
+        "mad.hi.u32 %2, qs, %9, %2;\n\t"
+        "selp.b32 sel, %11, %10, pl;\n\t"
         "prmt.b32 idx, qs, 0, sel;\n\t"
-        "mad.lo.u32 ad, idx, %10, %9;\n\t"
-        "st.shared.u16 [ad], %8;\n\t"
-        "selp.b32 inc, 0x10000, 1, pl;\n\t"
-        "shr.u32 up, qs, 16;\n\t"
+        "mad.lo.u32 ad, idx, %8, %7;\n\t"
+        "st.shared.u16 [ad], %6;\n\t"
+        "selp.b32 inc, %9, %12, pl;\n\t"
         "@ph add.u32 %1, %1, inc;\n\t"
         "@!ph add.u32 %0, %0, inc;\n\t"
-        "@!ph add.u32 %3, %3, %2;\n\t"
-        "@ph add.u32 %2, %2, 1;\n\t"
-        "@!pl add.u32 %4, %4, up;\n\t"
         "}"
-        : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
-        : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base), "r"(two)
+        : "+r"(Q01), "+r"(Q23), "+r"(acc2)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi), "h"((unsigned short)key), "r"(base), "r"(pc.two), "r"(pc.c64k),
+          "r"(pc.c4410), "r"(pc.c4432), "r"(pc.one)
         : "memory");
   }
   // the same without the store: the last level only has to count
-  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
-                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi) {
+  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& acc2, uint32_t w,
+                                                uint32_t bit_lo, uint32_t bit_hi, const PipeConst& pc) {
     asm volatile(
         "{\n\t"
         ".reg .pred ph, pl;\n\t"
-        ".reg .b32 t, qs, inc, up;\n\t"
-        "and.b32 t, %5, %7;\n\t"
+        ".reg .b32 t, qs, inc;\n\t"
+        "and.b32 t, %3, %5;\n\t"
         "setp.ne.u32 ph, t, 0;\n\t"
-        "and.b32 t, %5, %6;\n\t"
+        "and.b32 t, %3, %4;\n\t"
         "setp.ne.u32 pl, t, 0;\n\t"
         "selp.b32 qs, %1, %0, ph;\n\t"
-        "selp.b32 inc, 0x10000, 1, pl;\n\t"
-        "shr.u32 up, qs, 16;\n\t"
+        "mad.hi.u32 %2, qs, %6, %2;\n\t"
+        "selp.b32 inc, %6, %7, pl;\n\t"
         "@ph add.u32 %1, %1, inc;\n\t"
         "@!ph add.u32 %0, %0, inc;\n\t"
-        "@!ph add.u32 %3, %3, %2;\n\t"
-        "@ph add.u32 %2, %2, 1;\n\t"
-        "@!pl add.u32 %4, %4, up;\n\t"
         "}"
-        : "+r"(Q01), "+r"(Q23), "+r"(S), "+r"(acc), "+r"(acc2)
-        : "r"(w), "r"(bit_lo), "r"(bit_hi));
+        : "+r"(Q01), "+r"(Q23), "+r"(acc2)
+        : "r"(w), "r"(bit_lo), "r"(bit_hi), "r"(pc.c64k), "r"(pc.one));
   }
   static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
@@ -193,26 +200,24 @@ struct Mem<true> {
   static __device__ __forceinline__ uint32_t off(ptr p, ptr base) { return (uint32_t)(p - base); }
   static __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b, uint32_t) { return a + b; }
   static __device__ __forceinline__ uint32_t hi16(uint32_t w, uint32_t) { return w >> 16; }
-  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
-                                               uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi,
-                                               uint32_t key, ptr base, uint32_t) {
+  static __device__ __forceinline__ void step4(uint32_t& Q01, uint32_t& Q23, uint32_t& acc2, uint32_t w,
+                                               uint32_t bit_lo, uint32_t bit_hi, uint32_t key, ptr base,
+                                               const PipeConst&) {
     const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
     const uint32_t qs = ph ? Q23 : Q01;
     const uint32_t idx = pl ? (qs >> 16) : (qs & 0xffffu);
     *reinterpret_cast<unsigned short*>(base + 2 * (size_t)idx) = (unsigned short)key;
     const uint32_t inc = pl ? 0x10000u : 1u;
-    if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
-    if (ph) S += 1;
-    if (!pl) acc2 += qs >> 16;
+    if (ph) Q23 += inc; else Q01 += inc;
+    acc2 += qs >> 16;
   }
-  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& S, uint32_t& acc,
-                                                uint32_t& acc2, uint32_t w, uint32_t bit_lo, uint32_t bit_hi) {
+  static __device__ __forceinline__ void step4c(uint32_t& Q01, uint32_t& Q23, uint32_t& acc2, uint32_t w,
+                                                uint32_t bit_lo, uint32_t bit_hi, const PipeConst&) {
     const bool ph = (w & bit_hi) != 0u, pl = (w & bit_lo) != 0u;
     const uint32_t qs = ph ? Q23 : Q01;
     const uint32_t inc = pl ? 0x10000u : 1u;
-    if (ph) { Q23 += inc; } else { Q01 += inc; acc += S; }
-    if (ph) S += 1;
-    if (!pl) acc2 += qs >> 16;
+    if (ph) Q23 += inc; else Q01 += inc;
+    acc2 += qs >> 16;
   }
   static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) { atomicAdd(reinterpret_cast<uint32_t*>(p), v); }
   // generic addressing reaches shared memory too
@@ -237,13 +242,45 @@ struct Mem<true> {
 // where the second term is, for a key of class 0, the class-1 keys before it, and for a key of
 // class 2 all N1 class-1 keys plus the class-3 keys before it.  Per level:
 //   sweep 1  counts the range's keys per class, two keys per 32-bit word at once
-//            ((w >> s) & 0x00010001 summed in two 16-bit fields);
+//            ((w >> s) & 0x00010001 summed in two 16-bit fields), and -- same fields, one more
+//            IMAD per word -- the sum J1 of the local indices of the hi = 1 keys: the whole hi-bit
+//            term of the thread follows from it in closed form (a hi = 0 key at local index j has
+//            j - (hi = 0 keys before it) hi = 1 keys before it inside the range);
 //   two packed warp scans + warp-total reductions give the class counts before the range;
 //   sweep 2  walks the range with four running slot indices (packed 2 x 16 bit in Q01, Q23),
-//            stores every key to its slot of the other buffer and accumulates the count.
+//            stores every key to its slot of the other buffer and sums the running slot of the
+//            key's lo = 1 sibling class over all keys (step4); the lo = 1 keys' own share of that
+//            sum -- their destination slots, two arithmetic series -- is taken out in closed form.
 // No ballots, no per-key population counts: about 16 instructions per key and level of two bits.
 // With an odd number of bits the first level treats the missing top bit as zero.
 //   acc64 += the count over all levels (this thread's share)
+struct LevelCounts {
+  uint32_t n1, n2, n3, J1;
+};
+// class counts and the hi-index sum of one thread's range from the packed sums of sweep 1:
+// cl/ch/cb = per-half sums of the lo / hi / lo&hi bits, wm = per-half sums of (word index) * hi bit
+__device__ __forceinline__ LevelCounts fold_counts(uint32_t cl, uint32_t ch, uint32_t cb, uint32_t wm) {
+  LevelCounts c;
+  c.n3 = (cb & 0xffffu) + (cb >> 16);
+  c.n2 = (ch & 0xffffu) + (ch >> 16) - c.n3;
+  c.n1 = (cl & 0xffffu) + (cl >> 16) - c.n3;
+  // key 2m sits in the low half of word m, key 2m+1 in the high half
+  c.J1 = 2u * ((wm & 0xffffu) + (wm >> 16)) + (ch >> 16);
+  return c;
+}
+// the thread's share of a level's count (all arithmetic modulo 2^32; the true value is small):
+//   hi term   n_hi0 * (hi keys before the range) + sum_{hi=0 keys} j - C(n_hi0, 2)
+//   lo term   acc2 (all keys) - slots of the class-1 keys - slots of the class-3 keys
+//             - n0 * N0 - n2 * (N0 + N2)     (class bases; N1 class-1 keys precede every class-2 key)
+__device__ __forceinline__ uint32_t level_share(const LevelCounts& c, uint32_t R, uint32_t acc2, uint32_t e23,
+                                                uint32_t start1, uint32_t start3, uint32_t N0, uint32_t N2) {
+  const uint32_t nh0 = R - c.n2 - c.n3, n0 = nh0 - c.n1;
+  const uint32_t hi_term = nh0 * e23 + ((R * (R - 1u)) >> 1) - c.J1 - ((nh0 * (nh0 - 1u)) >> 1);
+  const uint32_t lo_term = acc2 - c.n1 * start1 - ((c.n1 * (c.n1 - 1u)) >> 1) - c.n3 * start3 -
+                           ((c.n3 * (c.n3 - 1u)) >> 1) - n0 * N0 - c.n2 * (N0 + N2);
+  return hi_term + lo_term;
+}
+
 template <bool G>
 __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
                                            const int nwarps, const int L, uint32_t* descA, uint32_t* descB,
@@ -257,7 +294,8 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
   const uint32_t cap = ((uint32_t)nwarps << 5) * R;    // keys per buffer
   for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
     const typename M::ptr ra = M::add(a, (int32_t)my_off);
-    uint32_t cl = 0, ch = 0, cb = 0;
+    uint32_t cl = 0, cb = 0, wm = 0, m4 = 0;
+    uint32_t chj[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
     for (int c = 0; c < kk; ++c) {
       uint32_t w[4];
@@ -266,13 +304,16 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
       for (int j = 0; j < 4; ++j) {
         const uint32_t lo = (w[j] >> s) & 0x00010001u, hi = (w[j] >> (s + 1)) & 0x00010001u;
         cl = M::fadd(cl, lo, pc.one);
-        ch = M::fadd(ch, hi, pc.one);
+        chj[j] = M::fadd(chj[j], hi, pc.one);
         cb = M::fadd(cb, lo & hi, pc.one);
+        wm += hi * m4;  // word index 4c + j: the 4c part here, the j part from chj[] below
       }
+      m4 += 4u;
     }
-    const uint32_t n3 = (cb & 0xffffu) + (cb >> 16);
-    const uint32_t n2 = (ch & 0xffffu) + (ch >> 16) - n3;
-    const uint32_t n1 = (cl & 0xffffu) + (cl >> 16) - n3;
+    const uint32_t ch = chj[0] + chj[1] + chj[2] + chj[3];
+    wm += chj[1] + 2u * chj[2] + 3u * chj[3];
+    const LevelCounts lc = fold_counts(cl, ch, cb, wm);
+    const uint32_t n1 = lc.n1, n2 = lc.n2, n3 = lc.n3;
     const uint32_t A = n1 | (n2 << 16), B = n3;
     uint32_t inclA = A, inclB = B;
 #pragma unroll
@@ -295,9 +336,10 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
     const uint32_t e1 = exA & 0xffffu, e2 = exA >> 16, e3 = exB;           // class counts before my range
     const uint32_t N1 = totA & 0xffffu, N2 = totA >> 16, N3 = totB;
     const uint32_t N0 = cap - N1 - N2 - N3;
-    uint32_t Q01 = ((N0 + e1) << 16) | (my_pos - e1 - e2 - e3);
-    uint32_t Q23 = ((N0 + N1 + N2 + e3) << 16) | (N0 + N1 + e2);
-    uint32_t S = e2 + e3, acc = 0, acc2 = 0;
+    const uint32_t start1 = N0 + e1, start3 = N0 + N1 + N2 + e3;
+    uint32_t Q01 = (start1 << 16) | (my_pos - e1 - e2 - e3);
+    uint32_t Q23 = (start3 << 16) | (N0 + N1 + e2);
+    uint32_t acc2 = 0;
     uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
     asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));  // keep the bit tests single LOP3s
     if (s > 0) {
@@ -307,8 +349,8 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
         M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          M::step4(Q01, Q23, S, acc, acc2, w[j], bLl, bHl, w[j], b, pc.two);
-          M::step4(Q01, Q23, S, acc, acc2, w[j], bLh, bHh, M::hi16(w[j], pc.c64k), b, pc.two);
+          M::step4(Q01, Q23, acc2, w[j], bLl, bHl, w[j], b, pc);
+          M::step4(Q01, Q23, acc2, w[j], bLh, bHh, M::hi16(w[j], pc.c64k), b, pc);
         }
       }
     } else {  // the sorted sequence itself is not needed: the last level only counts
@@ -318,15 +360,13 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
         M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          M::step4c(Q01, Q23, S, acc, acc2, w[j], bLl, bHl);
-          M::step4c(Q01, Q23, S, acc, acc2, w[j], bLh, bHh);
+          M::step4c(Q01, Q23, acc2, w[j], bLl, bHl, pc);
+          M::step4c(Q01, Q23, acc2, w[j], bLh, bHh, pc);
         }
       }
     }
-    // acc2 summed absolute slot indices: take out the class bases (class 1 starts at N0, class 3
-    // at N0+N1+N2) and add the N1 class-1 keys that precede every class-2 key after the hi partition
-    const uint32_t n0 = R - n1 - n2 - n3;
-    acc64 += (unsigned long long)(acc + acc2 - n0 * N0 - n2 * (N0 + N2));
+    (void)N3;
+    acc64 += (unsigned long long)level_share(lc, R, acc2, e2 + e3, start1, start3, N0, N2);
     __syncthreads();  // also protects descA/descB for the next level
     const typename M::ptr t = a;
     a = b;

@@ -9,6 +9,23 @@
 
 namespace icikt {
 
+// The launchers report failure as a negative count; the CUDA error that caused it is parked here
+// (cudaGetLastError clears it) so that the C ABI can put its text into icikt_last_error().
+extern thread_local cudaError_t g_launch_error;
+extern thread_local const char* g_launch_note;
+inline int launch_status(int launches) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return launches;
+  g_launch_error = e;
+  g_launch_note = "kernel launch";
+  return -1;
+}
+inline int launch_refused(const char* why) {
+  g_launch_error = cudaGetLastError();
+  g_launch_note = why;
+  return -1;
+}
+
 // Device-resident per-column tables produced by K1 (layout: DESIGN.md "Data layout in HBM").
 struct ColumnTables {
   int64_t n = 0;        // rows (features)
@@ -78,16 +95,11 @@ struct PairLaunch {
 
 // Scratch of the column kernels (allocated by the plan).
 struct ColumnWork {
-  unsigned long long* keys_in = nullptr;   // [C][nstride] sort keys
-  unsigned long long* keys_out = nullptr;  // [C][nstride] sorted keys
-  uint16_t* vals_in = nullptr;             // [C][nstride] row ids
+  unsigned long long* keys_in = nullptr;   // [C][nstride] sort keys by row (long columns only)
+  unsigned long long* keys_out = nullptr;  // [C][nstride] keys in sorted order
+  uint16_t* vals_in = nullptr;             // [C][nstride] second row-id buffer of the sort, then walk ranks
   uint32_t* gpos = nullptr;                // [C][nstride+64] start position of every tie group
-  long long* seg_begin = nullptr;          // [C]
-  long long* seg_end = nullptr;            // [C]
-  void* cub_temp = nullptr;
-  size_t cub_bytes = 0;
 };
-size_t columns_cub_bytes(int64_t n, int64_t C, int64_t nstride);
 bool columns_fused(int64_t n);  // short columns: one kernel per column does everything (and writes tord)
 
 // K1: data (device, column-major, ld) -> tables of columns [col_lo, col_hi).  Does not touch
@@ -151,6 +163,27 @@ struct MatrixFill {
 };
 int launch_matrix_fill(const MatrixFill& mf, cudaStream_t stream);
 
+// The same for a block of columns [c_lo, c_hi) when the pairs were computed on several devices: each
+// device fills its block of every matrix from the result arrays of all devices (peer pointers).
+constexpr int kMaxMatrixDevices = 16;
+struct BlockFill {
+  int n_dev;
+  const double* tau[kMaxMatrixDevices];
+  const double* pvalue[kMaxMatrixDevices];
+  const double* taumax[kMaxMatrixDevices];
+  const double* completeness[kMaxMatrixDevices];
+  const int32_t* status[kMaxMatrixDevices];
+  long long pair_lo[kMaxMatrixDevices + 1];  // first pair of every device's slice; [n_dev] = total
+  long long n, C, c_lo, c_hi;
+  int scale_max, diag_good;
+  double max_taumax;       // over all devices; NaN if no pair is valid
+  const int32_t* n_good;   // device [C] (diag_good only)
+  int best_good;           // max(n_good)
+  double* m[5];            // this device's blocks: [c_hi - c_lo][C] each, any may be null
+  unsigned long long* hist;  // device [16], zeroed by the caller
+};
+int launch_matrix_block_fill(const BlockFill& f, cudaStream_t stream);
+
 // pairwise_completeness (R/kendalltau.R:563-629) from missing-row bit masks:
 // bits[w][C] (word-major so that neighbouring pairs read neighbouring words)
 int launch_missing_bits(const double* d_data, int64_t ld, int64_t n, int64_t C, const double* d_lit, int nlit,
@@ -168,5 +201,8 @@ int64_t tiled_max_n();
 
 // shared-memory read+write sweep, GB/s for 32-bit and 128-bit accesses (benchmark utility)
 int measure_smem_bandwidth(double* gbps32, double* gbps128);
+// sustained warp-instruction issue rate (G warp instructions / s over the whole GPU): LOP3 only (ALU
+// pipe), IMAD only (FMA pipe), and the two interleaved (benchmark utility)
+int measure_issue_rate(double* alu, double* fma, double* mixed);
 
 }  // namespace icikt

@@ -41,6 +41,8 @@
 #include "icikt_count.cuh"
 
 namespace icikt {
+thread_local cudaError_t g_launch_error = cudaSuccess;
+thread_local const char* g_launch_note = "";
 namespace {
 
 
@@ -175,7 +177,7 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
   const uint32_t ra = a + my_off;
   for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
     uint32_t w[KK][4];
-    uint32_t cl = 0, ch = 0, cb = 0;
+    uint32_t cl = 0, ch = 0, cb = 0, wm = 0;
 #pragma unroll
     for (int c = 0; c < KK; ++c) {
       M::ld128(ra + (c << 4), w[c][0], w[c][1], w[c][2], w[c][3]);
@@ -185,11 +187,11 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
         cl = M::fadd(cl, lo, pc.one);
         ch = M::fadd(ch, hi, pc.one);
         cb = M::fadd(cb, lo & hi, pc.one);
+        wm += hi * (uint32_t)(4 * c + j);  // word index (compile-time): see count_pass
       }
     }
-    const uint32_t n3 = (cb & 0xffffu) + (cb >> 16);
-    const uint32_t n2 = (ch & 0xffffu) + (ch >> 16) - n3;
-    const uint32_t n1 = (cl & 0xffffu) + (cl >> 16) - n3;
+    const LevelCounts lc = fold_counts(cl, ch, cb, wm);
+    const uint32_t n1 = lc.n1, n2 = lc.n2, n3 = lc.n3;
     const uint32_t A = n1 | (n2 << 16), B = n3;
     uint32_t inclA = A, inclB = B;
 #pragma unroll
@@ -212,9 +214,10 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
     const uint32_t e1 = exA & 0xffffu, e2 = exA >> 16, e3 = exB;
     const uint32_t N1 = totA & 0xffffu, N2 = totA >> 16, N3 = totB;
     const uint32_t N0 = cap - N1 - N2 - N3;
-    uint32_t Q01 = ((N0 + e1) << 16) | (my_pos - e1 - e2 - e3);
-    uint32_t Q23 = ((N0 + N1 + N2 + e3) << 16) | (N0 + N1 + e2);
-    uint32_t S = e2 + e3, acc = 0, acc2 = 0;
+    const uint32_t start1 = N0 + e1, start3 = N0 + N1 + N2 + e3;
+    uint32_t Q01 = (start1 << 16) | (my_pos - e1 - e2 - e3);
+    uint32_t Q23 = (start3 << 16) | (N0 + N1 + e2);
+    uint32_t acc2 = 0;
     uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
     asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));
     if (s > 0) {
@@ -222,8 +225,8 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
       for (int c = 0; c < KK; ++c) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          M::step4(Q01, Q23, S, acc, acc2, w[c][j], bLl, bHl, w[c][j], a, pc.two);
-          M::step4(Q01, Q23, S, acc, acc2, w[c][j], bLh, bHh, M::hi16(w[c][j], pc.c64k), a, pc.two);
+          M::step4(Q01, Q23, acc2, w[c][j], bLl, bHl, w[c][j], a, pc);
+          M::step4(Q01, Q23, acc2, w[c][j], bLh, bHh, M::hi16(w[c][j], pc.c64k), a, pc);
         }
       }
     } else {
@@ -231,13 +234,13 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
       for (int c = 0; c < KK; ++c) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          M::step4c(Q01, Q23, S, acc, acc2, w[c][j], bLl, bHl);
-          M::step4c(Q01, Q23, S, acc, acc2, w[c][j], bLh, bHh);
+          M::step4c(Q01, Q23, acc2, w[c][j], bLl, bHl, pc);
+          M::step4c(Q01, Q23, acc2, w[c][j], bLh, bHh, pc);
         }
       }
     }
-    const uint32_t n0 = R - n1 - n2 - n3;
-    acc64 += (unsigned long long)(acc + acc2 - n0 * N0 - n2 * (N0 + N2));
+    (void)N3;
+    acc64 += (unsigned long long)level_share(lc, R, acc2, e2 + e3, start1, start3, N0, N2);
     __syncthreads();
   }
 }
@@ -1207,6 +1210,59 @@ double run_smem_sweep(int n_sm, unsigned* d_sink) {
   return best;
 }
 
+// ---- instruction-issue microbenchmark (the second roofline denominator) ---------------------
+// The pair kernel is bound by instruction issue on the two integer-capable pipes: the ALU pipe
+// (LOP3 / IADD3 / SHF / SEL / PRMT) and the FMA pipe (IMAD), each taking one warp instruction every
+// other cycle per scheduler.  MODE 0: LOP3 only, 1: IMAD only, 2: the two interleaved.  Eight
+// independent chains per thread hide the 4-cycle latency; 32 warps per SM keep every scheduler fed.
+template <int MODE>
+__global__ void __launch_bounds__(1024) issue_sweep_kernel(int iters, uint32_t m, uint32_t* sink) {
+  uint32_t a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 2654435761u + (uint32_t)k * 40503u + blockIdx.x;
+  uint32_t b = m | 1u, c = m ^ 0x9e3779b9u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool fma = MODE == 1 || (MODE == 2 && (k & 1));
+        if (fma)
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+        else
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b), "r"(c));
+      }
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x ^= a[k];
+  if (x == 0x12345u) sink[0] = x;  // keeps the chains alive
+}
+
+template <int MODE>
+double run_issue_sweep(int n_sm, uint32_t* d_sink) {
+  const int iters = 4000, grid = n_sm * 2;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  issue_sweep_kernel<MODE><<<grid, 1024>>>(iters / 10, 3u, d_sink);
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    issue_sweep_kernel<MODE><<<grid, 1024>>>(iters, 3u, d_sink);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1; break; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double warp_inst = (double)grid * 32.0 * iters * 64.0;  // 64 instructions per thread and iteration
+    best = std::max(best, warp_inst / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
+
 TiledParams make_params(const PairLaunch& pl) {
   const ColumnTables& t = *pl.tab;
   TiledParams p;
@@ -1238,9 +1294,7 @@ TiledParams make_params(const PairLaunch& pl) {
   p.max_tied = t.max_tied;
   p.tier = 0;
   p.budget = 16LL * t.n;
-  p.pc.one = 1u;
-  p.pc.two = 2u;
-  p.pc.c64k = 65536u;
+  p.pc = make_pipe_const();
   return p;
 }
 
@@ -1260,6 +1314,22 @@ int measure_smem_bandwidth(double* gbps32, double* gbps128) {
   if (a < 0 || b < 0) return -1;
   *gbps32 = a;
   *gbps128 = b;
+  return 0;
+}
+
+int measure_issue_rate(double* alu, double* fma, double* mixed) {
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  uint32_t* d_sink = nullptr;
+  if (cudaMalloc(reinterpret_cast<void**>(&d_sink), sizeof(uint32_t) * 4) != cudaSuccess) return -1;
+  const double a = run_issue_sweep<0>(n_sm, d_sink), f = run_issue_sweep<1>(n_sm, d_sink),
+               m = run_issue_sweep<2>(n_sm, d_sink);
+  cudaFree(d_sink);
+  if (a < 0 || f < 0 || m < 0) return -1;
+  *alu = a;
+  *fma = f;
+  *mixed = m;
   return 0;
 }
 
@@ -1368,13 +1438,19 @@ template <int MAXT, int MINB, bool G, bool PW = false, int IP = 0>
 int tiled_occupancy(int threads, size_t smem) {
   auto kern = pairs_tiled_kernel<MAXT, MINB, G, PW, IP>;
   if (threads > MAXT) return 0;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    cudaGetLastError();
+  // always the architectural maximum, never the shape's own need: the attribute is per device, and two
+  // host threads driving plans of different shapes on one device must not shrink it under each other
+  // between the query and the launch
+  (void)smem;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    g_launch_error = cudaGetLastError();
+    g_launch_note = "cudaFuncSetAttribute(max dynamic shared memory)";
     return 0;
   }
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) {
-    cudaGetLastError();
+    g_launch_error = cudaGetLastError();
+    g_launch_note = "cudaOccupancyMaxActiveBlocksPerMultiprocessor";
     return 0;
   }
   return per_sm;
@@ -1383,7 +1459,7 @@ int tiled_occupancy(int threads, size_t smem) {
 template <int MAXT, int MINB, bool G, bool PW = false, int IP = 0>
 int launch_tiled_variant(const TiledParams& p, int threads, long long grid, size_t smem, cudaStream_t stream) {
   pairs_tiled_kernel<MAXT, MINB, G, PW, IP><<<(unsigned)grid, threads, smem, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 // Three register classes of the same code (64 / 40 / 32 registers per thread): take the roomiest
@@ -1393,13 +1469,13 @@ int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, 
   const int threads = 32 * sh.warps;
   if (!G && sh.inplace_kk == 9) {  // long vectors in place: 28 warps at most, ~72 registers
     const int occ = tiled_occupancy<896, 1, false, false, 9>(threads, smem);
-    if (occ < 1) return -1;
+    if (occ < 1) return launch_refused("the in-place pair kernel does not fit an SM (occupancy 0)");
     long long grid = std::max<long long>(1, std::min<long long>((long long)n_sm * occ, p.n_units));
     return launch_tiled_variant<896, 1, false, false, 9>(p, threads, grid, smem, stream);
   }
   if (p.pw) {  // complete-observations mode: one register class
     const int occ = tiled_occupancy<1024, 1, G, true>(threads, smem);
-    if (occ < 1) return -1;
+    if (occ < 1) return launch_refused("the complete-observations pair kernel does not fit an SM (occupancy 0)");
     long long grid = (long long)n_sm * occ;
     if (grid > p.n_units) grid = p.n_units;
     if (G && grid > sh.scratch_ctas) grid = sh.scratch_ctas;
@@ -1419,7 +1495,10 @@ int launch_tiled_g(TiledParams& p, const TiledShape& sh, size_t smem, int n_sm, 
     if (v == 1 && o40 > 0) { cls = 1; best = o40; }
     if (v == 2 && o32 > 0) { cls = 2; best = o32; }
   }
-  if (best < 1) return -1;
+  if (best < 1) {
+    if (g_launch_error != cudaSuccess) return -1;  // the occupancy query itself failed: keep its error
+    return launch_refused("the pair kernel does not fit an SM (occupancy 0 in every register class)");
+  }
   long long grid = (long long)n_sm * best;
   if (grid > p.n_units) grid = p.n_units;
   if (G && grid > sh.scratch_ctas) grid = sh.scratch_ctas;
@@ -1465,14 +1544,14 @@ int launch_column_consts(ColumnTables& tab, const TiledShape& sh, unsigned char*
     p.scratch_stride = sh.scratch_stride;
     grid = std::min<long long>(grid, sh.scratch_ctas);
     const size_t smem = tiled_smem_bytes(0, p.wstride, fw);
-    if (cudaFuncSetAttribute(column_const_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(column_const_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
     column_const_kernel<true><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)col_lo, (int)col_hi);
   } else {
     const size_t smem = tiled_smem_bytes(region, p.wstride, fw);
-    if (cudaFuncSetAttribute(column_const_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(column_const_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
     column_const_kernel<false><<<(unsigned)grid, 32 * W, smem, stream>>>(p, tab.stats, (int)col_lo, (int)col_hi);
   }
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 size_t naive_scratch_bytes(int64_t n, int64_t n_threads) {
@@ -1485,7 +1564,7 @@ int launch_pairs_naive(const PairLaunch& pl, int64_t P, uint32_t* d_scratch, int
   const int block = 128;
   const long long grid = (n_threads + block - 1) / block;
   pairs_naive_kernel<<<(unsigned)grid, block, 0, stream>>>(p, P, d_scratch, n_threads);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream) {
@@ -1512,13 +1591,13 @@ int launch_epilogue(const EpilogueLaunch& el, cudaStream_t stream) {
   while ((1 << p.lane_shift) < el.max_unit_pairs && p.lane_shift < 5) ++p.lane_shift;
   const long long grid = ((el.n_units << p.lane_shift) + 127) / 128;
   epilogue_kernel<<<(unsigned)grid, 128, 0, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 int launch_pnorm(const double* d_z, int64_t n, int lower, double* d_out, cudaStream_t stream) {
   if (n <= 0) return 0;
   pnorm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_z, n, lower, d_out);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 }  // namespace icikt

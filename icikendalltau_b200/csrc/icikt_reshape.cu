@@ -148,7 +148,66 @@ __global__ void __launch_bounds__(256) missing_matrix_kernel(const uint32_t* __r
   m[i + j * C] = 1.0 - (double)cnt / (double)n;
 }
 
+// Multi-GPU matrix output: this device fills columns [c_lo, c_hi) of the five C x C matrices -- a
+// contiguous block of every (column-major) matrix, so that it leaves for the caller's arrays as one
+// copy per matrix.  The value of entry (r, c) is the result of pair (min, max) wherever that pair was
+// computed: the per-pair result arrays of all devices are read in place (peer memory over NVLink, or
+// the same device).  Rows below the diagonal of a column are consecutive pairs (coalesced reads), rows
+// above it are one pair per row of the triangle (8-byte gathers; ~C^2/2 of them per job, a few MB over
+// the links).  One thread per entry; writes are coalesced.
+__global__ void __launch_bounds__(256) matrix_block_fill_kernel(const BlockFill f) {
+  const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long c = f.c_lo + blockIdx.y;
+  if (r >= f.C) return;
+  const long long C = f.C, ptri = C * (C - 1) / 2;
+  const long long o = r + (c - f.c_lo) * C;
+  const double na = __longlong_as_double(0x7ff00000000007a2LL);  // R's NA_real_
+  long long k;
+  if (r == c) {
+    if (f.diag_good) {  // R/kendalltau.R:374-386, never scaled
+      const double g = (double)f.n_good[c];
+      if (f.m[0]) f.m[0][o] = g / (double)f.best_good;
+      if (f.m[1]) f.m[1][o] = g / (double)f.best_good;
+      if (f.m[2]) f.m[2][o] = 0.0;
+      if (f.m[3]) f.m[3][o] = 1.0;
+      if (f.m[4]) f.m[4][o] = g / (double)f.n;
+      return;
+    }
+    k = ptri + c;  // the (i,i) pairs are computed pairs when !diag_good (R/kendalltau.R:191-194)
+  } else {
+    const long long i = r < c ? r : c, j = r < c ? c : r;
+    k = i * (2 * C - i - 1) / 2 + (j - i - 1);
+  }
+  int d = 0;
+  while (d + 1 < f.n_dev && k >= f.pair_lo[d + 1]) ++d;
+  const long long slot = k - f.pair_lo[d];
+  const int st = f.status[d][slot];
+  const bool once = r >= c;  // every pair is met twice (both triangles): count it where r > c
+  if (st != 0) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+      if (f.m[q]) f.m[q][o] = na;
+    if (once) atomicAdd(f.hist + (st & 15), 1ULL);
+    return;
+  }
+  const double raw = f.tau[d][slot];
+  if (f.m[0]) f.m[0][o] = f.scale_max ? raw / f.max_taumax : raw;
+  if (f.m[1]) f.m[1][o] = raw;
+  if (f.m[2]) f.m[2][o] = f.pvalue[d][slot];
+  if (f.m[3]) f.m[3][o] = f.taumax[d][slot];
+  if (f.m[4]) f.m[4][o] = f.completeness[d][slot];
+}
+
 }  // namespace
+
+int launch_matrix_block_fill(const BlockFill& f, cudaStream_t stream) {
+  const long long ncols = f.c_hi - f.c_lo;
+  if (ncols <= 0) return 0;
+  if (ncols > 65535) return -1;  // gridDim.y
+  const dim3 grid((unsigned)((f.C + 255) / 256), (unsigned)ncols);
+  matrix_block_fill_kernel<<<grid, 256, 0, stream>>>(f);
+  return launch_status(1);
+}
 
 int launch_matrix_fill(const MatrixFill& mf, cudaStream_t stream) {
   int launches = 0;
@@ -165,14 +224,14 @@ int launch_matrix_fill(const MatrixFill& mf, cudaStream_t stream) {
     matrix_diag_kernel<<<1, 1024, 0, stream>>>(mf);
     ++launches;
   }
-  return cudaGetLastError() == cudaSuccess ? launches : -1;
+  return launch_status(launches);
 }
 
 int launch_missing_bits(const double* d_data, int64_t ld, int64_t n, int64_t C, const double* d_lit, int nlit,
                         int na_nan, int na_inf, uint32_t* bits, int64_t words, cudaStream_t stream) {
   const dim3 grid((unsigned)C, (unsigned)((words + 7) / 8));
   missing_bits_kernel<<<grid, 256, 0, stream>>>(d_data, ld, n, C, d_lit, nlit, na_nan, na_inf, bits, words);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 int launch_pair_missing(const uint32_t* bits, int64_t words, int64_t n, int64_t C, const int32_t* pi,
@@ -181,7 +240,7 @@ int launch_pair_missing(const uint32_t* bits, int64_t words, int64_t n, int64_t 
   if (P <= 0) return 0;
   pair_missing_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(bits, words, n, C, pi, pj, P, missing,
                                                                         completeness);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 int launch_missing_matrix(const uint32_t* bits, int64_t words, int64_t n, int64_t C, double* matrix,
@@ -189,7 +248,7 @@ int launch_missing_matrix(const uint32_t* bits, int64_t words, int64_t n, int64_
   if (C > 65535) return -1;  // gridDim.y
   const dim3 grid((unsigned)((C + 255) / 256), (unsigned)C);
   missing_matrix_kernel<<<grid, 256, 0, stream>>>(bits, words, n, C, matrix);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  return launch_status(1);
 }
 
 }  // namespace icikt

@@ -158,6 +158,18 @@ int icikt_matrices(const double* data, int64_t n, int64_t C, int64_t ld, const d
                    double* completeness, int64_t* status_counts, double* max_taumax,
                    icikt_timings* timings);
 
+/* icikt_matrices (all pairs) over several GPUs of one box in ONE call: the pair order is sliced over
+ * the devices like icikt_all_pairs_multi (sharded K1 + peer gather of the tables), then device k
+ * fills columns [C*k/N, C*(k+1)/N) of the five matrices -- reading the per-pair results of the other
+ * devices in place over NVLink -- and copies its block straight into the caller's arrays, so the
+ * 5 x C x C doubles leave over N PCIe links at once.  Needs peer access between the devices; without
+ * it (or with one device) the call runs icikt_matrices on devices[0].  n_devices <= 16.          */
+int icikt_matrices_multi(const double* data, int64_t n, int64_t C, int64_t ld, const double* global_na,
+                         int32_t n_global_na, const icikt_opts* opts, const int32_t* devices,
+                         int32_t n_devices, int32_t scale_max, int32_t diag_good, const int32_t* n_good,
+                         double* cor, double* raw, double* pvalue, double* taumax, double* completeness,
+                         int64_t* status_counts, double* max_taumax, icikt_timings* timings);
+
 /* pairwise_completeness (R/kendalltau.R:563-629): missing[k] = rows missing in column pi[k] or
  * pj[k] (missing_either, :626-629), completeness[k] = 1 - missing/n (:617).  Here, as in
  * setup_missing_matrix (R/utils.R:1-23), NaN/NA rows are missing only if global_na holds a NaN,
@@ -253,6 +265,13 @@ void icikt_release_workspace(void);
  * one 32-bit store per element per level).  Returns GB/s through the pointers (either may
  * be NULL): 32-bit accesses and 128-bit accesses.  Benchmark utility, not on the hot path. */
 int icikt_measure_smem_bandwidth(int32_t device, double* gbps_32bit, double* gbps_128bit);
+
+/* Measures the sustained instruction-issue rate of `device`, in G warp-instructions per second over
+ * the whole GPU, for the two pipes the pair kernel lives on: LOP3 only (integer ALU pipe), IMAD only
+ * (FMA pipe), and the two interleaved (what a kernel that balances them can reach).  The pair
+ * kernel's executed warp instructions divided by its run time, over the interleaved figure, is the
+ * INT/issue roofline fraction bench.py prints.  Any pointer may be NULL.                        */
+int icikt_measure_issue_rate(int32_t device, double* alu_only, double* fma_only, double* interleaved);
 
 #ifdef __cplusplus
 }

@@ -145,7 +145,8 @@ ici_kendalltau = function(data_matrix, global_na = c(NA, Inf, 0), perspective = 
   samples = colnames(data_matrix)
   exclude_loc = .missing_matrix(data_matrix, global_na)
   # the all-pairs matrix path never needs the 1-based index vectors (12.5 M pairs at 5 000 samples)
-  on_device = return_matrix && length(device) == 1L
+  # (several devices: all pairs only -- every GPU returns its own block of columns of each matrix)
+  on_device = return_matrix && (length(device) == 1L || is.null(include_only))
   plan = .plan_pairs(samples, include_only, diag_good, include_arg, need_indices = !on_device || check_timing)
   n_todo = plan$n_todo
 

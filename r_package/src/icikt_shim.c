@@ -167,9 +167,17 @@ SEXP C_icikt_matrices(SEXP data, SEXP global_na, SEXP pi, SEXP pj, SEXP perspect
   SET_VECTOR_ELT(res, 6, mxs);
   int64_t hist[ICIKT_NSTATUS];
   double mx = NA_REAL;
-  const int rc = icikt_matrices(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), zi, zj, (int64_t)P,
-                                &o, asLogical(scale_max) == TRUE, asLogical(diag_good) == TRUE, INTEGER(n_good),
-                                m[0], m[1], m[2], m[3], m[4], hist, &mx, NULL);
+  /* `device`: one ordinal, or (all pairs only) several -> every GPU computes a slice of the pair order and
+   * fills and returns its own block of columns of the five matrices */
+  const int multi = !have_list && isInteger(device) && XLENGTH(device) > 1;
+  const int rc = multi
+                     ? icikt_matrices_multi(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), &o,
+                                            INTEGER(device), (int32_t)XLENGTH(device), asLogical(scale_max) == TRUE,
+                                            asLogical(diag_good) == TRUE, INTEGER(n_good), m[0], m[1], m[2], m[3],
+                                            m[4], hist, &mx, NULL)
+                     : icikt_matrices(REAL(data), n, C, n, REAL(global_na), (int32_t)XLENGTH(global_na), zi, zj,
+                                      (int64_t)P, &o, asLogical(scale_max) == TRUE, asLogical(diag_good) == TRUE,
+                                      INTEGER(n_good), m[0], m[1], m[2], m[3], m[4], hist, &mx, NULL);
   if (rc != ICIKT_OK) {
     UNPROTECT(1);
     error("libicikt_b200 (%d): %s", rc, icikt_last_error());

@@ -873,3 +873,38 @@ def test_pairwise_completeness_kernel(gna):
     long = ik.pairwise_completeness(x, gna, colnames=names, include_only="s3", return_matrix=False)
     keep = (pi == 3) | (pj == 3)
     assert np.array_equal(long["missingness"], miss[keep])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale_max,diag_good", [(True, True), (False, False), (True, False)])
+def test_multi_gpu_matrices_match_single_gpu(scale_max, diag_good):
+    """icikt_matrices_multi: the pair order sliced over the devices, every device filling and returning
+    its own block of columns (reading the other devices' per-pair results in place), gives the very
+    bytes of the single-device matrices -- incl. NA_real_ for degenerate pairs, the diag_good diagonal
+    and the status counts.  With one GPU the slices run on the same device."""
+    ndev = _lib.load().icikt_device_count()
+    x = gen(900, 37, "mixed", 0.25, seed=123)
+    x[:, 11] = 3.0      # a constant column: status 3 in a whole row/column of every matrix
+    x[:, 30] = np.nan   # an all-missing one: status 1
+    gna = (np.nan, np.inf, 0.0)
+    n_good = (~O.setup_missing_matrix(x, gna)).sum(axis=0)
+    one = _lib.run_matrices(x, gna, scale_max, diag_good, n_good, perspective="local")
+    for devices in ([0, 1 % ndev, 0], list(range(ndev)) if ndev > 1 else [0, 0], [0, 0, 0, 0, 0]):
+        many = _lib.run_matrices(x, gna, scale_max, diag_good, n_good, perspective="local", devices=devices)
+        for k in _lib.MATRIX_NAMES:
+            assert np.array_equal(one[k].view(np.uint64), many[k].view(np.uint64)), (k, devices)
+        assert np.array_equal(one["status_counts"], many["status_counts"]), devices
+        assert one["max_taumax"] == many["max_taumax"]
+    # n_good derived by the library (n - missing rows) when the caller passes none
+    a = _lib.run_matrices(x, (), scale_max, diag_good, None, perspective="global")
+    b = _lib.run_matrices(x, (), scale_max, diag_good, None, perspective="global", devices=[0, 0, 0])
+    for k in _lib.MATRIX_NAMES:
+        assert np.array_equal(a[k].view(np.uint64), b[k].view(np.uint64)), k
+    # and through the R-level API
+    names = [f"s{i}" for i in range(x.shape[1])]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r1 = ik.ici_kendalltau(x, colnames=names)
+        r2 = ik.ici_kendalltau(x, colnames=names, n_gpus=max(2, min(ndev, 8)) if ndev > 1 else 1)
+    for k in _lib.MATRIX_NAMES:
+        assert np.array_equal(r1[k], r2[k], equal_nan=True), k

@@ -28,8 +28,8 @@ def _matrix(seed=3, n=700, C=9):
     x = rng.normal(size=(n, 1)) + rng.normal(size=(n, C))
     x[:, 2] = np.round(x[:, 2] * 2)
     x = np.where(x < np.quantile(x, 0.2), np.nan, x)
-    x[:, 5] = 4.25      # single unique value -> status 3
-    x[:, 7] = np.nan    # all missing -> status 1
+    x[:, C - 4] = 4.25    # single unique value -> status 3
+    x[:, C - 2] = np.nan  # all missing -> status 1
     return np.asfortranarray(x)
 
 
@@ -112,8 +112,15 @@ def test_matrices_entry_matches_binding(sh, scale_max, diag_good, listed):
         assert r[k].shape == (8, 8)
         assert np.array_equal(r[k].view(np.uint64), ref[k].view(np.uint64)), k  # bit patterns: NA_real_ included
     assert np.array_equal(r["status_counts"].astype(np.int64), ref["status_counts"])
-    assert sh.is_na(r["cor"][5, 0]) if not listed else True  # the constant column: NA, symmetric
+    assert sh.is_na(r["cor"][4, 0]) if not listed else True  # the constant column: NA, symmetric
     assert _same(r["raw"], r["raw"].T)
+    if not listed:  # a vector of ordinals: icikt_matrices_multi, the very same bytes
+        ndev = _lib.load().icikt_device_count()
+        rm = sh.dot_call("C_icikt_matrices", sh.real_matrix(x), sh.real([0.0]), sh.nil(), sh.nil(),
+                         sh.string("global"), sh.string("two.sided"), sh.logical(False), sh.logical(True),
+                         sh.integer([0, 1 % ndev, 0]), sh.logical(scale_max), sh.logical(diag_good), sh.integer(n_good))
+        for k in r:
+            assert np.array_equal(r[k].view(np.uint64), rm[k].view(np.uint64)), k
 
 
 def test_pairwise_completeness_entry_matches_binding(sh):
