@@ -1333,6 +1333,10 @@ int measure_issue_rate(double* alu, double* fma, double* mixed) {
   return 0;
 }
 
+// Pass A sums the word indices of a thread's hi = 1 keys in two packed 16-bit fields (count_pass):
+// 2 kk (4 kk - 1) must stay below 65 536
+constexpr int kMaxRuns = 90;
+
 // 8-key runs per thread such that W warps cover n keys: the smallest odd count (bank-conflict-free
 // 128-bit loads), unless that pushes the padded length past the 65536 slots the packed 16-bit
 // slot indices of pass A can address; then the smallest count, or 0 if W cannot cover n at all.
@@ -1384,7 +1388,7 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n
   double best = 1e300;
   for (int w = 1; w <= 32; ++w) {
     const int kk = odd_runs(n, w);
-    if (kk == 0) continue;
+    if (kk == 0 || kk > kMaxRuns) continue;
     const size_t smem = smem_of(w);
     if (smem > 227 * 1024) continue;
     // resident CTAs per SM: threads, shared memory, registers (64 per thread in the roomy class)
@@ -1400,7 +1404,7 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n
   }
   if (const char* e = getenv("ICIKT_WARPS")) {
     const int v = atoi(e);
-    if (v >= 1 && v <= 32 && odd_runs(n, v) > 0) W = v;
+    if (v >= 1 && v <= 32 && odd_runs(n, v) > 0 && odd_runs(n, v) <= kMaxRuns) W = v;
   }
   if (getenv("ICIKT_FORCE_GMEM")) W = 32;
   sh.warps = W;
