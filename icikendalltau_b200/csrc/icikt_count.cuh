@@ -281,23 +281,34 @@ __device__ __forceinline__ uint32_t level_share(const LevelCounts& c, uint32_t R
   return hi_term + lo_term;
 }
 
+// `lead`: the sequence is known to START with that many zero keys (x's first tie group is written in
+// ascending y order, so its rows of y's lowest rank -- on left-censored data the rows missing in BOTH
+// columns, a fifth of all rows -- come first).  Zero keys are class 0 at every level and the stable
+// partition keeps a leading block of them exactly where it is; no one-key ever precedes them, so they
+// add nothing to any count.  Threads whose whole range lies inside that block skip both sweeps of
+// every level (they only take part in the scans, with zero counts, and in the barriers).
 template <bool G>
 __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<G>::ptr b, const int kk,
                                            const int nwarps, const int L, uint32_t* descA, uint32_t* descB,
                                            const int lane, const int warp, const PipeConst pc,
-                                           unsigned long long& acc64) {
+                                           unsigned long long& acc64, const uint32_t lead = 0u) {
   typedef Mem<G> M;
   const uint32_t tid = ((uint32_t)warp << 5) + (uint32_t)lane;
   const uint32_t R = (uint32_t)kk << 3;                // keys per thread range
   const uint32_t my_off = tid * (R << 1);              // bytes
   const uint32_t my_pos = tid * R;
   const uint32_t cap = ((uint32_t)nwarps << 5) * R;    // keys per buffer
+  const bool idle = my_pos + R <= lead;
+  if (idle && L > 2) {  // the block must read as zeros in the other buffer too (levels alternate)
+    const typename M::ptr rb = M::add(b, (int32_t)my_off);
+    for (int c = 0; c < kk; ++c) M::st128(M::add(rb, c << 4), 0u, 0u, 0u, 0u);
+  }
   for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
     const typename M::ptr ra = M::add(a, (int32_t)my_off);
     uint32_t cl = 0, cb = 0, wm = 0, m4 = 0;
     uint32_t chj[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
-    for (int c = 0; c < kk; ++c) {
+    for (int c = 0; c < (idle ? 0 : kk); ++c) {
       uint32_t w[4];
       M::ld128(M::add(ra, c << 4), w[0], w[1], w[2], w[3]);
 #pragma unroll
@@ -342,7 +353,9 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
     uint32_t acc2 = 0;
     uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
     asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));  // keep the bit tests single LOP3s
-    if (s > 0) {
+    if (idle) {
+      // nothing to move, nothing to count
+    } else if (s > 0) {
 #pragma unroll 1
       for (int c = 0; c < kk; ++c) {
         uint32_t w[4];
@@ -366,7 +379,7 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
       }
     }
     (void)N3;
-    acc64 += (unsigned long long)level_share(lc, R, acc2, e2 + e3, start1, start3, N0, N2);
+    if (!idle) acc64 += (unsigned long long)level_share(lc, R, acc2, e2 + e3, start1, start3, N0, N2);
     __syncthreads();  // also protects descA/descB for the next level
     const typename M::ptr t = a;
     a = b;

@@ -167,7 +167,8 @@ __device__ __forceinline__ void bucket_pass(typename Mem<G>::ptr a, typename Mem
 template <int KK>
 __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int nwarps, const int L,
                                                    uint32_t* descA, uint32_t* descB, const int lane,
-                                                   const int warp, const PipeConst pc, unsigned long long& acc64) {
+                                                   const int warp, const PipeConst pc, unsigned long long& acc64,
+                                                   const uint32_t lead) {
   typedef Mem<false> M;
   const uint32_t tid = ((uint32_t)warp << 5) + (uint32_t)lane;
   constexpr uint32_t R = (uint32_t)KK << 3;
@@ -175,9 +176,14 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
   const uint32_t my_pos = tid * R;
   const uint32_t cap = ((uint32_t)nwarps << 5) * R;
   const uint32_t ra = a + my_off;
+  const bool idle = my_pos + R <= lead;  // inside the leading block of zero keys, see count_pass
   for (int s = (L - 1) & ~1; s >= 0; s -= 2) {
     uint32_t w[KK][4];
     uint32_t cl = 0, ch = 0, cb = 0, wm = 0;
+    if (idle) {  // (block-divergent, warp-mostly-uniform) nothing to load: every key is zero
+#pragma unroll
+      for (int c = 0; c < KK; ++c) w[c][0] = w[c][1] = w[c][2] = w[c][3] = 0u;
+    } else
 #pragma unroll
     for (int c = 0; c < KK; ++c) {
       M::ld128(ra + (c << 4), w[c][0], w[c][1], w[c][2], w[c][3]);
@@ -220,7 +226,9 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
     uint32_t acc2 = 0;
     uint32_t bLl = 1u << s, bHl = 2u << s, bLh = 1u << (s + 16), bHh = 2u << (s + 16);
     asm volatile("" : "+r"(bLl), "+r"(bHl), "+r"(bLh), "+r"(bHh));
-    if (s > 0) {
+    if (idle) {
+      // the block stays where it is
+    } else if (s > 0) {
 #pragma unroll
       for (int c = 0; c < KK; ++c) {
 #pragma unroll
@@ -240,7 +248,7 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
       }
     }
     (void)N3;
-    acc64 += (unsigned long long)level_share(lc, R, acc2, e2 + e3, start1, start3, N0, N2);
+    if (!idle) acc64 += (unsigned long long)level_share(lc, R, acc2, e2 + e3, start1, start3, N0, N2);
     __syncthreads();
   }
 }
@@ -324,6 +332,8 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
       if (lane == 0 && zeros) M::red_add32(hist, zeros);
     }
     __syncthreads();
+    // rows of the group with the other column's lowest rank: they lead the emitted sequence
+    if (EMIT && k0 == 0 && tid == 0) mini[18] = M::ld32(hist) & 0xffffu;
     // 2. rows per thread range, block scan
     const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
     uint32_t pos = 0, total = 0;
@@ -765,6 +775,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       // previous pair) as one TMA bulk copy, in flight during the mask counting below
       if (!RG && tid == 0)
         bulk_g2s(smem_addr(sm.region_ptr) + 2u * (uint32_t)cap, rankY_g, (uint32_t)p.nstride * 2u, mbar);
+      if (tid == 0) sm.mini[18] = 0u;  // leading zero keys of the sequence (set by the first-group emission)
       // joint-missing rows (b) and joint lowest group (g00, differs from b only if a column's
       // missing rows tie with its minimum)
       uint32_t bpart = 0, g00part = 0;
@@ -873,11 +884,13 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
                                        sm.descT, sm.mini + 16, nwarps);
       }
       unsigned long long accA = 0;
+      const uint32_t lead = sm.mini[18];  // published by the barrier after the gather
       if (IP != 0)
         count_pass_inplace<(IP != 0 ? IP : 1)>(smem_addr(sm.region_ptr), nwarps, L, sm.descT,
-                                               reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
+                                               reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA, lead);
       else
-        count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA);
+        count_pass<G>(bufA, bufB16, kk, nwarps, L, sm.descT, reinterpret_cast<uint32_t*>(sm.descB), lane, warp, p.pc, accA,
+                      lead);
       if (IP == 0 && m > 0 && by_pass_b) {
         const int kkB = (((m + 31) >> 5) + nwarps - 1) / nwarps;
         const int capB = (nwarps * kkB) << 5;
