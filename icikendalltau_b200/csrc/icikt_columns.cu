@@ -253,6 +253,57 @@ __host__ __device__ inline int sort_threads(int n, int threads) {
   return t < threads ? t : threads;
 }
 
+// The order by the keys' HIGH 32 bits is almost the order by the keys: two doubles share their high word only
+// if they agree to ~6 significant digits (or are integers below 2^21, whose low word is zero anyway).  So the
+// sort runs its 8 passes on the high word only and this routine repairs what is left: an odd-even
+// transposition restricted to neighbours with EQUAL high words, comparing the low words.  Runs of equal high
+// words are short in practice (a few pairs per column of continuous data; tie groups of count data need no
+// swap at all), so one or two double rounds suffice.  Returns false if `max_rounds` double rounds did not
+// finish the job (long runs of values that differ only in the low word): the caller then sorts all 64 bits.
+// Thread t < T owns the pairs (p, p + 1) whose first position lies in its slice; `cur` is read and written.
+__device__ __forceinline__ bool repair_equal_high_runs(const unsigned char* hi_src, const int hi_shift, const int hi_off,
+                                                       const unsigned char* lo_src, const int lo_shift, const int lo_off,
+                                                       uint16_t* cur, const int n, uint32_t* misc, const int T,
+                                                       const int max_rounds) {
+  const int tid = threadIdx.x;
+  const int I = (n + T - 1) / T;
+  const int p0 = tid < T ? min(tid * I, n) : n, p1 = min(p0 + I, n);
+  for (int round = 0; round < max_rounds; ++round) {
+    if (tid == 0) misc[9] = 0u;
+    __syncthreads();
+    for (int parity = 0; parity < 2; ++parity) {
+      bool changed = false;
+      for (int p = p0 + ((p0 ^ parity) & 1); p < p1 && p + 1 < n; p += 2) {
+        const uint32_t a = cur[p], b = cur[p + 1];
+        const uint32_t ha = *reinterpret_cast<const uint32_t*>(hi_src + ((size_t)a << hi_shift) + hi_off);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(hi_src + ((size_t)b << hi_shift) + hi_off);
+        if (ha == hb) {
+          const uint32_t la = *reinterpret_cast<const uint32_t*>(lo_src + ((size_t)a << lo_shift) + lo_off);
+          const uint32_t lb = *reinterpret_cast<const uint32_t*>(lo_src + ((size_t)b << lo_shift) + lo_off);
+          if (la > lb) {
+            cur[p] = (uint16_t)b;
+            cur[p + 1] = (uint16_t)a;
+            changed = true;
+          }
+        }
+      }
+      if (changed) misc[9] = 1u;
+      __syncthreads();
+    }
+    const bool done = misc[9] == 0u;
+    __syncthreads();  // misc[9] is reset at the top of the next round
+    if (done) return true;
+  }
+  return false;
+}
+
+// the identity order, for a column whose high-word passes were all skipped
+__device__ __forceinline__ void fill_identity(uint16_t* buf, int n) {
+  for (int t = threadIdx.x; t < n; t += blockDim.x) buf[t] = (uint16_t)t;
+  __syncthreads();
+}
+constexpr int kRepairRounds = 6;
+
 // counters of the sort: cnt8 [16][T] bytes, pre16 [16][T] u16, misc 64 words
 __host__ __device__ inline size_t sort_counter_bytes(int threads) { return 48 * (size_t)threads + 256; }
 
@@ -306,8 +357,15 @@ __global__ void __launch_bounds__(SORT_THREADS)
       if ((tid & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
     }
     __syncthreads();
-    const uint16_t* cur = radix_argsort(reinterpret_cast<const unsigned char*>(skey), 3, 0, 64, nullptr, idA, idB, n,
-                                        cnt8, pre16, smisc, sort_threads(n, SORT_THREADS));
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(skey);
+    const int ts = sort_threads(n, SORT_THREADS);
+    const uint16_t* cur = radix_argsort(kb, 3, 32, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, ts);  // high words
+    if (!cur) {
+      fill_identity(idA, n);
+      cur = idA;
+    }
+    if (!repair_equal_high_runs(kb, 3, 4, kb, 3, 0, const_cast<uint16_t*>(cur), n, smisc, ts, kRepairRounds))
+      cur = radix_argsort(kb, 3, 0, 64, nullptr, idA, idB, n, cnt8, pre16, smisc, ts);  // all 64 bits, from scratch
     // blocked arrangement: thread t takes sorted positions t*ITEMS .. (padding sorts last; no value
     // maps to the all-ones key, NaN being missing)
 #pragma unroll
@@ -593,23 +651,36 @@ __global__ void __launch_bounds__(kSortThreads)
       for (int g = 0; g < n_global_na; ++g) miss = miss || (v == global_na[g]);
       const unsigned long long k = miss ? 0ull : order_key(v);
       kin[r] = k;
-      if (SM) part[r] = (uint32_t)k;
+      if (SM) part[r] = (uint32_t)(k >> 32);
     }
     const uint32_t m = __ballot_sync(FULL, miss);
     if ((tid & 31) == 0 && (r >> 5) < wstride) nabits[(size_t)col * wstride + (r >> 5)] = m;
   }
   __syncthreads();
-  const uint16_t* cur = nullptr;
-  if (SM) {
-    cur = radix_argsort(reinterpret_cast<const unsigned char*>(part), 2, 0, 32, cur, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
-    __syncthreads();
-    for (int r = tid; r < n; r += kSortThreads) part[r] = (uint32_t)(kin[r] >> 32);  // written by this thread above
-    __syncthreads();
-    cur = radix_argsort(reinterpret_cast<const unsigned char*>(part), 2, 0, 32, cur, idA, idB, n, cnt8, pre16, smisc,
-                        kSortThreads);
-  } else {
-    cur = radix_argsort(reinterpret_cast<const unsigned char*>(kin), 3, 0, 64, cur, idA, idB, n, cnt8, pre16, smisc,
-                        kSortThreads);
+  // high words first, then the repair of equal-high runs against the low words (read from the key array in
+  // global memory: only neighbours with equal high words look there); all 64 bits only if the repair gives up
+  const unsigned char* kb = reinterpret_cast<const unsigned char*>(kin);
+  const unsigned char* pb = reinterpret_cast<const unsigned char*>(part);
+  const uint16_t* cur = SM ? radix_argsort(pb, 2, 0, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads)
+                           : radix_argsort(kb, 3, 32, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+  if (!cur) {
+    fill_identity(idA, n);
+    cur = idA;
+  }
+  const bool repaired = SM ? repair_equal_high_runs(pb, 2, 0, kb, 3, 0, const_cast<uint16_t*>(cur), n, smisc, kSortThreads, kRepairRounds)
+                           : repair_equal_high_runs(kb, 3, 4, kb, 3, 0, const_cast<uint16_t*>(cur), n, smisc, kSortThreads, kRepairRounds);
+  if (!repaired) {
+    if (SM) {
+      for (int r = tid; r < n; r += kSortThreads) part[r] = (uint32_t)kin[r];
+      __syncthreads();
+      cur = radix_argsort(pb, 2, 0, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+      __syncthreads();
+      for (int r = tid; r < n; r += kSortThreads) part[r] = (uint32_t)(kin[r] >> 32);
+      __syncthreads();
+      cur = radix_argsort(pb, 2, 0, 32, cur, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+    } else {
+      cur = radix_argsort(kb, 3, 0, 64, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+    }
   }
   __syncthreads();
   unsigned long long* ko = keys_out + (size_t)col * nstride;

@@ -908,3 +908,29 @@ def test_multi_gpu_matrices_match_single_gpu(scale_max, diag_good):
         r2 = ik.ici_kendalltau(x, colnames=names, n_gpus=max(2, min(ndev, 8)) if ndev > 1 else 1)
     for k in _lib.MATRIX_NAMES:
         assert np.array_equal(r1[k], r2[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [3000, 12000, 30000])
+def test_sort_high_word_collisions(n):
+    """K1 sorts the keys' high 32 bits and repairs neighbours with equal high words against the low words;
+    long runs fall back to the full 64-bit sort.  Columns built to hit every branch, in all three sort
+    variants (fused n <= 8192, shared-memory n <= 22528, global): values that differ ONLY in the low word
+    (one run as long as the column -> fallback), clusters of 2..11 such values inside ordinary data (repair),
+    integers (low word zero: ties, nothing to repair), plus missing values."""
+    rng = np.random.default_rng(n)
+    eps = 2.0 ** -45
+    c0 = 1.0 + eps * rng.permutation(n)                         # all high words equal, all values distinct
+    c1 = rng.normal(size=n)
+    for start in range(0, n - 16, 97):                          # clusters that share a high word
+        k = int(rng.integers(2, 12))
+        c1[start:start + k] = c1[start] * (1.0 + eps * rng.permutation(k))
+    c2 = np.floor(np.exp(rng.normal(size=n) * 2.0))             # counts
+    c3 = rng.normal(size=n)
+    c4 = np.where(rng.random(n) < 0.5, 3.0 + eps * rng.integers(0, 6, size=n), rng.normal(size=n))  # short runs + ties
+    x = np.column_stack([c0, c1, c2, c3, c4])
+    x[rng.random(x.shape) < 0.15] = np.nan
+    x = np.asfortranarray(x)
+    for persp in ("global", "local"):
+        got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
+        assert_parity(got, oracle_pairs(x, perspective=persp), f"high-word collisions n={n} {persp}")
