@@ -300,15 +300,65 @@ int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes) {
   return ICIKT_OK;
 }
 
+int ensure_stage(icikt_plan* p) {
+  if (p->h_stage[0]) return ICIKT_OK;
+  p->stage_bytes = stage_chunk();
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_stage[i]), p->stage_bytes));
+    CK(cudaEventCreateWithFlags(&p->stage_ev[i], cudaEventDisableTiming));
+  }
+  return ICIKT_OK;
+}
+
+// Pageable host memory -> device through the plan's two pinned chunks: cudaMemcpyAsync from pageable
+// memory is staged by the driver on one thread (~10 GB/s, a fraction of the link); here chunk k + 1 is
+// copied into pinned memory by several host threads while chunk k is on the wire.  The source is fully
+// consumed when this returns (same guarantee as the plain call).
+int staged_copy_in(icikt_plan* p, void* d_dst, const void* src, size_t bytes) {
+  int rc = ensure_stage(p);
+  if (rc != ICIKT_OK) return rc;
+  unsigned char* dst = static_cast<unsigned char*>(d_dst);
+  const unsigned char* in = static_cast<const unsigned char*>(src);
+  bool pending[2] = {false, false};
+  int k = 0;
+  for (size_t o = 0; o < bytes; ++k) {
+    const int cur = k & 1;
+    if (pending[cur]) CK(cudaEventSynchronize(p->stage_ev[cur]));  // the chunk sent two steps ago has left
+    const size_t l = std::min(p->stage_bytes, bytes - o);
+    host_copy(p->h_stage[cur], in + o, l);
+    CK(cudaMemcpyAsync(dst + o, p->h_stage[cur], l, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaEventRecord(p->stage_ev[cur], p->stream));
+    pending[cur] = true;
+    o += l;
+  }
+  return ICIKT_OK;
+}
+
+bool host_is_pinned(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 // host -> device copy of columns [c_lo, c_hi) into the plan's own matrix buffer
 int upload_columns(icikt_plan* p, const double* data, int64_t ld, int64_t c_lo, int64_t c_hi) {
   CK(cudaSetDevice(p->device));
   if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
   CK(cudaEventRecord(p->ev[0], p->stream));
-  if (c_hi > c_lo)
-    CK(cudaMemcpy2DAsync(p->d_data_own + (size_t)c_lo * p->n, sizeof(double) * p->n, data + (size_t)c_lo * ld,
-                         sizeof(double) * ld, sizeof(double) * p->n, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice,
-                         p->stream));
+  if (c_hi > c_lo) {
+    const size_t bytes = sizeof(double) * (size_t)p->n * (size_t)(c_hi - c_lo);
+    if (ld == p->n && bytes >= (8u << 20) && !std::getenv("ICIKT_NO_STAGED_UPLOAD") && !host_is_pinned(data + (size_t)c_lo * ld)) {
+      const int rc = staged_copy_in(p, p->d_data_own + (size_t)c_lo * p->n, data + (size_t)c_lo * ld, bytes);
+      if (rc != ICIKT_OK) return rc;
+    } else {
+      CK(cudaMemcpy2DAsync(p->d_data_own + (size_t)c_lo * p->n, sizeof(double) * p->n, data + (size_t)c_lo * ld,
+                           sizeof(double) * ld, sizeof(double) * p->n, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice,
+                           p->stream));
+    }
+  }
   CK(cudaEventRecord(p->ev[1], p->stream));
   p->d_data = p->d_data_own;
   p->ld = p->n;
@@ -495,17 +545,7 @@ int64_t icikt_plan_num_pairs(const icikt_plan* p) { return p ? p->P : 0; }
 
 int icikt_plan_upload(icikt_plan* p, const double* data, int64_t ld) {
   if (!p || !data || ld < p->n) return fail(ICIKT_ERR_BAD_ARG, "bad upload arguments");
-  CK(cudaSetDevice(p->device));
-  if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
-  CK(cudaEventRecord(p->ev[0], p->stream));
-  CK(cudaMemcpy2DAsync(p->d_data_own, sizeof(double) * p->n, data, sizeof(double) * ld,
-                       sizeof(double) * p->n, (size_t)p->C, cudaMemcpyHostToDevice, p->stream));
-  CK(cudaEventRecord(p->ev[1], p->stream));
-  p->d_data = p->d_data_own;
-  p->ld = p->n;
-  p->columns_done = false;
-  p->pairs_done = false;
-  return ICIKT_OK;
+  return upload_columns(p, data, ld, 0, p->C);
 }
 
 int icikt_plan_set_device_matrix(icikt_plan* p, const double* d_data, int64_t ld) {
@@ -805,12 +845,9 @@ int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_
     for (int k = 0; k < 5; ++k)
       if (outs[k]) host_copy(outs[k], p->h_mat + (size_t)k * cc * sizeof(double), sizeof(double) * cc);
   } else {
-    if (!p->h_stage[0]) {
-      p->stage_bytes = stage_chunk();
-      for (int i = 0; i < 2; ++i) {
-        CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_stage[i]), p->stage_bytes));
-        CK(cudaEventCreateWithFlags(&p->stage_ev[i], cudaEventDisableTiming));
-      }
+    {
+      const int rc = ensure_stage(p);
+      if (rc != ICIKT_OK) return rc;
     }
     for (int k = 0; k < 5; ++k)
       if (outs[k]) {
@@ -1337,12 +1374,9 @@ int icikt_matrices_multi(const double* data, int64_t n, int64_t C, int64_t ld, c
         }
         if (!p->d_hist) CK(dmalloc(&p->d_hist, 16));
         if (!p->d_ngood) CK(dmalloc(&p->d_ngood, (size_t)C));
-        if (!p->h_stage[0]) {
-          p->stage_bytes = stage_chunk();
-          for (int i = 0; i < 2; ++i) {
-            CK(cudaMallocHost(reinterpret_cast<void**>(&p->h_stage[i]), p->stage_bytes));
-            CK(cudaEventCreateWithFlags(&p->stage_ev[i], cudaEventDisableTiming));
-          }
+        {
+          const int r3 = ensure_stage(p);
+          if (r3 != ICIKT_OK) return r3;
         }
         CK(cudaEventRecord(p->ev[6], p->stream));
         CK(cudaMemsetAsync(p->d_hist, 0, 16 * sizeof(unsigned long long), p->stream));
