@@ -11,12 +11,14 @@
 //                       contiguous slice of the current order in byte counters, one flat scan over
 //                       the [digit][thread] counters makes the pass stable.  Stability itself is
 //                       irrelevant downstream (rows of a tie group are interchangeable for every
-//                       count) but is what makes LSD passes compose.
+//                       count) but is what makes LSD passes compose.  The passes run on the keys' HIGH
+//                       32 bits only; neighbours with equal high words are then put in order by their
+//                       low words (repair_equal_high_runs), all 64 bits are sorted only if that gives up.
 //   ranks and tables    compare_self + cumsum (:15-31, :250-251) -> dense ranks; tie-group
 //                       sizes -> count_rank_tie sums (:103-118) in exact int64; the bit masks
 //                       and the tied-row list (rows + dense group index) the pair kernel needs.
 //   Three shapes: n <= 8192 one fused kernel per column (keys in shared memory, everything else in
-//   registers); n <= 22528 sort kernel with the keys' 32-bit halves and both row-id buffers in
+//   registers); n <= 22528 sort kernel with the keys' high words and both row-id buffers in
 //   shared memory + rank kernel; longer columns the same sort on global (L2-resident) buffers.
 #include <algorithm>
 #include <cstdlib>
@@ -617,8 +619,8 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
 }
 
 // Long columns (n > 8192): keys + sort in one kernel, one 1024-thread CTA per column.
-//   SM = true  (n <= kSortSmemRows): the keys' 32-bit halves (low half first, then the high half:
-//              4 + 4 byte passes) and both row-id buffers live in shared memory, 8 bytes per row;
+//   SM = true  (n <= kSortSmemRows): the keys' high words (the low words only if the repair of equal-high
+//              runs gives up) and both row-id buffers live in shared memory, 8 bytes per row;
 //   SM = false (longer): the same passes on global memory -- digits are read from the column's key
 //              array (480 KB at n = 60 000, L2 resident), the row ids ping-pong between `perm` and a
 //              scratch column.  Such shapes spend < 2 % of a job here.
