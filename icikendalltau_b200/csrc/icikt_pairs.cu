@@ -475,6 +475,14 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
 // not even one group's K counters fit, one group at a time in windows of ranks.  Returns (summed
 // over the threads) the joint ties inside those groups.  `pre` is a shared array of 256 words;
 // `lg` the column's (start, size) table.
+// Rows of one bin met by several lanes are added once (match.any + one atomic per distinct bin).  Plain
+// shared-memory atomics (ICIKT_MATCH_DEDUP=0) are 3 % faster on config 4 (27.7 against 28.6 ms), but the
+// different register allocation of the whole kernel costs the tie-free target 2.7 % (278.9 against 271.4 ms,
+// same box clocks; profiles/r02_match_dedup_ab.txt), so the deduplicating form stays.
+#ifndef ICIKT_MATCH_DEDUP
+#define ICIKT_MATCH_DEDUP 1
+#endif
+constexpr bool kMatchDedup = ICIKT_MATCH_DEDUP != 0;
 template <bool G, bool RG>
 __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                         const int hist_words, const uint16_t* __restrict__ permX,
@@ -519,9 +527,13 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
             in = r < (uint32_t)kw;
             if (in) bin = (uint32_t)(j * kw) + r;
           }
-          const uint32_t peers = __match_any_sync(FULL, bin);
-          if (in && (peers & ((1u << lane) - 1u)) == 0u)
-            M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), (uint32_t)__popc(peers) << ((bin & 1u) * 16u));
+          if (kMatchDedup) {  // rows of one bin met by several lanes are added once
+            const uint32_t peers = __match_any_sync(FULL, bin);
+            if (in && (peers & ((1u << lane) - 1u)) == 0u)
+              M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), (uint32_t)__popc(peers) << ((bin & 1u) * 16u));
+          } else if (in) {
+            M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), 1u << ((bin & 1u) * 16u));
+          }
         }
       }
       __syncthreads();
