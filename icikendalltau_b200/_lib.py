@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicikt_b200.so")
+# ICIKT_LIB_PATH: another build of the same library (A/B runs of tuning variants); default: the in-tree build
+LIB_PATH = os.environ.get("ICIKT_LIB_PATH") or os.path.join(_HERE, "libicikt_b200.so")
 
 OK = 0
 ERR_NO_DEVICE, ERR_BAD_ARG, ERR_TOO_LONG, ERR_CUDA, ERR_ALLOC = -1, -2, -3, -4, -5

@@ -934,3 +934,21 @@ def test_sort_high_word_collisions(n):
     for persp in ("global", "local"):
         got = ik.run_pairs(x, (), perspective=persp, want_counts=True)
         assert_parity(got, oracle_pairs(x, perspective=persp), f"high-word collisions n={n} {persp}")
+
+
+@pytest.mark.gpu
+def test_staged_pageable_upload_matches_plain_copy(monkeypatch):
+    """Matrices of 8 MB and more in pageable host memory are uploaded through the plan's two pinned chunks by
+    several host threads (staged_copy_in); the results must be the bytes of the plain cudaMemcpy2DAsync path,
+    also when the matrix is larger than one chunk and the last chunk is ragged."""
+    x = gen(1300, 900, "mixed", 0.2, seed=31337)  # 9.4 MB
+    monkeypatch.setenv("ICIKT_STAGE_CHUNK", str(3 << 20))  # several chunks, ragged tail
+    _lib.release_workspace()
+    a = ik.run_pairs(x, (), perspective="local", pair_lo=0, pair_hi=5000)
+    monkeypatch.setenv("ICIKT_NO_STAGED_UPLOAD", "1")
+    _lib.release_workspace()
+    b = ik.run_pairs(x, (), perspective="local", pair_lo=0, pair_hi=5000)
+    _lib.release_workspace()
+    for k in ("raw", "pvalue", "taumax", "completeness", "status"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert a["max_taumax"] == b["max_taumax"]
