@@ -11,6 +11,9 @@
 #ifndef ICIKT_COUNT_UNROLL
 #define ICIKT_COUNT_UNROLL 1
 #endif
+#ifndef ICIKT_HI_KEY_MASKS
+#define ICIKT_HI_KEY_MASKS 1
+#endif
 #ifndef ICIKT_SCATTER_UNROLL
 #define ICIKT_SCATTER_UNROLL 1
 #endif
@@ -372,7 +375,12 @@ __device__ __forceinline__ void count_pass(typename Mem<G>::ptr a, typename Mem<
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           M::step4(Q01, Q23, acc2, w[j], bLl, bHl, w[j], b, pc);
+#if ICIKT_HI_KEY_MASKS
           M::step4(Q01, Q23, acc2, w[j], bLh, bHh, M::hi16(w[j], pc.c64k), b, pc);
+#else
+          const uint32_t kh = M::hi16(w[j], pc.c64k);  // the odd key, tested with the even key's masks
+          M::step4(Q01, Q23, acc2, kh, bLl, bHl, kh, b, pc);
+#endif
         }
       }
     } else {  // the sorted sequence itself is not needed: the last level only counts

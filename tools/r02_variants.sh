@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of build variants of the same library (ICIKT_LIB_PATH), target + config 5, quick benches
 mkdir -p gpurun_out
-for v in base su2 cu2 cu5 exp o2 base; do
+for v in base khm base khm; do
 for wl in target config5; do
 ICIKT_LIB_PATH=$PWD/icikendalltau_b200/variant_$v.so timeout 600 python bench.py --workload $wl --steps 5 --warmup 3 --quick 2>/dev/null | tail -1 | python -c "
 import json,sys
