@@ -32,7 +32,7 @@ EXPORTS = [
     "icikt_pair_from_index", "icikt_all_pairs_multi", "icikt_matrices", "icikt_plan_download_matrices",
     "icikt_pairwise_completeness", "icikt_plan_upload_columns", "icikt_plan_columns_range",
     "icikt_plan_tables", "icikt_plan_columns_finish", "icikt_measure_issue_rate",
-    "icikt_matrices_multi",
+    "icikt_matrices_multi", "icikt_stage_table",
 ]
 NSTATUS = 10
 
@@ -160,6 +160,9 @@ def load():
     L.icikt_measure_smem_bandwidth.restype = ctypes.c_int
     L.icikt_measure_issue_rate.argtypes = [ctypes.c_int32, _dp, _dp, _dp]
     L.icikt_measure_issue_rate.restype = ctypes.c_int
+    L.icikt_stage_table.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                    _lp, ctypes.c_int64, _lp, _lp]
+    L.icikt_stage_table.restype = ctypes.c_int64
     _lib = L
     return L
 
@@ -433,6 +436,22 @@ def measure_issue_rate(device=0):
     a, f, m = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
     check(load().icikt_measure_issue_rate(device, ctypes.byref(a), ctypes.byref(f), ctypes.byref(m)))
     return a.value, f.value, m.value
+
+
+def stage_table(C, include_diag=False, cta_slots=296, n_blocks=8):
+    """The launches of the pipelined one-shot call for C columns (host only, no device needed):
+    (units [U, 4] = slot, first column, other column of the first pair, pairs;
+     launches [L, 6] = col_lo, col_hi, unit_lo, unit_hi, slot_lo, slot_hi)."""
+    L = load()
+    nl = ctypes.c_int64(0)
+    nu = L.icikt_stage_table(C, int(bool(include_diag)), cta_slots, n_blocks, 0, None, 0, None, ctypes.byref(nl))
+    if nu < 0:
+        check(int(nu))
+    units = np.zeros((max(nu, 1), 4), dtype=np.int64)
+    launches = np.zeros((max(nl.value, 1), 6), dtype=np.int64)
+    L.icikt_stage_table(C, int(bool(include_diag)), cta_slots, n_blocks, nu, units.ctypes.data, nl.value,
+                        launches.ctypes.data, ctypes.byref(nl))
+    return units[:nu], launches[:nl.value]
 
 
 def pair_from_index(C, index, include_diag=False):

@@ -65,6 +65,111 @@ static size_t env_bytes(const char* name, size_t dflt) {
 static size_t stage_all() { return env_bytes("ICIKT_STAGE_ALL", 96u << 20); }
 static size_t stage_chunk() { return env_bytes("ICIKT_STAGE_CHUNK", 32u << 20); }
 
+// One launch of the pipelined one-shot call.
+struct StageLaunch {
+  int64_t col_lo = 0, col_hi = 0;    // columns uploaded and preprocessed right before it (empty: none)
+  int64_t unit_lo = 0, unit_hi = 0;  // its units
+  int64_t slot_lo = 0, slot_hi = 0;  // results complete once it has run: a contiguous range of the pair order
+  int max_unit_pairs = 1;
+};
+
+// The launches of the pipelined one-shot call over all pairs of C columns (combn order, then the C diagonal
+// pairs if include_diag).  Columns arrive in chunks [0, f), [f, 2f), [2f, 4f) ... (f ~ C/16): the launch of a
+// chunk covers every pair (i, j), i < j, whose LATER column j lies in the chunk, so it needs nothing that has
+// not been uploaded, and the upload of the next chunk hides behind it (the work of a chunk grows with the
+// square of the columns, the upload linearly).  The last chunk holds most of the pairs; it is cut into
+// `n_blocks` row blocks of about equal work: once the block of rows [r0, r1) has run, every pair of those rows
+// is done -- slots [row_start(r0), row_start(r1)) of the pair order -- and can be copied out while the next
+// block runs.  Units never straddle rows; their length tapers off towards the end of a launch (long units
+// while much work is left, single pairs at the end) so that the persistent CTAs run dry together.
+void build_stage_table(int64_t C, bool include_diag, int64_t cta_slots, int n_blocks, std::vector<PairUnit>& U,
+                       std::vector<StageLaunch>& S) {
+  U.clear();
+  S.clear();
+  const int64_t ptri = C * (C - 1) / 2;
+  auto rstart = [C](int64_t i) { return i * (2 * C - i - 1) / 2; };
+  std::vector<int64_t> cb{0};
+  int64_t f = std::max<int64_t>(64, ((C / 16) + 7) & ~int64_t(7));
+  for (; 4 * f <= 3 * C; f *= 2) cb.push_back(f);
+  cb.push_back(C);
+  // pairs (i, j) with r0 <= i < r1 and max(i + 1, lo) <= j < hi, as units appended to U
+  auto emit = [&](int64_t r0, int64_t r1, int64_t lo, int64_t hi, StageLaunch& st) {
+    int64_t total = 0;
+    for (int64_t i = r0; i < r1; ++i) total += std::max<int64_t>(0, hi - std::max(i + 1, lo));
+    const int64_t ulen_max = std::max<int64_t>(1, std::min<int64_t>(16, total / (16 * cta_slots)));
+    int64_t left = total;
+    st.unit_lo = (int64_t)U.size();
+    for (int64_t i = r0; i < r1; ++i) {
+      const int64_t ja = std::max(i + 1, lo);
+      for (int64_t j = ja; j < hi;) {
+        const int64_t want = std::max<int64_t>(1, std::min<int64_t>(ulen_max, left / (4 * cta_slots)));
+        const int64_t len = std::min<int64_t>(want, hi - j);
+        PairUnit u;
+        u.slot0 = rstart(i) + (j - i - 1);
+        u.col = (int32_t)i;
+        u.j0 = (int32_t)j;
+        u.count = (int32_t)len;
+        u.j_explicit = 0;
+        U.push_back(u);
+        st.max_unit_pairs = std::max(st.max_unit_pairs, (int)len);
+        j += len;
+        left -= len;
+      }
+    }
+    st.unit_hi = (int64_t)U.size();
+  };
+  const size_t nchunks = cb.size() - 1;
+  for (size_t s = 0; s + 1 < nchunks; ++s) {
+    StageLaunch st;
+    st.col_lo = cb[s];
+    st.col_hi = cb[s + 1];
+    emit(0, cb[s + 1] - 1, cb[s], cb[s + 1], st);
+    S.push_back(st);
+  }
+  // the last chunk in row blocks of about equal work
+  const int64_t lo = cb[nchunks - 1];
+  int64_t total = 0;
+  for (int64_t i = 0; i + 1 < C; ++i) total += C - std::max(i + 1, lo);
+  const int B = (int)std::max<int64_t>(1, std::min<int64_t>(n_blocks, total / std::max<int64_t>(1, 64 * cta_slots)));
+  int64_t r0 = 0, acc = 0;
+  for (int b = 0; b < B; ++b) {
+    int64_t r1 = r0;
+    const int64_t goal = total * (b + 1) / B;
+    if (b == B - 1) {
+      r1 = std::max<int64_t>(C - 1, 0);
+      acc = total;
+    } else {
+      while (r1 + 1 < C && acc < goal) {
+        acc += C - std::max(r1 + 1, lo);
+        ++r1;
+      }
+    }
+    StageLaunch st;
+    if (b == 0) {
+      st.col_lo = lo;
+      st.col_hi = C;
+    }
+    emit(r0, r1, lo, C, st);
+    st.slot_lo = rstart(r0);
+    st.slot_hi = (b == B - 1) ? ptri : rstart(r1);
+    if (b == B - 1 && include_diag) {
+      for (int64_t i = 0; i < C; ++i) {
+        PairUnit u;
+        u.slot0 = ptri + i;
+        u.col = (int32_t)i;
+        u.j0 = (int32_t)i;
+        u.count = 1;
+        u.j_explicit = 0;
+        U.push_back(u);
+      }
+      st.unit_hi = (int64_t)U.size();
+      st.slot_hi = ptri + C;
+    }
+    S.push_back(st);
+    r0 = r1;
+  }
+}
+
 struct icikt_plan {
   int device = 0;
   int n_sm = 0;
@@ -101,6 +206,7 @@ struct icikt_plan {
   unsigned char* h_stage[2] = {nullptr, nullptr};  // large result sets: two pinned chunks, copy-out pipelined
   size_t stage_bytes = 0;
   cudaEvent_t stage_ev[2]{};
+  bool stage_busy[2] = {false, false};  // an upload out of the chunk is in flight (staged_copy_in)
   size_t res_bytes = 0;
   double *d_tau = nullptr, *d_p = nullptr, *d_tm = nullptr, *d_comp = nullptr;
   unsigned long long* d_maxbits = nullptr;
@@ -116,6 +222,16 @@ struct icikt_plan {
   unsigned long long* d_hist = nullptr;  // [16] pairs per status class
   int32_t* d_ngood = nullptr;       // [C] caller-supplied n_good
   bool pairs_done = false;
+
+  // Pipelined one-shot call (staged plans only, see build_stage_table / run_staged): the pair order is cut
+  // into launches that need only the columns uploaded so far, then into row blocks whose results are
+  // contiguous in the pair order and leave while the next block is computed.
+  bool staged = false;
+  bool staged_run = false;               // the last run went through run_staged (selects the timing sums)
+  std::vector<StageLaunch> stages;
+  cudaStream_t copy_stream = nullptr;    // uploads and downloads of a staged run
+  std::vector<cudaEvent_t> sync_ev;      // per launch: [2l] its columns have landed, [2l+1] its results are ready
+  std::vector<cudaEvent_t> time_ev;      // per launch: K1 start/end, K2 start, K2 end, K3 end
 
   cudaEvent_t ev[9]{};
   icikt_timings tm{};
@@ -164,6 +280,11 @@ void free_plan(icikt_plan* p) {
   cudaFree(p->d_ngood);
   for (auto& e : p->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : p->sync_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : p->time_ev)
+    if (e) cudaEventDestroy(e);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -276,11 +397,12 @@ void host_copy(void* dst, const void* src, size_t bytes) {
 // Device -> pageable host memory through two pinned chunks: the copy of chunk k+1 runs while chunk k
 // is moved from the staging buffer into the caller's array (cudaMemcpyAsync straight into pageable
 // memory is staged by the driver at a fraction of the link rate).
-int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes) {
+int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes, cudaStream_t stream) {
   unsigned char* out = static_cast<unsigned char*>(dst);
   const unsigned char* src = static_cast<const unsigned char*>(d_src);
   size_t off[2] = {0, 0}, len[2] = {0, 0};
   int k = 0;
+  p->stage_busy[0] = p->stage_busy[1] = false;  // uploads out of the chunks precede these copies in stream order
   for (size_t o = 0; o < bytes || len[0] || len[1]; ++k) {
     const int cur = k & 1;
     if (len[cur]) {  // the chunk issued two steps ago has landed in h_stage[cur]
@@ -290,8 +412,8 @@ int staged_copy_out(icikt_plan* p, void* dst, const void* d_src, size_t bytes) {
     }
     if (o < bytes) {
       const size_t l = std::min(p->stage_bytes, bytes - o);
-      CK(cudaMemcpyAsync(p->h_stage[cur], src + o, l, cudaMemcpyDeviceToHost, p->stream));
-      CK(cudaEventRecord(p->stage_ev[cur], p->stream));
+      CK(cudaMemcpyAsync(p->h_stage[cur], src + o, l, cudaMemcpyDeviceToHost, stream));
+      CK(cudaEventRecord(p->stage_ev[cur], stream));
       off[cur] = o;
       len[cur] = l;
       o += l;
@@ -314,21 +436,23 @@ int ensure_stage(icikt_plan* p) {
 // memory is staged by the driver on one thread (~10 GB/s, a fraction of the link); here chunk k + 1 is
 // copied into pinned memory by several host threads while chunk k is on the wire.  The source is fully
 // consumed when this returns (same guarantee as the plain call).
-int staged_copy_in(icikt_plan* p, void* d_dst, const void* src, size_t bytes) {
+int staged_copy_in(icikt_plan* p, void* d_dst, const void* src, size_t bytes, cudaStream_t stream) {
   int rc = ensure_stage(p);
   if (rc != ICIKT_OK) return rc;
   unsigned char* dst = static_cast<unsigned char*>(d_dst);
   const unsigned char* in = static_cast<const unsigned char*>(src);
-  bool pending[2] = {false, false};
   int k = 0;
   for (size_t o = 0; o < bytes; ++k) {
     const int cur = k & 1;
-    if (pending[cur]) CK(cudaEventSynchronize(p->stage_ev[cur]));  // the chunk sent two steps ago has left
+    if (p->stage_busy[cur]) {  // the chunk sent two steps ago (possibly by the previous call) has left
+      CK(cudaEventSynchronize(p->stage_ev[cur]));
+      p->stage_busy[cur] = false;
+    }
     const size_t l = std::min(p->stage_bytes, bytes - o);
     host_copy(p->h_stage[cur], in + o, l);
-    CK(cudaMemcpyAsync(dst + o, p->h_stage[cur], l, cudaMemcpyHostToDevice, p->stream));
-    CK(cudaEventRecord(p->stage_ev[cur], p->stream));
-    pending[cur] = true;
+    CK(cudaMemcpyAsync(dst + o, p->h_stage[cur], l, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(p->stage_ev[cur], stream));
+    p->stage_busy[cur] = true;
     o += l;
   }
   return ICIKT_OK;
@@ -343,27 +467,29 @@ bool host_is_pinned(const void* ptr) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// host -> device copy of columns [c_lo, c_hi) into the plan's own matrix buffer
+// host -> device copy of columns [c_lo, c_hi) into the plan's own matrix buffer, on `stream`
+int copy_columns_in(icikt_plan* p, const double* data, int64_t ld, int64_t c_lo, int64_t c_hi, cudaStream_t stream) {
+  if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
+  if (c_hi <= c_lo) return ICIKT_OK;
+  const size_t bytes = sizeof(double) * (size_t)p->n * (size_t)(c_hi - c_lo);
+  if (ld == p->n && bytes >= (8u << 20) && !std::getenv("ICIKT_NO_STAGED_UPLOAD") && !host_is_pinned(data + (size_t)c_lo * ld))
+    return staged_copy_in(p, p->d_data_own + (size_t)c_lo * p->n, data + (size_t)c_lo * ld, bytes, stream);
+  CK(cudaMemcpy2DAsync(p->d_data_own + (size_t)c_lo * p->n, sizeof(double) * p->n, data + (size_t)c_lo * ld,
+                       sizeof(double) * ld, sizeof(double) * p->n, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice, stream));
+  return ICIKT_OK;
+}
+
 int upload_columns(icikt_plan* p, const double* data, int64_t ld, int64_t c_lo, int64_t c_hi) {
   CK(cudaSetDevice(p->device));
-  if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
   CK(cudaEventRecord(p->ev[0], p->stream));
-  if (c_hi > c_lo) {
-    const size_t bytes = sizeof(double) * (size_t)p->n * (size_t)(c_hi - c_lo);
-    if (ld == p->n && bytes >= (8u << 20) && !std::getenv("ICIKT_NO_STAGED_UPLOAD") && !host_is_pinned(data + (size_t)c_lo * ld)) {
-      const int rc = staged_copy_in(p, p->d_data_own + (size_t)c_lo * p->n, data + (size_t)c_lo * ld, bytes);
-      if (rc != ICIKT_OK) return rc;
-    } else {
-      CK(cudaMemcpy2DAsync(p->d_data_own + (size_t)c_lo * p->n, sizeof(double) * p->n, data + (size_t)c_lo * ld,
-                           sizeof(double) * ld, sizeof(double) * p->n, (size_t)(c_hi - c_lo), cudaMemcpyHostToDevice,
-                           p->stream));
-    }
-  }
+  const int rc = copy_columns_in(p, data, ld, c_lo, c_hi, p->stream);
+  if (rc != ICIKT_OK) return rc;
   CK(cudaEventRecord(p->ev[1], p->stream));
   p->d_data = p->d_data_own;
   p->ld = p->n;
   p->columns_done = false;
   p->pairs_done = false;
+  p->staged_run = false;
   return ICIKT_OK;
 }
 
@@ -423,8 +549,9 @@ int64_t icikt_max_n(void) { return tiled_max_n(); }
 
 const char* icikt_last_error(void) { return g_err.c_str(); }
 
-int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi, const int32_t* pj,
-                      int64_t P, const icikt_opts* opts_in) {
+// `staged`: the unit table of the pipelined one-shot call (all pairs only), see build_stage_table
+static int plan_create_impl(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi, const int32_t* pj,
+                            int64_t P, const icikt_opts* opts_in, bool staged) {
   if (!out) return fail(ICIKT_ERR_BAD_ARG, "plan pointer is NULL");
   *out = nullptr;
   if (n < 1 || C < 1) return fail(ICIKT_ERR_BAD_ARG, "n and C must be >= 1");
@@ -451,8 +578,18 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
     free_plan(p);
     return fail(ICIKT_ERR_NO_DEVICE, "device is not sm_100-class; this library is built for sm_100a only");
   }
-  rc = build_units(p, pi, pj, P);
-  if (rc != ICIKT_OK) { free_plan(p); return rc; }
+  if (staged) {
+    if (pi || o.pair_lo != 0 || o.pair_hi != 0) { free_plan(p); return fail(ICIKT_ERR_BAD_ARG, "staged plans cover all pairs"); }
+    p->staged = true;
+    p->P = tri_pairs(C) + (o.include_diag ? C : 0);
+    // row blocks of the last chunk: the copy-out of the final block is all that stays exposed
+    int blocks = (size_t)p->P * (4 * sizeof(double) + sizeof(int32_t)) > stage_all() ? 16 : 8;
+    if (const char* e = std::getenv("ICIKT_PIPELINE_BLOCKS")) blocks = std::max(1, std::min(64, std::atoi(e)));
+    build_stage_table(C, o.include_diag != 0, (int64_t)p->n_sm * 2, blocks, p->units, p->stages);
+  } else {
+    rc = build_units(p, pi, pj, P);
+    if (rc != ICIKT_OK) { free_plan(p); return rc; }
+  }
   for (const PairUnit& u : p->units) p->max_unit_pairs = std::max(p->max_unit_pairs, (int)u.count);
 
 #define PCK(call)                                                \
@@ -468,6 +605,13 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
 
   PCK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   for (auto& e : p->ev) PCK(cudaEventCreate(&e));
+  if (staged) {
+    PCK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    p->sync_ev.assign(2 * p->stages.size(), nullptr);
+    p->time_ev.assign(5 * p->stages.size(), nullptr);
+    for (auto& e : p->sync_ev) PCK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : p->time_ev) PCK(cudaEventCreate(&e));
+  }
   ColumnTables& t = p->tab;
   t.n = n;
   t.C = C;
@@ -541,6 +685,11 @@ int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi,
   return ICIKT_OK;
 }
 
+int icikt_plan_create(icikt_plan** out, int64_t n, int64_t C, const int32_t* pi, const int32_t* pj,
+                      int64_t P, const icikt_opts* opts_in) {
+  return plan_create_impl(out, n, C, pi, pj, P, opts_in, false);
+}
+
 int64_t icikt_plan_num_pairs(const icikt_plan* p) { return p ? p->P : 0; }
 
 int icikt_plan_upload(icikt_plan* p, const double* data, int64_t ld) {
@@ -562,8 +711,11 @@ int icikt_plan_set_device_matrix(icikt_plan* p, const double* d_data, int64_t ld
 
 // K1 over columns [col_lo, col_hi); `finish`: the statistics of every column are in place afterwards
 // (a full run), so the pair kernel may be launched
+// `reset`: a partial run that starts a sequence of partial runs over all columns on this device (the
+// column kernels then raise the tier maxima themselves); e0/e1: timing events (default ev[2], ev[3])
 static int plan_columns_impl(icikt_plan* p, const double* global_na, int32_t n_global_na, int64_t col_lo,
-                             int64_t col_hi, bool finish) {
+                             int64_t col_hi, bool finish, bool reset = false, cudaEvent_t e0 = nullptr,
+                             cudaEvent_t e1 = nullptr) {
   if (!p || !p->d_data) return fail(ICIKT_ERR_BAD_ARG, "no matrix set on the plan");
   if (n_global_na < 0 || (n_global_na > 0 && !global_na)) return fail(ICIKT_ERR_BAD_ARG, "bad global_na");
   if (col_lo < 0 || col_hi > p->C || col_lo > col_hi) return fail(ICIKT_ERR_BAD_ARG, "column range out of bounds");
@@ -579,7 +731,8 @@ static int plan_columns_impl(icikt_plan* p, const double* global_na, int32_t n_g
     lit[nlit++] = v;
   }
   if (nlit) CK(cudaMemcpyAsync(p->d_global_na, lit, sizeof(double) * nlit, cudaMemcpyHostToDevice, p->stream));
-  CK(cudaEventRecord(p->ev[2], p->stream));
+  if (reset) CK(cudaMemsetAsync(p->tab.max_tied, 0, 4 * sizeof(int32_t), p->stream));
+  CK(cudaEventRecord(e0 ? e0 : p->ev[2], p->stream));
   // the largest tier decides whether the global scratch may be needed at all
   const int64_t n_units = (int64_t)p->units.size();
   const bool inplace_ok = p->opts.perspective != ICIKT_PERSPECTIVE_COMPLETE;  // that mode has no in-place kernel
@@ -609,10 +762,10 @@ static int plan_columns_impl(icikt_plan* p, const double* global_na, int32_t n_g
   const int l = launch_columns(p->d_data, p->ld, p->d_global_na, nlit, na_inf, p->tab, p->wk, p->shape,
                                p->d_scratch, p->stream, col_lo, col_hi);
   if (l < 0) return launch_fail("column kernels");
-  CK(cudaEventRecord(p->ev[3], p->stream));
+  CK(cudaEventRecord(e1 ? e1 : p->ev[3], p->stream));
   // no synchronisation: `lit` is pageable host memory, so the copy above was staged before
   // cudaMemcpyAsync returned
-  p->tm.n_launches = l;
+  p->tm.n_launches = reset || !e0 ? l : p->tm.n_launches + l;
   p->columns_done = finish;
   p->pairs_done = false;
   return ICIKT_OK;
@@ -662,24 +815,25 @@ int icikt_plan_tables(icikt_plan* p, icikt_table* out, int32_t cap) {
   return n_all;
 }
 
-int icikt_plan_pairs(icikt_plan* p) {
-  if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
-  CK(cudaSetDevice(p->device));
+// K2 (every tier's shape; the device-side maxima pick the one that runs) + K3 over units [unit_lo, unit_hi);
+// e_start / e_mid / e_end bracket K2 and K3 on the plan's stream
+static int launch_pair_group(icikt_plan* p, int64_t unit_lo, int64_t unit_hi, int max_unit_pairs, cudaEvent_t e_start,
+                             cudaEvent_t e_mid, cudaEvent_t e_end, int* launches_out) {
   CK(cudaMemsetAsync(p->d_scalars, 0, 2 * sizeof(unsigned long long), p->stream));
-  CK(cudaMemsetAsync(p->d_maxbits, 0, sizeof(unsigned long long), p->stream));
-  CK(cudaEventRecord(p->ev[4], p->stream));
-  if (p->P <= 0) CK(cudaEventRecord(p->ev[8], p->stream));
+  CK(cudaEventRecord(e_start, p->stream));
   PairLaunch pl;
   pl.tab = &p->tab;
-  pl.units = p->d_units;
-  pl.n_units = (int64_t)p->units.size();
+  pl.units = p->d_units + unit_lo;
+  pl.n_units = unit_hi - unit_lo;
   pl.pj_list = p->d_pj;
   pl.raw = p->d_raw;
   pl.pw = (p->opts.perspective == ICIKT_PERSPECTIVE_COMPLETE) ? p->d_pw : nullptr;
   pl.unit_counter = p->d_scalars;
   pl.scratch = p->d_scratch;
   int launches = 0;
-  if (p->P > 0) {
+  if (pl.n_units <= 0) {
+    CK(cudaEventRecord(e_mid, p->stream));
+  } else {
     int l;
     if (pl.pw && p->opts.kernel == ICIKT_KERNEL_NAIVE)
       return fail(ICIKT_ERR_BAD_ARG, "the complete-observations mode needs the tiled kernel");
@@ -701,12 +855,12 @@ int icikt_plan_pairs(icikt_plan* p) {
                                       "shared memory (long vectors with heavy ties)");
     if (l < 0) return launch_fail("pair kernel");
     launches += l;
-    CK(cudaEventRecord(p->ev[8], p->stream));
+    CK(cudaEventRecord(e_mid, p->stream));
     EpilogueLaunch el;
     el.tab = &p->tab;
-    el.units = p->d_units;
+    el.units = pl.units;
     el.n_units = pl.n_units;
-    el.max_unit_pairs = p->max_unit_pairs;
+    el.max_unit_pairs = max_unit_pairs;
     el.pj_list = p->d_pj;
     el.raw = p->d_raw;
     el.pw = pl.pw;
@@ -724,9 +878,21 @@ int icikt_plan_pairs(icikt_plan* p) {
     if (l < 0) return launch_fail("epilogue kernel");
     launches += l;
   }
-  CK(cudaEventRecord(p->ev[5], p->stream));
+  CK(cudaEventRecord(e_end, p->stream));
+  *launches_out += launches;
+  return ICIKT_OK;
+}
+
+int icikt_plan_pairs(icikt_plan* p) {
+  if (!p || !p->columns_done) return fail(ICIKT_ERR_BAD_ARG, "icikt_plan_columns has not run");
+  CK(cudaSetDevice(p->device));
+  CK(cudaMemsetAsync(p->d_maxbits, 0, sizeof(unsigned long long), p->stream));
+  int launches = 0;
+  const int rc = launch_pair_group(p, 0, (int64_t)p->units.size(), p->max_unit_pairs, p->ev[4], p->ev[8], p->ev[5], &launches);
+  if (rc != ICIKT_OK) return rc;
   p->tm.n_launches = (p->tm.n_launches & 0xffff) | (launches << 16);
   p->pairs_done = true;
+  p->staged_run = false;
   return ICIKT_OK;
 }
 
@@ -764,12 +930,12 @@ int icikt_plan_download(icikt_plan* p, double* raw, double* pvalue, double* taum
   } else {
     if (np) {
       int rc = ICIKT_OK;
-      if (raw) rc = staged_copy_out(p, raw, p->d_tau, sizeof(double) * np);
-      if (rc == ICIKT_OK && pvalue) rc = staged_copy_out(p, pvalue, p->d_p, sizeof(double) * np);
-      if (rc == ICIKT_OK && taumax) rc = staged_copy_out(p, taumax, p->d_tm, sizeof(double) * np);
-      if (rc == ICIKT_OK && completeness) rc = staged_copy_out(p, completeness, p->d_comp, sizeof(double) * np);
-      if (rc == ICIKT_OK && status) rc = staged_copy_out(p, status, p->d_status, sizeof(int32_t) * np);
-      if (rc == ICIKT_OK && counts) rc = staged_copy_out(p, counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS);
+      if (raw) rc = staged_copy_out(p, raw, p->d_tau, sizeof(double) * np, p->stream);
+      if (rc == ICIKT_OK && pvalue) rc = staged_copy_out(p, pvalue, p->d_p, sizeof(double) * np, p->stream);
+      if (rc == ICIKT_OK && taumax) rc = staged_copy_out(p, taumax, p->d_tm, sizeof(double) * np, p->stream);
+      if (rc == ICIKT_OK && completeness) rc = staged_copy_out(p, completeness, p->d_comp, sizeof(double) * np, p->stream);
+      if (rc == ICIKT_OK && status) rc = staged_copy_out(p, status, p->d_status, sizeof(int32_t) * np, p->stream);
+      if (rc == ICIKT_OK && counts) rc = staged_copy_out(p, counts, p->d_counts, sizeof(int64_t) * np * ICIKT_NCOUNTS, p->stream);
       if (rc != ICIKT_OK) return rc;
     }
     CK(cudaMemcpyAsync(&bits, p->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, p->stream));
@@ -851,7 +1017,7 @@ int icikt_plan_download_matrices(icikt_plan* p, int32_t scale_max, int32_t diag_
     }
     for (int k = 0; k < 5; ++k)
       if (outs[k]) {
-        const int rc = staged_copy_out(p, outs[k], mf.m[k], sizeof(double) * cc);
+        const int rc = staged_copy_out(p, outs[k], mf.m[k], sizeof(double) * cc, p->stream);
         if (rc != ICIKT_OK) return rc;
       }
   }
@@ -893,11 +1059,23 @@ int icikt_plan_timings(icikt_plan* p, icikt_timings* t) {
   const int launches = (p->tm.n_launches & 0xffff) + (p->tm.n_launches >> 16);
   std::memset(t, 0, sizeof(*t));
   t->n_launches = launches;
-  // the stream is idle, so every recorded event has completed
+  if (p->copy_stream) CK(cudaStreamSynchronize(p->copy_stream));
+  // the streams are idle, so every recorded event has completed
   t->h2d_ms = ev_ms(p->ev[0], p->ev[1]);
-  t->columns_ms = ev_ms(p->ev[2], p->ev[3]);
-  t->pairs_ms = ev_ms(p->ev[4], p->ev[8]);
-  t->epilogue_ms = ev_ms(p->ev[8], p->ev[5]);
+  if (p->staged_run) {
+    // pipelined call: kernel times are sums over the launches; h2d = start until the last column has landed,
+    // d2h = first result copy until the last one (both overlap the kernels, so the parts exceed total_ms)
+    for (size_t l = 0; l < p->stages.size(); ++l) {
+      const cudaEvent_t* e = &p->time_ev[5 * l];
+      if (p->stages[l].col_hi > p->stages[l].col_lo) t->columns_ms += ev_ms(e[0], e[1]);
+      t->pairs_ms += ev_ms(e[2], e[3]);
+      t->epilogue_ms += ev_ms(e[3], e[4]);
+    }
+  } else {
+    t->columns_ms = ev_ms(p->ev[2], p->ev[3]);
+    t->pairs_ms = ev_ms(p->ev[4], p->ev[8]);
+    t->epilogue_ms = ev_ms(p->ev[8], p->ev[5]);
+  }
   t->d2h_ms = ev_ms(p->ev[6], p->ev[7]);
   t->total_ms = ev_ms(p->ev[0], p->ev[7]);
   cudaGetLastError();
@@ -906,13 +1084,135 @@ int icikt_plan_timings(icikt_plan* p, icikt_timings* t) {
 
 void icikt_plan_destroy(icikt_plan* p) { free_plan(p); }
 
+// The pipelined one-shot call on a staged plan (build_stage_table): uploads on the copy stream chunk by chunk,
+// K1 of a chunk and the pair launches that need nothing beyond it on the compute stream, the results of
+// a finished row block back on the copy stream while the next block runs.  `download` false: the results
+// stay on the device (matrix output follows).  Same results as upload + columns + pairs + download: only
+// the order in which the pairs are computed differs.
+static int run_staged(icikt_plan* p, const double* data, int64_t ld, const double* global_na, int32_t n_global_na,
+                      bool download, double* raw, double* pvalue, double* taumax, double* completeness,
+                      int32_t* status, int64_t* counts, double* max_taumax) {
+  if (!p || !p->staged) return fail(ICIKT_ERR_BAD_ARG, "not a staged plan");
+  if (!data || ld < p->n) return fail(ICIKT_ERR_BAD_ARG, "bad upload arguments");
+  if (counts && !p->d_counts) return fail(ICIKT_ERR_BAD_ARG, "plan was created without want_counts");
+  CK(cudaSetDevice(p->device));
+  if (!p->d_data_own) CK(dmalloc(&p->d_data_own, (size_t)p->n * p->C));
+  p->d_data = p->d_data_own;
+  p->ld = p->n;
+  p->columns_done = false;
+  p->pairs_done = false;
+  p->staged_run = true;
+  CK(cudaEventRecord(p->ev[0], p->stream));
+  CK(cudaStreamWaitEvent(p->copy_stream, p->ev[0], 0));
+  CK(cudaMemsetAsync(p->d_maxbits, 0, sizeof(unsigned long long), p->stream));
+  int pair_launches = 0;
+  const size_t L = p->stages.size();
+  for (size_t l = 0; l < L; ++l) {
+    const StageLaunch& st = p->stages[l];
+    cudaEvent_t* te = &p->time_ev[5 * l];
+    if (st.col_hi > st.col_lo) {
+      int rc = copy_columns_in(p, data, ld, st.col_lo, st.col_hi, p->copy_stream);
+      if (rc != ICIKT_OK) return rc;
+      CK(cudaEventRecord(p->sync_ev[2 * l], p->copy_stream));
+      if (st.col_hi == p->C) CK(cudaEventRecord(p->ev[1], p->copy_stream));
+      CK(cudaStreamWaitEvent(p->stream, p->sync_ev[2 * l], 0));
+      rc = plan_columns_impl(p, global_na, n_global_na, st.col_lo, st.col_hi, st.col_hi == p->C, st.col_lo == 0, te[0], te[1]);
+      if (rc != ICIKT_OK) return rc;
+    }
+    const int rc = launch_pair_group(p, st.unit_lo, st.unit_hi, st.max_unit_pairs, te[2], te[3], te[4], &pair_launches);
+    if (rc != ICIKT_OK) return rc;
+    CK(cudaEventRecord(p->sync_ev[2 * l + 1], p->stream));
+  }
+  p->tm.n_launches = (p->tm.n_launches & 0xffff) | (pair_launches << 16);
+  p->pairs_done = true;
+  bool d2h_started = false;  // ev[6]: the first result copy may start
+  unsigned long long bits = 0;
+  if (download) {
+    const size_t np = (size_t)p->P, npad = std::max<size_t>(np, 1);
+    struct Out { void* host; const unsigned char* dev; size_t elem; size_t res_off; };
+    const Out outs[6] = {
+        {raw, reinterpret_cast<const unsigned char*>(p->d_tau), sizeof(double), 0},
+        {pvalue, reinterpret_cast<const unsigned char*>(p->d_p), sizeof(double), npad * sizeof(double)},
+        {taumax, reinterpret_cast<const unsigned char*>(p->d_tm), sizeof(double), 2 * npad * sizeof(double)},
+        {completeness, reinterpret_cast<const unsigned char*>(p->d_comp), sizeof(double), 3 * npad * sizeof(double)},
+        {status, reinterpret_cast<const unsigned char*>(p->d_status), sizeof(int32_t),
+         4 * npad * sizeof(double) + sizeof(unsigned long long)},
+        {counts, reinterpret_cast<const unsigned char*>(p->d_counts), sizeof(int64_t) * ICIKT_NCOUNTS, 0},
+    };
+    if (p->h_res) {
+      // every block's copies into the pinned mirror are enqueued at once (each waits for its block), the
+      // host then follows block by block and moves the ranges into the caller's arrays
+      for (size_t l = 0; l < L; ++l) {
+        const StageLaunch& st = p->stages[l];
+        if (st.slot_hi <= st.slot_lo) continue;
+        CK(cudaStreamWaitEvent(p->copy_stream, p->sync_ev[2 * l + 1], 0));
+        if (!d2h_started) CK(cudaEventRecord(p->ev[6], p->copy_stream));
+        d2h_started = true;
+        for (int k = 0; k < 6; ++k) {
+          if (!outs[k].host) continue;
+          const size_t o = (size_t)st.slot_lo * outs[k].elem, b = (size_t)(st.slot_hi - st.slot_lo) * outs[k].elem;
+          void* dst = (k == 5) ? static_cast<void*>(static_cast<unsigned char*>(outs[k].host) + o)
+                               : static_cast<void*>(p->h_res + outs[k].res_off + o);
+          CK(cudaMemcpyAsync(dst, outs[k].dev + o, b, cudaMemcpyDeviceToHost, p->copy_stream));
+        }
+        CK(cudaEventRecord(p->sync_ev[2 * l], p->copy_stream));  // free since the block's columns were waited for
+      }
+      for (size_t l = 0; l < L; ++l) {
+        const StageLaunch& st = p->stages[l];
+        if (st.slot_hi <= st.slot_lo) continue;
+        CK(cudaEventSynchronize(p->sync_ev[2 * l]));
+        for (int k = 0; k < 5; ++k) {
+          if (!outs[k].host) continue;
+          const size_t o = (size_t)st.slot_lo * outs[k].elem, b = (size_t)(st.slot_hi - st.slot_lo) * outs[k].elem;
+          host_copy(static_cast<unsigned char*>(outs[k].host) + o, p->h_res + outs[k].res_off + o, b);
+        }
+      }
+    } else {
+      for (size_t l = 0; l < L; ++l) {
+        const StageLaunch& st = p->stages[l];
+        if (st.slot_hi <= st.slot_lo) continue;
+        CK(cudaStreamWaitEvent(p->copy_stream, p->sync_ev[2 * l + 1], 0));
+        if (!d2h_started) CK(cudaEventRecord(p->ev[6], p->copy_stream));
+        d2h_started = true;
+        for (int k = 0; k < 6; ++k) {
+          if (!outs[k].host) continue;
+          const size_t o = (size_t)st.slot_lo * outs[k].elem, b = (size_t)(st.slot_hi - st.slot_lo) * outs[k].elem;
+          const int rc = staged_copy_out(p, static_cast<unsigned char*>(outs[k].host) + o, outs[k].dev + o, b, p->copy_stream);
+          if (rc != ICIKT_OK) return rc;
+        }
+      }
+    }
+  }
+  CK(cudaStreamWaitEvent(p->copy_stream, p->sync_ev[2 * L - 1], 0));
+  if (!d2h_started) CK(cudaEventRecord(p->ev[6], p->copy_stream));
+  CK(cudaMemcpyAsync(&bits, p->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, p->copy_stream));
+  CK(cudaEventRecord(p->ev[7], p->copy_stream));
+  CK(cudaStreamSynchronize(p->copy_stream));
+  CK(cudaStreamSynchronize(p->stream));
+  if (max_taumax) {
+    double v;
+    std::memcpy(&v, &bits, sizeof(v));
+    *max_taumax = bits ? v : std::nan("");
+  }
+  return ICIKT_OK;
+}
+
+// all pairs of a matrix this large go through the pipelined call (ICIKT_PIPELINE_MIN_BYTES, default 32 MB of
+// input; ICIKT_NO_PIPELINE=1 switches it off)
+static bool want_staged(int64_t n, int64_t C, const icikt_opts& o, bool all_pairs) {
+  if (!all_pairs || o.pair_lo != 0 || o.pair_hi != 0 || o.kernel != ICIKT_KERNEL_TILED) return false;
+  if (std::getenv("ICIKT_NO_PIPELINE")) return false;
+  const size_t min_bytes = env_bytes("ICIKT_PIPELINE_MIN_BYTES", 32u << 20);
+  return C >= 128 && sizeof(double) * (size_t)n * (size_t)C >= min_bytes;
+}
+
 // One cached plan for the one-shot entry points (all-pairs shape only).
 static icikt_plan* g_cached = nullptr;
 static icikt_plan* g_cached_multi[64] = {};  // one slot per worker of icikt_all_pairs_multi
 static std::mutex g_cache_mu;
 
-static bool cache_matches(const icikt_plan* p, int64_t n, int64_t C, const icikt_opts& o) {
-  return p && p->n == n && p->C == C && p->opts.device == o.device && p->opts.kernel == o.kernel &&
+static bool cache_matches(const icikt_plan* p, int64_t n, int64_t C, const icikt_opts& o, bool staged) {
+  return p && p->staged == staged && p->n == n && p->C == C && p->opts.device == o.device && p->opts.kernel == o.kernel &&
          p->opts.include_diag == o.include_diag && p->opts.pair_lo == o.pair_lo &&
          p->opts.pair_hi == o.pair_hi && p->want_counts == (o.want_counts != 0);
 }
@@ -933,11 +1233,13 @@ static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const 
   icikt_opts o;
   if (opts) o = *opts; else icikt_default_opts(&o);
   o.want_counts = counts ? 1 : 0;
+  if (!pi && o.pair_lo == 0 && o.pair_hi == tri_pairs(C) + (o.include_diag ? C : 0)) o.pair_hi = 0;  // the whole order
   std::lock_guard<std::mutex> lock(g_cache_mu);
   icikt_plan* p = nullptr;
   const bool cacheable = (pi == nullptr);
+  const bool staged = want_staged(n, C, o, pi == nullptr);
   int rc = ICIKT_OK;
-  if (cacheable && cache_matches(g_cached, n, C, o) &&
+  if (cacheable && cache_matches(g_cached, n, C, o, staged) &&
       (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || g_cached->d_pw)) {
     p = g_cached;
     p->opts.perspective = o.perspective;
@@ -946,17 +1248,22 @@ static int one_shot(const double* data, int64_t n, int64_t C, int64_t ld, const 
     p->opts.na_inf = o.na_inf;
   } else {
     if (cacheable && g_cached) { icikt_plan_destroy(g_cached); g_cached = nullptr; }
-    rc = icikt_plan_create(&p, n, C, pi, pj, P, &o);
+    rc = plan_create_impl(&p, n, C, pi, pj, P, &o, staged);
     if (rc != ICIKT_OK) return rc;
     if (cacheable) g_cached = p;
   }
-  rc = icikt_plan_upload(p, data, ld);
-  if (rc == ICIKT_OK) rc = icikt_plan_columns(p, global_na, n_global_na);
-  if (rc == ICIKT_OK) rc = icikt_plan_pairs(p);
+  if (staged) {
+    rc = run_staged(p, data, ld, global_na, n_global_na, mat == nullptr, raw, pvalue, taumax, completeness, status,
+                    counts, max_taumax);
+  } else {
+    rc = icikt_plan_upload(p, data, ld);
+    if (rc == ICIKT_OK) rc = icikt_plan_columns(p, global_na, n_global_na);
+    if (rc == ICIKT_OK) rc = icikt_plan_pairs(p);
+  }
   if (rc == ICIKT_OK && mat)
     rc = icikt_plan_download_matrices(p, mat->scale_max, mat->diag_good, mat->n_good, mat->cor, raw, pvalue, taumax,
                                       completeness, mat->status_counts, max_taumax);
-  else if (rc == ICIKT_OK)
+  else if (rc == ICIKT_OK && !staged)
     rc = icikt_plan_download(p, raw, pvalue, taumax, completeness, status, counts, max_taumax);
   if (rc == ICIKT_OK && timings) rc = icikt_plan_timings(p, timings);
   const std::string keep = g_err;
@@ -994,6 +1301,26 @@ void icikt_release_workspace(void) {
   if (g_cached) { icikt_plan_destroy(g_cached); g_cached = nullptr; }
   for (icikt_plan*& s : g_cached_multi)
     if (s) { icikt_plan_destroy(s); s = nullptr; }
+}
+
+int64_t icikt_stage_table(int64_t C, int32_t include_diag, int32_t cta_slots, int32_t n_blocks, int64_t cap_units,
+                          int64_t* units, int64_t cap_launches, int64_t* launches, int64_t* n_launches) {
+  if (C < 1 || cta_slots < 1 || n_blocks < 1) return fail(ICIKT_ERR_BAD_ARG, "bad stage table arguments");
+  std::vector<PairUnit> U;
+  std::vector<StageLaunch> S;
+  build_stage_table(C, include_diag != 0, cta_slots, n_blocks, U, S);
+  for (size_t k = 0; units && k < U.size() && (int64_t)k < cap_units; ++k) {
+    units[4 * k + 0] = U[k].slot0;
+    units[4 * k + 1] = U[k].col;
+    units[4 * k + 2] = U[k].j0;
+    units[4 * k + 3] = U[k].count;
+  }
+  for (size_t l = 0; launches && l < S.size() && (int64_t)l < cap_launches; ++l) {
+    const int64_t row[6] = {S[l].col_lo, S[l].col_hi, S[l].unit_lo, S[l].unit_hi, S[l].slot_lo, S[l].slot_hi};
+    std::memcpy(launches + 6 * l, row, sizeof(row));
+  }
+  if (n_launches) *n_launches = (int64_t)S.size();
+  return (int64_t)U.size();
 }
 
 int icikt_measure_smem_bandwidth(int32_t device, double* g32, double* g128) {
@@ -1178,7 +1505,7 @@ int multi_worker_pairs(MultiJob& J, int k, icikt_plan** out) {
   // pay the device allocations again
   icikt_plan*& slot = g_cached_multi[k];
   icikt_plan* p = nullptr;
-  if (cache_matches(slot, J.n, J.C, o) && (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || slot->d_pw)) {
+  if (cache_matches(slot, J.n, J.C, o, false) && (o.perspective != ICIKT_PERSPECTIVE_COMPLETE || slot->d_pw)) {
     p = slot;
     p->opts.perspective = o.perspective;
     p->opts.alternative = o.alternative;
@@ -1405,7 +1732,7 @@ int icikt_matrices_multi(const double* data, int64_t n, int64_t C, int64_t ld, c
         if (launch_matrix_block_fill(f, p->stream) < 0) return launch_fail("matrix block fill kernel");
         for (int q = 0; q < 5; ++q)
           if (outs[q] && blk) {
-            const int r2 = staged_copy_out(p, outs[q] + (size_t)c_lo * (size_t)C, f.m[q], sizeof(double) * blk);
+            const int r2 = staged_copy_out(p, outs[q] + (size_t)c_lo * (size_t)C, f.m[q], sizeof(double) * blk, p->stream);
             if (r2 != ICIKT_OK) return r2;
           }
         CK(cudaMemcpyAsync(w.hist, p->d_hist, sizeof(w.hist), cudaMemcpyDeviceToHost, p->stream));

@@ -260,6 +260,21 @@ int icikt_pair_from_index(int64_t C, int32_t include_diag, int64_t index, int32_
  * frees it (the R shim calls it from .onUnload).                                      */
 void icikt_release_workspace(void);
 
+/* How the one-shot calls (icikt_all_pairs, icikt_matrices) pipeline a large all-pairs job (input of
+ * ICIKT_PIPELINE_MIN_BYTES = 32 MB or more, 128 columns or more; ICIKT_NO_PIPELINE=1 switches it off).
+ * The reference hands each furrr worker the whole matrix and a slice of the pair list (R/kendalltau.R:
+ * 236-253); here the columns are uploaded in chunks [0,f), [f,2f), [2f,4f) ... and the launch that follows a
+ * chunk computes every pair whose later column lies in it, so the upload of the next chunk hides behind
+ * it; the last chunk is cut into n_blocks row blocks whose results are contiguous in the pair order and
+ * are copied out while the next block runs.  This host-only function reports that table for C columns:
+ * units[4k..] = (slot, first column, other column of its first pair, pairs), launches[6l..] = (col_lo,
+ * col_hi, unit_lo, unit_hi, slot_lo, slot_hi); cta_slots = resident CTAs of the pair kernel (2 x SMs).
+ * Returns the number of units (or a negative error); at most cap_units / cap_launches entries are
+ * written (either array may be NULL).  Needs no device.                                         */
+int64_t icikt_stage_table(int64_t C, int32_t include_diag, int32_t cta_slots, int32_t n_blocks,
+                          int64_t cap_units, int64_t* units, int64_t cap_launches, int64_t* launches,
+                          int64_t* n_launches);
+
 /* Measures the shared-memory bandwidth of `device` with a conflict-free read+write sweep
  * (the traffic pattern the roofline model of the pair kernel assumes: one 32-bit load and
  * one 32-bit store per element per level).  Returns GB/s through the pointers (either may

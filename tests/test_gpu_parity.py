@@ -952,3 +952,61 @@ def test_staged_pageable_upload_matches_plain_copy(monkeypatch):
     for k in ("raw", "pvalue", "taumax", "completeness", "status"):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     assert a["max_taumax"] == b["max_taumax"]
+
+
+def _same_pairs(a, b, what):
+    for k in ("raw", "pvalue", "taumax", "completeness", "status", "counts"):
+        if k in a or k in b:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"{what}: {k}")
+    assert a["max_taumax"] == b["max_taumax"] or (np.isnan(a["max_taumax"]) and np.isnan(b["max_taumax"])), what
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("persp,diag,kind", [("global", False, "mixed"), ("local", True, "ties"),
+                                             ("complete", False, "mixed")])
+def test_pipelined_one_shot_matches_plain_call(monkeypatch, persp, diag, kind):
+    """Large all-pairs jobs go through the pipelined call (column chunks uploaded while earlier chunks are
+    computed, row blocks copied out while later ones run; icikt_stage_table).  Forced on for a small matrix it
+    must return the bytes of the plain upload -> columns -> pairs -> download sequence, through both result
+    paths (one pinned mirror / two pinned chunks) and for pageable and pinned input."""
+    import torch
+    x = gen(900, 300, kind, 0.2, seed=4242)
+    kw = dict(perspective=persp, include_diag=diag, want_counts=True)
+    monkeypatch.setenv("ICIKT_NO_PIPELINE", "1")
+    _lib.release_workspace()
+    plain = ik.run_pairs(x, (), **kw)
+    if persp != "complete":  # (the complete-observations mode is checked against kt_fast's own tests)
+        assert_parity(plain, oracle_pairs(x, perspective=persp, include_diag=diag), f"plain {persp}")
+    monkeypatch.delenv("ICIKT_NO_PIPELINE")
+    monkeypatch.setenv("ICIKT_PIPELINE_MIN_BYTES", "1")
+    _lib.release_workspace()
+    piped = ik.run_pairs(x, (), **kw)
+    _same_pairs(piped, plain, f"pipelined {persp}")
+    assert piped["timings"]["n_launches"] > plain["timings"]["n_launches"], "the pipelined path did not run"
+    again = ik.run_pairs(x, (), **kw)  # the cached staged plan, second use
+    _same_pairs(again, plain, f"pipelined, cached plan {persp}")
+    xp = torch.from_numpy(np.asfortranarray(x).T.copy()).pin_memory().numpy().T  # pinned, column-major
+    _same_pairs(ik.run_pairs(xp, (), **kw), plain, f"pipelined, pinned input {persp}")
+    monkeypatch.setenv("ICIKT_STAGE_ALL", "1000")       # results through the two pinned chunks ...
+    monkeypatch.setenv("ICIKT_STAGE_CHUNK", str(40000))  # ... several chunks per block and array
+    monkeypatch.setenv("ICIKT_PIPELINE_BLOCKS", "3")
+    _lib.release_workspace()
+    _same_pairs(ik.run_pairs(x, (), **kw), plain, f"pipelined, chunked results {persp}")
+    _lib.release_workspace()
+
+
+@pytest.mark.gpu
+def test_pipelined_matrices_match_plain_call(monkeypatch):
+    x = gen(800, 260, "mixed", 0.25, seed=777)
+    monkeypatch.setenv("ICIKT_NO_PIPELINE", "1")
+    _lib.release_workspace()
+    plain = _lib.run_matrices(x, (), perspective="global", diag_good=False)
+    monkeypatch.delenv("ICIKT_NO_PIPELINE")
+    monkeypatch.setenv("ICIKT_PIPELINE_MIN_BYTES", "1")
+    _lib.release_workspace()
+    piped = _lib.run_matrices(x, (), perspective="global", diag_good=False)
+    _lib.release_workspace()
+    for k in _lib.MATRIX_NAMES:
+        np.testing.assert_array_equal(piped[k], plain[k], err_msg=k)
+    np.testing.assert_array_equal(piped["status_counts"], plain["status_counts"])
+    assert piped["max_taumax"] == plain["max_taumax"]
