@@ -803,16 +803,29 @@ int icikt_plan_tables(icikt_plan* p, icikt_table* out, int32_t cap) {
   if (!p) return fail(ICIKT_ERR_BAD_ARG, "plan is NULL");
   const ColumnTables& t = p->tab;
   const bool complete = p->opts.perspective == ICIKT_PERSPECTIVE_COMPLETE;
+  // the sorted positions of the tied rows are read only by the pair kernel's variants for long vectors
+  // (rank table not staged: in place / global scratch)
+  bool positions = false;
+  for (int tier = 0; tier < 3; ++tier) {
+    const TiledShape sh = tiled_shape(p->n, tier, t.wstride, p->n_sm, 0, !complete);
+    positions = positions || sh.gmem || sh.inplace_kk != 0;
+  }
   const icikt_table all[] = {
       {t.perm, (int64_t)(2 * t.nstride)},       {t.rank, (int64_t)(2 * t.nstride)},
       {t.trow, (int64_t)(2 * t.nstride)},       {t.trun, (int64_t)(2 * t.nstride)},
       {t.tord, (int64_t)(4 * t.nstride)},       {t.nabits, (int64_t)(4 * t.wstride)},
       {t.firstbits, (int64_t)(4 * t.wstride)},  {t.lgrp, (int64_t)(2 * kLargeStride)},
-      {t.stats, (int64_t)sizeof(ColStats)},     {t.gstart, (int64_t)(2 * t.gstride)},
+      {t.stats, (int64_t)sizeof(ColStats)},     {t.tend, (int64_t)(2 * t.nstride)},
+      {t.gstart, (int64_t)(2 * t.gstride)},
   };
-  const int n_all = (int)(sizeof(all) / sizeof(all[0])) - (complete ? 0 : 1);  // gstart: that mode only
-  for (int k = 0; k < n_all && out && k < cap; ++k) out[k] = all[k];
-  return n_all;
+  int n_out = 0;
+  for (const icikt_table& e : all) {
+    if (e.ptr == (void*)t.tend && !positions) continue;
+    if (e.ptr == (void*)t.gstart && !complete) continue;  // that mode only
+    if (out && n_out < cap) out[n_out] = e;
+    ++n_out;
+  }
+  return n_out;
 }
 
 // K2 (every tier's shape; the device-side maxima pick the one that runs) + K3 over units [unit_lo, unit_hi);

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
         const bool large = (lmask >> i) & 1u;
         tr[pos] = vals[i];
         tg[pos] = (uint16_t)((gcount - 1) | (large ? kLargeFlag : 0u));
-        te[pos] = (uint16_t)(large ? pos : pos + after[i]);  // tied rows of a group are consecutive in the list
+        te[pos] = (uint16_t)(base + i);  // its position in sorted order (the pair kernel's in-place comparison)
         ++pos;
       }
     }
@@ -853,6 +853,10 @@ __global__ void __launch_bounds__(RANK_THREADS)
       const int e = te[k];
       const uint32_t walk = e > k ? (uint32_t)(e - k - 1) : 0u;
       to[whist[walk] + wr[k]] = ((uint32_t)k << 16) | walk;
+      // from here on `tend` holds the row's position in sorted order instead (what the pair kernel's in-place
+      // comparison of small groups reads): e - k rows of its group lie at and behind it, the group ends at
+      // gpos[rank + 1]; rows of large groups are never compared, theirs stays unset
+      if (e > k) te[k] = (uint16_t)(gpos[rk[tr[k]] + 1] - (uint32_t)(e - k));
     }
   }
 

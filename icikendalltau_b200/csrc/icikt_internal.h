@@ -36,8 +36,8 @@ struct ColumnTables {
   uint16_t* rank = nullptr;       // [C][nstride] dense rank of every row
   uint16_t* trow = nullptr;       // [C][nstride] rows of tied (non-first-group) elements, sorted order
   uint16_t* trun = nullptr;       // [C][nstride] dense index of their tie group (0..n_tgroups-1), | kLargeFlag
-  uint16_t* tend = nullptr;       // [C][nstride] index in the tied-row list one past the row's group
-                                  //              (= the row's own index for rows of large groups); K1-internal since tord
+  uint16_t* tend = nullptr;       // [C][nstride] position in sorted order of the tied-row list's entries (rows of small
+                                  //              groups; K1 keeps the list index one past the row's group here first)
   uint32_t* tord = nullptr;       // [C][nstride] the tied-row list in walk order: (list index << 16 | rows behind it in its
                                   //              group, 0 for rows of large groups), longest walk first
   uint32_t* nabits = nullptr;     // [C][wstride] bit r: row r missing

@@ -468,6 +468,37 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
   __syncthreads();
 }
 
+// The same comparison where y's rank table is not staged (long vectors): on the gathered sequence itself,
+// after the gather.  The rows of a tie group are consecutive in x order, so the keys of the rows behind a
+// row are the ones behind its position (K1's `tend` table: position in sorted order of every list entry);
+// no second lookup of the ranks through L2, no copy of the keys.  Large groups and the first group occupy
+// other positions, so nothing this routine reads is rewritten before pass A's first barrier.
+template <bool G>
+__device__ __forceinline__ void small_groups_inplace(typename Mem<G>::ptr seq, const int m,
+                                                     const uint32_t* __restrict__ tord,
+                                                     const uint16_t* __restrict__ tpos, uint32_t& inv,
+                                                     uint32_t& ties) {
+  typedef Mem<G> M;
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int i = tid; i < m; i += T) {
+    const uint32_t e = __ldg(tord + i);
+    const int walk = (int)(e & 0xffffu);
+    if (walk == 0) break;  // sorted: nothing but rows without a walk from here on
+    const int k = (int)__ldg(tpos + (e >> 16));
+    const uint32_t mine = M::ld16w(M::add(seq, k << 1));
+    const uint32_t m1 = mine - 1u, nm = ~mine;
+    uint32_t ge = 0, le = 0;
+#pragma unroll 4
+    for (int j = k + 1; j <= k + walk; ++j) {
+      const uint32_t other = M::ld16w(M::add(seq, j << 1));
+      ge += (m1 - other) >> 31;
+      le += (other + nm) >> 31;
+    }
+    inv += (uint32_t)walk - ge;        // other < mine
+    ties += ge + le - (uint32_t)walk;  // other == mine
+  }
+}
+
 // Large tie groups of x (other than the first): their rows' y-ranks, already gathered into the
 // sequence in x order, are rewritten in ascending order group by group, so that the groups
 // contribute no inversions to pass A.  Same histogram technique as group_hist, several groups per
@@ -483,6 +514,22 @@ __device__ __forceinline__ void small_groups_direct(typename Mem<G>::ptr keys, c
 #define ICIKT_MATCH_DEDUP 1
 #endif
 constexpr bool kMatchDedup = ICIKT_MATCH_DEDUP != 0;
+// ICIKT_LG_FROM_SEQ: the histogram of a large group reads the y ranks back from the sequence (shared memory,
+// consecutive) instead of looking them up again through perm_x (0 never, 1 where the rank table is not
+// staged, 2 always).  ICIKT_LG_PLAIN_RG: plain atomics where the rank table is not staged.
+#ifndef ICIKT_LG_FROM_SEQ
+#define ICIKT_LG_FROM_SEQ 1
+#endif
+#ifndef ICIKT_LG_PLAIN_RG
+#define ICIKT_LG_PLAIN_RG 1
+#endif
+constexpr int kFromSeq = ICIKT_LG_FROM_SEQ, kPlainRG = ICIKT_LG_PLAIN_RG;
+// ICIKT_SMALL_INPLACE: where the rank table is not staged, small tie groups are compared on the gathered
+// sequence (small_groups_inplace) instead of on a second copy of the tied rows' keys
+#ifndef ICIKT_SMALL_INPLACE
+#define ICIKT_SMALL_INPLACE 1
+#endif
+constexpr bool kSmallInplace = ICIKT_SMALL_INPLACE != 0;
 template <bool G, bool RG>
 __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                         const int hist_words, const uint16_t* __restrict__ permX,
@@ -521,13 +568,19 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
           uint32_t bin = 0x80000000u | (uint32_t)lane;  // idle lanes: a key of their own
           bool in = false;
           if (q < t) {
-            const uint32_t row = permX[s0 + q];
-            const uint32_t r = (RG ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)))) -
-                               (uint32_t)k0;
+            uint32_t r;
+            if (kFromSeq >= (RG ? 1 : 2) && kw == K) {
+              // the gather has put rank_y[perm_x[s0 + q]] at position s0 + q of the sequence, and with all of
+              // y's ranks in one window nothing of this batch is rewritten before the barrier below
+              r = M::ld16(M::add(buf, (int32_t)((s0 + q) << 1)));
+            } else {
+              const uint32_t row = permX[s0 + q];
+              r = (RG ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)))) - (uint32_t)k0;
+            }
             in = r < (uint32_t)kw;
             if (in) bin = (uint32_t)(j * kw) + r;
           }
-          if (kMatchDedup) {  // rows of one bin met by several lanes are added once
+          if (kMatchDedup && (kPlainRG == 0 || !RG)) {  // rows of one bin met by several lanes are added once
             const uint32_t peers = __match_any_sync(FULL, bin);
             if (in && (peers & ((1u << lane) - 1u)) == 0u)
               M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), (uint32_t)__popc(peers) << ((bin & 1u) * 16u));
@@ -647,6 +700,7 @@ struct TiledParams {
   int tier;
   long long budget;  // large groups x distinct values above which pass B takes the tied rows
   PipeConst pc;
+  const uint16_t* tpos;  // [C][nstride] sorted position of the tied-row list's entries (ColumnTables::tend)
 };
 
 // Shared-memory layout of one CTA (all offsets multiples of 16 bytes)
@@ -836,7 +890,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       const int m = XS.n_tied, nlg = XS.flags >> 8;
       const bool by_pass_b = nlg > 0 && p.tier == 2 && (long long)nlg * YS.n_groups > p.budget;
       uint32_t accB = 0;
-      if (m > 0 && !by_pass_b)  // keys: 2 m <= 2 cap bytes, the still empty sequence buffer
+      if (!(RG && kSmallInplace) && m > 0 && !by_pass_b)  // keys: 2 m <= 2 cap bytes, the still empty sequence buffer
         small_groups_direct<G, RG>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tord + (size_t)xcol * p.nstride,
                                    rank_tbl, rankY_g, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
@@ -888,6 +942,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         }
       }
       __syncthreads();
+      if (RG && kSmallInplace && m > 0 && !by_pass_b)
+        small_groups_inplace<G>(bufA, m, p.tord + (size_t)xcol * p.nstride, p.tpos + (size_t)xcol * p.nstride, accB, ties);
       if (nlg > 0 && !by_pass_b) {
         // large tie groups of x: sorted by y in place (the counters live behind the two pass-A buffers)
         ties += large_groups_sorted<G, RG>(bufA, M::add(bufA, AQ * cap), (p.region_bytes - AQ * cap) >> 2, permX, rank_tbl, rankY_g, YS.n_groups,
@@ -1296,6 +1352,7 @@ TiledParams make_params(const PairLaunch& pl) {
   p.trow = t.trow;
   p.trun = t.trun;
   p.tord = t.tord;
+  p.tpos = t.tend;
   p.nabits = t.nabits;
   p.firstbits = t.firstbits;
   p.stats = t.stats;
@@ -1448,6 +1505,12 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n
       sh.warps = W = w;
       sh.kk = KK;
       sh.region_bytes = region;
+      if (tier == 1 && !getenv("ICIKT_INPLACE_SMALL_HIST")) {
+        // one CTA per SM either way: the rank counters of the large tie groups take all that is left
+        // (more groups per round)
+        const size_t fixed = tiled_smem_bytes(0, (int)wstride, fmask_words(w, KK << 3));
+        sh.region_bytes = (int)((227 * 1024 - fixed) & ~size_t(15));
+      }
     }
   }
   {  // the per-column constant kernel has its own shape: its pass-A buffers must fit a scratch slot too

@@ -16,6 +16,8 @@ rng = np.random.default_rng(seed)
 SIZES = [2, 3, 31, 32, 33, 255, 256, 257, 511, 1000, 1791, 1792, 1793, 2047, 2048, 2049, 4095, 4096, 5000,
          5376, 5377, 8191, 8192, 8193, 10000, 16383, 16384, 20000, 22527, 22528, 22529, 24576, 28672, 32768, 32769, 40000, 50000,
          57344, 64511, 64512, 64513, 65535]
+if os.environ.get("ICIKT_FUZZ_SIZES"):  # e.g. only the lengths of the in-place / global-scratch variants
+    SIZES = [int(v) for v in os.environ["ICIKT_FUZZ_SIZES"].split(",")]
 t0 = time.time()
 cases = 0
 fails = 0
