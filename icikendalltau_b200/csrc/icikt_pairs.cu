@@ -530,6 +530,11 @@ constexpr int kFromSeq = ICIKT_LG_FROM_SEQ, kPlainRG = ICIKT_LG_PLAIN_RG;
 #define ICIKT_SMALL_INPLACE 1
 #endif
 constexpr bool kSmallInplace = ICIKT_SMALL_INPLACE != 0;
+// ICIKT_LG_V2: large_groups_sorted2 instead of large_groups_sorted (0 never, 1 where the rank table is not staged, 2 always)
+#ifndef ICIKT_LG_V2
+#define ICIKT_LG_V2 1
+#endif
+constexpr int kLgV2 = ICIKT_LG_V2;
 template <bool G, bool RG>
 __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                         const int hist_words, const uint16_t* __restrict__ permX,
@@ -659,6 +664,173 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
         for (uint32_t k = tid; k < c; k += T) M::st16(M::add(buf, (int32_t)((off + k) << 1)), r2);
       }
       __syncthreads();
+    }
+  }
+  return ties;
+}
+
+// Second form of large_groups_sorted, used where ICIKT_LG_V2 selects it (long vectors: rank table not
+// staged).  Same rounds and counters; what differs is everything around them:
+//   * the batch's (start, size) pairs are fetched once by nb threads into shared memory and warp 0 turns them
+//     into the output slot of each group's first counter (instead of one thread walking the global table, and
+//     a global load per non-empty counter in the emission);
+//   * groups of up to kWideGroup rows are histogrammed by ONE warp each (28 warps evaluating the loop header
+//     of every small group cost more than the rows themselves), longer ones by the whole CTA;
+//   * runs of kListRun (16) keys and more are parked in the list, longer ones in pieces of kRunPiece, and every
+//     list entry is written by one warp (the CTA-wide loop spent 28 loop headers per entry).
+// `pre` = 256 words of shared memory: [0,128) the packed group table, [128,256) the output slots.
+constexpr int kWideGroup = 512, kListRun = 16, kRunPiece = 512;
+template <bool G, bool RG>
+__device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
+                                                         const int hist_words, const uint16_t* __restrict__ permX,
+                                                         typename Mem<G>::ptr rank_tbl,
+                                                         const uint16_t* __restrict__ rank_g, const int K,
+                                                         const uint16_t* __restrict__ lg, const int nlg,
+                                                         uint32_t* __restrict__ pre, uint32_t* __restrict__ list,
+                                                         const int list_cap, uint32_t* descT, uint32_t* list_n,
+                                                         const int nwarps) {
+  typedef Mem<G> M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  uint32_t* grp = pre;         // start | size << 16 of the batch's groups (the table's own layout)
+  uint32_t* slot0 = pre + 128;  // start - rows of the batch's earlier groups: where the group's first counter writes
+  const uint32_t* lg32 = reinterpret_cast<const uint32_t*>(lg);
+  const int bins_avail = 2 * hist_words;
+  const int gb_max = max(1, min(128, bins_avail / K));  // groups per batch
+  const int Kw = min(K, bins_avail);                    // ranks per window (< K only if gb_max == 1)
+  uint32_t ties = 0;
+  for (int g0 = 0; g0 < nlg; g0 += gb_max) {
+    const int nb = min(gb_max, nlg - g0);
+    uint32_t done = 0;  // rows of the (single) group written by earlier windows
+    for (int k0 = 0; k0 < K; k0 += Kw) {
+      const int kw = min(Kw, K - k0);
+      const int bins = nb * kw, hw = (bins + 1) >> 1, wpt = (hw + T - 1) / T;
+      if (tid < nb) grp[tid] = __ldg(lg32 + g0 + tid);
+      if (tid == 0) *list_n = 0u;
+      for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
+      __syncthreads();
+      if (warp == 0) {  // exclusive prefix of the sizes, four groups per lane
+        uint32_t sz[4], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * lane + i;
+          sz[i] = j < nb ? grp[j] >> 16 : 0u;
+          sum += sz[i];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += t;
+        }
+        uint32_t before = incl - sum;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * lane + i;
+          if (j < nb) slot0[j] = (grp[j] & 0xffffu) - (kw == K ? before : 0u);
+          before += sz[i];
+        }
+      }
+      // 1. histogram
+      auto add_row = [&](const int j, const int s0, const int q) {
+        uint32_t r;
+        if (RG && kw == K) {  // the gather has put rank_y[perm_x[s0 + q]] there, see large_groups_sorted
+          r = M::ld16(M::add(buf, (int32_t)((s0 + q) << 1)));
+        } else {
+          const uint32_t row = permX[s0 + q];
+          r = (RG ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)))) - (uint32_t)k0;
+        }
+        if (r < (uint32_t)kw) {
+          const uint32_t bin = (uint32_t)(j * kw) + r;
+          M::red_add32(M::add(hist, (int32_t)((bin >> 1) << 2)), 1u << ((bin & 1u) * 16u));
+        }
+      };
+      for (int j = 0; j < nb; ++j) {  // long groups: the whole CTA
+        const uint32_t g = grp[j];
+        const int t = (int)(g >> 16);
+        if (t <= kWideGroup) continue;
+        for (int q = tid; q < t; q += T) add_row(j, (int)(g & 0xffffu), q);
+      }
+      for (int j = warp; j < nb; j += nwarps) {  // the others: one warp each
+        const uint32_t g = grp[j];
+        const int t = (int)(g >> 16);
+        if (t > kWideGroup) continue;
+        for (int q = lane; q < t; q += 32) add_row(j, (int)(g & 0xffffu), q);
+      }
+      __syncthreads();
+      // 2. rows per thread range of counters, block scan
+      const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
+      uint32_t mine = 0;
+      for (int w = w0; w < w1; ++w) {
+        const uint32_t c = M::ld32(M::add(hist, w << 2));
+        mine += (c & 0xffffu) + (c >> 16);
+      }
+      uint32_t incl = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) descT[warp] = incl;
+      __syncthreads();
+      const uint32_t v = (lane < nwarps) ? descT[lane] : 0u;
+      const uint32_t total = __reduce_add_sync(FULL, v);
+      uint32_t pos = __reduce_add_sync(FULL, (lane < warp) ? v : 0u) + incl - mine;
+      // 3. write the runs: rank r of group j goes to slot0[j] + (rows of the batch before it)
+      int b = 2 * w0;
+      int j = b / kw, r = b - j * kw;
+      for (int w = w0; w < w1; ++w) {
+        const uint32_t cw = M::ld32(M::add(hist, w << 2));
+        if (cw == 0u) {  // most counters are empty: a group touches at most as many ranks as it has rows
+          b += 2;
+          r += 2;
+          while (r >= kw) {
+            r -= kw;
+            ++j;
+          }
+          continue;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t c = h ? (cw >> 16) : (cw & 0xffffu);
+          if (b < bins && c != 0u) {
+            const uint32_t dst = slot0[j] + done + pos;
+            const uint32_t rank = (uint32_t)(k0 + r);
+            if (c == 1u) {
+              M::st16(M::add(buf, (int32_t)(dst << 1)), rank);
+            } else {
+              ties += (c * (c - 1u)) >> 1;
+              uint32_t left = c, at = dst;
+              if (c >= (uint32_t)kListRun) {  // one list entry per piece, written by a warp each below
+                const uint32_t pieces = (c + kRunPiece - 1) / kRunPiece;
+                const uint32_t first = atomicAdd(list_n, pieces);
+                for (uint32_t i = 0; i < pieces && first + i < (uint32_t)list_cap; ++i) {
+                  const uint32_t len = min(left, (uint32_t)kRunPiece);
+                  list[3 * (first + i) + 0] = rank;
+                  list[3 * (first + i) + 1] = at;
+                  list[3 * (first + i) + 2] = len;
+                  at += len;
+                  left -= len;
+                }
+              }
+              for (uint32_t k = 0; k < left; ++k) M::st16(M::add(buf, (int32_t)((at + k) << 1)), rank);  // short, or list full
+            }
+            pos += c;
+          }
+          ++b;
+          if (++r == kw) {
+            r = 0;
+            ++j;
+          }
+        }
+      }
+      done += total;
+      __syncthreads();
+      const uint32_t nl = min(*list_n, (uint32_t)list_cap);
+      for (uint32_t e = warp; e < nl; e += nwarps) {
+        const uint32_t r2 = list[3 * e], off = list[3 * e + 1], c = list[3 * e + 2];
+        for (uint32_t k = lane; k < c; k += 32) M::st16(M::add(buf, (int32_t)((off + k) << 1)), r2);
+      }
+      __syncthreads();  // list, counters and group table are reused by the next round
     }
   }
   return ties;
@@ -946,6 +1118,12 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         small_groups_inplace<G>(bufA, m, p.tord + (size_t)xcol * p.nstride, p.tpos + (size_t)xcol * p.nstride, accB, ties);
       if (nlg > 0 && !by_pass_b) {
         // large tie groups of x: sorted by y in place (the counters live behind the two pass-A buffers)
+        if (kLgV2 >= (RG ? 1 : 2))
+          ties += large_groups_sorted2<G, RG>(bufA, M::add(bufA, AQ * cap), (p.region_bytes - AQ * cap) >> 2, permX, rank_tbl, rankY_g, YS.n_groups,
+                                              p.lgrp + (size_t)xcol * kLargeStride, nlg,
+                                              reinterpret_cast<uint32_t*>(sm.red), sm.fmask, fmask_words(nwarps, kkc) / 3,
+                                              sm.descT, sm.mini + 16, nwarps);
+        else
         ties += large_groups_sorted<G, RG>(bufA, M::add(bufA, AQ * cap), (p.region_bytes - AQ * cap) >> 2, permX, rank_tbl, rankY_g, YS.n_groups,
                                        p.lgrp + (size_t)xcol * kLargeStride, nlg,
                                        reinterpret_cast<uint32_t*>(sm.red), sm.fmask, fmask_words(nwarps, kkc) / 3,

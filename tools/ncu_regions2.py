@@ -23,9 +23,11 @@ skip = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 rows = rows[starts[skip]:starts[skip + 1]]
 hdr, data = rows[1], [r for r in rows[2:] if len(r) > 10]
 iS, iE = hdr.index('# Samples'), hdr.index('Instructions Executed')
-regions = [('count.cuh step4 (scatter)', 'icikt_count.cuh', 100, 175), ('count.cuh count_pass rest', 'icikt_count.cuh', 176, 400), ('count.cuh accessors', 'icikt_count.cuh', 1, 99),
-           ('group_hist', 'icikt_pairs.cu', 270, 400), ('small_groups', 'icikt_pairs.cu', 401, 460), ('large_groups', 'icikt_pairs.cu', 461, 600),
-           ('kernel body: unit/masks', 'icikt_pairs.cu', 700, 835), ('gather', 'icikt_pairs.cu', 836, 870), ('tail/reduce', 'icikt_pairs.cu', 871, 980)]
+regions = [('count.cuh step4 (scatter)', 'icikt_count.cuh', 130, 235), ('count.cuh count_pass rest', 'icikt_count.cuh', 236, 420), ('count.cuh accessors', 'icikt_count.cuh', 1, 129),
+           ('count_pass_inplace', 'icikt_pairs.cu', 160, 256),
+           ('group_hist', 'icikt_pairs.cu', 257, 418), ('small_groups_direct', 'icikt_pairs.cu', 419, 470), ('small_groups_inplace', 'icikt_pairs.cu', 471, 510),
+           ('large_groups_sorted', 'icikt_pairs.cu', 511, 666),
+           ('kernel body: unit/masks', 'icikt_pairs.cu', 786, 911), ('gather', 'icikt_pairs.cu', 912, 944), ('tail/reduce', 'icikt_pairs.cu', 945, 1048)]
 agg = {}
 ts = te = 0
 for k, r in enumerate(data):
