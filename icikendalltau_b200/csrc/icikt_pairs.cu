@@ -535,6 +535,12 @@ constexpr bool kSmallInplace = ICIKT_SMALL_INPLACE != 0;
 #define ICIKT_LG_V2 1
 #endif
 constexpr int kLgV2 = ICIKT_LG_V2;
+// ICIKT_STAGED_GATHER: the in-place variant stages y's rank table in parts through the idle counter area
+// (staged_gather) and sorts x's first group with the large groups (large_groups_sorted2)
+#ifndef ICIKT_STAGED_GATHER
+#define ICIKT_STAGED_GATHER 1
+#endif
+constexpr bool kStagedGather = ICIKT_STAGED_GATHER != 0;
 template <bool G, bool RG>
 __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                         const int hist_words, const uint16_t* __restrict__ permX,
@@ -688,9 +694,15 @@ __device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr bu
                                                          const uint16_t* __restrict__ lg, const int nlg,
                                                          uint32_t* __restrict__ pre, uint32_t* __restrict__ list,
                                                          const int list_cap, uint32_t* descT, uint32_t* list_n,
-                                                         const int nwarps) {
+                                                         const int nwarps, const int first = 0,
+                                                         uint32_t* lead_out = nullptr) {
+  // `first` > 0: the first tie group of x (positions [0, first), usually its missing rows) was gathered in x
+  // order like everything else and is sorted here as one more group, ahead of the column's large groups; the
+  // rows with y's lowest rank (missing in both columns: by far the fullest counter) are counted by ballot and
+  // their number goes to *lead_out (the leading zero keys pass A skips)
   typedef Mem<G> M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  const int vfirst = first > 0 ? 1 : 0;
   uint32_t* grp = pre;         // start | size << 16 of the batch's groups (the table's own layout)
   uint32_t* slot0 = pre + 128;  // start - rows of the batch's earlier groups: where the group's first counter writes
   const uint32_t* lg32 = reinterpret_cast<const uint32_t*>(lg);
@@ -698,13 +710,14 @@ __device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr bu
   const int gb_max = max(1, min(128, bins_avail / K));  // groups per batch
   const int Kw = min(K, bins_avail);                    // ranks per window (< K only if gb_max == 1)
   uint32_t ties = 0;
-  for (int g0 = 0; g0 < nlg; g0 += gb_max) {
-    const int nb = min(gb_max, nlg - g0);
+  const int ng = nlg + vfirst;
+  for (int g0 = 0; g0 < ng; g0 += gb_max) {
+    const int nb = min(gb_max, ng - g0);
     uint32_t done = 0;  // rows of the (single) group written by earlier windows
     for (int k0 = 0; k0 < K; k0 += Kw) {
       const int kw = min(Kw, K - k0);
       const int bins = nb * kw, hw = (bins + 1) >> 1, wpt = (hw + T - 1) / T;
-      if (tid < nb) grp[tid] = __ldg(lg32 + g0 + tid);
+      if (tid < nb) grp[tid] = (g0 + tid < vfirst) ? ((uint32_t)first << 16) : __ldg(lg32 + g0 + tid - vfirst);
       if (tid == 0) *list_n = 0u;
       for (int w = tid; w < hw; w += T) M::st32(M::add(hist, w << 2), 0u);
       __syncthreads();
@@ -748,6 +761,25 @@ __device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr bu
         const uint32_t g = grp[j];
         const int t = (int)(g >> 16);
         if (t <= kWideGroup) continue;
+        if (vfirst && g0 + j == 0 && k0 == 0) {  // the first group: its rank-0 rows by ballot (warp-uniform trips)
+          uint32_t zeros = 0;
+          for (int qw = tid & ~31; qw < t; qw += T) {
+            const int q = qw + lane;
+            uint32_t r = 0xffffffffu;
+            if (q < t) {
+              if (RG && kw == K) {
+                r = M::ld16(M::add(buf, (int32_t)(q << 1)));
+              } else {
+                const uint32_t row = permX[q];
+                r = RG ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)));
+              }
+            }
+            zeros += __popc(__ballot_sync(FULL, r == 0u));
+            if (r != 0u && r < (uint32_t)kw) M::red_add32(M::add(hist, (int32_t)((r >> 1) << 2)), 1u << ((r & 1u) * 16u));
+          }
+          if (lane == 0 && zeros) M::red_add32(hist, zeros);
+          continue;
+        }
         for (int q = tid; q < t; q += T) add_row(j, (int)(g & 0xffffu), q);
       }
       for (int j = warp; j < nb; j += nwarps) {  // the others: one warp each
@@ -757,6 +789,7 @@ __device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr bu
         for (int q = lane; q < t; q += 32) add_row(j, (int)(g & 0xffffu), q);
       }
       __syncthreads();
+      if (vfirst && g0 == 0 && k0 == 0 && tid == 0 && lead_out) *lead_out = M::ld32(hist) & 0xffffu;
       // 2. rows per thread range of counters, block scan
       const int w0 = tid * wpt, w1 = min(w0 + wpt, hw);
       uint32_t mine = 0;
@@ -834,6 +867,59 @@ __device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr bu
     }
   }
   return ties;
+}
+
+// The gather of the in-place variant, seq[q] = rank_y[perm_x[q]] for ALL positions (the first group too: it is
+// sorted afterwards like a large group).  y's rank table does not fit beside the sequence, but the counter
+// area of the large groups is idle at this point: the table goes through it in parts of `part_rows` rows (one
+// TMA bulk copy each; two parts at 60 000 rows) and every part is one sweep over perm_x that fills in the
+// keys of the rows it holds -- shared-memory lookups instead of one 32-byte L2 sector per 2-byte rank.
+// Part 0 was requested by the caller (`mbar` has completed for it); the later parts are fetched here.
+__device__ __forceinline__ void staged_gather(const uint32_t seq, const uint32_t tbl, const int part_rows,
+                                              const uint16_t* __restrict__ permX,
+                                              const uint16_t* __restrict__ rankY_g, const int n, const int nstride,
+                                              const int cap, const uint32_t padA, const uint32_t mbar,
+                                              uint32_t& phase) {
+  typedef Mem<false> M;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const uint4* px8 = reinterpret_cast<const uint4*>(permX);
+  for (int base = 0; base < n; base += part_rows) {
+    const uint32_t rows = (uint32_t)min(part_rows, nstride - base);
+    if (base > 0) {
+      __syncthreads();  // every thread is done with the previous part
+      if (tid == 0) bulk_g2s(tbl, rankY_g + base, rows * 2u, mbar);
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+    }
+    auto rk = [&](const uint32_t row) -> uint32_t {
+      const uint32_t rel = row - (uint32_t)base;
+      return rel < rows ? M::ld16(tbl + (rel << 1)) : 0u;
+    };
+    for (int q8 = tid; q8 < (cap >> 3); q8 += T) {
+      const int q0 = q8 << 3;
+      uint32_t o[4];
+      if (q0 + 8 <= n) {
+        const uint4 pv = __ldg(px8 + q8);
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rk(pw[j] & 0xffffu) | (rk(pw[j] >> 16) << 16);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int qa = q0 + 2 * j, qb = qa + 1;
+          const uint32_t lo = (qa < n) ? rk(permX[qa]) : (base == 0 ? padA : 0u);
+          const uint32_t hi = (qb < n) ? rk(permX[qb]) : (base == 0 ? padA : 0u);
+          o[j] = lo | (hi << 16);
+        }
+      }
+      if (base > 0) {  // the keys of the earlier parts are in place
+        uint32_t a0, a1, a2, a3;
+        M::ld128(seq + (q0 << 1), a0, a1, a2, a3);
+        o[0] |= a0; o[1] |= a1; o[2] |= a2; o[3] |= a3;
+      }
+      M::st128(seq + (q0 << 1), o[0], o[1], o[2], o[3]);
+    }
+  }
 }
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -960,6 +1046,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   typedef Mem<G> M;
   constexpr bool RG = G || IP != 0;    // rank table not staged
   constexpr int AQ = IP != 0 ? 2 : 4;  // bytes of the pass-A buffers in units of cap
+  // in place: the rank table passes through the counter area in parts, the first group is sorted with the large ones
+  constexpr bool STG = IP != 0 && kStagedGather && kLgV2 >= 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
@@ -978,7 +1066,9 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
   const typename M::ptr bufA = region_base<G>(sm, p), bufB16 = M::add(bufA, 2 * cap);
   const uint32_t mbar = smem_addr(sm.unit_slot + 1);  // 8 bytes behind the unit slot
   uint32_t tma_phase = 0;
-  if (!RG && tid == 0) mbar_init(mbar, 1);
+  if ((!RG || STG) && tid == 0) mbar_init(mbar, 1);
+  const uint32_t stage_tbl = smem_addr(sm.region_ptr) + (uint32_t)(AQ * cap);  // STG: the counter area
+  const int stage_rows = min(p.nstride, ((p.region_bytes - AQ * cap) >> 1) & ~63);
   // (the first __syncthreads of the unit loop publishes the initialised barrier)
 
   for (;;) {
@@ -1013,6 +1103,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       // previous pair) as one TMA bulk copy, in flight during the mask counting below
       if (!RG && tid == 0)
         bulk_g2s(smem_addr(sm.region_ptr) + 2u * (uint32_t)cap, rankY_g, (uint32_t)p.nstride * 2u, mbar);
+      if (STG && tid == 0)  // first part of y's rank table into the idle counter area
+        bulk_g2s(stage_tbl, rankY_g, (uint32_t)min(stage_rows, p.nstride) * 2u, mbar);
       if (tid == 0) sm.mini[18] = 0u;  // leading zero keys of the sequence (set by the first-group emission)
       // joint-missing rows (b) and joint lowest group (g00, differs from b only if a column's
       // missing rows tie with its minimum)
@@ -1022,7 +1114,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         bpart += __popc(nb & sm.nabY[i]);
         if (absorbed) g00part += __popc(((XS.flags & 1) ? fbXg[i] : nb) & g0Yg[i]);
       }
-      if (!RG) {  // the rank table has landed (also on the early exit below: the barrier is reused)
+      if (!RG || STG) {  // the rank table has landed (also on the early exit below: the barrier is reused)
         mbar_wait(mbar, tma_phase);
         tma_phase ^= 1u;
       }
@@ -1066,7 +1158,7 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
         small_groups_direct<G, RG>(bufA, m, p.trow + (size_t)xcol * p.nstride, p.tord + (size_t)xcol * p.nstride,
                                    rank_tbl, rankY_g, accB, ties);
       // x's first tie group goes in already sorted by y; its joint ties with y fall out of it
-      if (f > 0) {
+      if (!STG && f > 0) {
         if (PW && XS.n_na > 0)
           ties += group_hist<G, true, true, RG>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, rankY_g, sm.mini,
                                                   sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
@@ -1081,7 +1173,9 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
                                          rank_tbl, p.rank + (size_t)xcol * p.nstride, sm.mini, sm.fmask,
                                          fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16, nwarps,
                                          p.gstart + (size_t)xcol * p.gstride, XS.n_na, pwx);
-      {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
+      if (STG) {
+        staged_gather(smem_addr(sm.region_ptr), stage_tbl, stage_rows, permX, rankY_g, n, p.nstride, cap, padA, mbar, tma_phase);
+      } else {  // seq[q] = rank_y[perm_x[q]] for q >= f, eight positions per thread and step
         auto rk = [&](uint32_t row) -> uint32_t {
           return RG ? (uint32_t)__ldg(rankY_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)));
         };
@@ -1116,13 +1210,13 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
       __syncthreads();
       if (RG && kSmallInplace && m > 0 && !by_pass_b)
         small_groups_inplace<G>(bufA, m, p.tord + (size_t)xcol * p.nstride, p.tpos + (size_t)xcol * p.nstride, accB, ties);
-      if (nlg > 0 && !by_pass_b) {
+      if ((nlg > 0 || (STG && f > 0)) && !by_pass_b) {
         // large tie groups of x: sorted by y in place (the counters live behind the two pass-A buffers)
         if (kLgV2 >= (RG ? 1 : 2))
           ties += large_groups_sorted2<G, RG>(bufA, M::add(bufA, AQ * cap), (p.region_bytes - AQ * cap) >> 2, permX, rank_tbl, rankY_g, YS.n_groups,
                                               p.lgrp + (size_t)xcol * kLargeStride, nlg,
                                               reinterpret_cast<uint32_t*>(sm.red), sm.fmask, fmask_words(nwarps, kkc) / 3,
-                                              sm.descT, sm.mini + 16, nwarps);
+                                              sm.descT, sm.mini + 16, nwarps, STG ? f : 0, sm.mini + 18);
         else
         ties += large_groups_sorted<G, RG>(bufA, M::add(bufA, AQ * cap), (p.region_bytes - AQ * cap) >> 2, permX, rank_tbl, rankY_g, YS.n_groups,
                                        p.lgrp + (size_t)xcol * kLargeStride, nlg,
@@ -1683,9 +1777,10 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n
       sh.warps = W = w;
       sh.kk = KK;
       sh.region_bytes = region;
-      if (tier == 1 && !getenv("ICIKT_INPLACE_SMALL_HIST")) {
-        // one CTA per SM either way: the rank counters of the large tie groups take all that is left
-        // (more groups per round)
+      if (!getenv("ICIKT_INPLACE_SMALL_HIST")) {
+        // one CTA per SM either way: the rank counters of the tie groups take all that is left (more groups
+        // per round); before that the area stages y's rank table for the gather (tier 0 as well: the first
+        // group is sorted there)
         const size_t fixed = tiled_smem_bytes(0, (int)wstride, fmask_words(w, KK << 3));
         sh.region_bytes = (int)((227 * 1024 - fixed) & ~size_t(15));
       }
