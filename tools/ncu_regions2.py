@@ -26,8 +26,8 @@ iS, iE = hdr.index('# Samples'), hdr.index('Instructions Executed')
 regions = [('count.cuh step4 (scatter)', 'icikt_count.cuh', 130, 235), ('count.cuh count_pass rest', 'icikt_count.cuh', 236, 420), ('count.cuh accessors', 'icikt_count.cuh', 1, 129),
            ('count_pass_inplace', 'icikt_pairs.cu', 160, 256),
            ('group_hist', 'icikt_pairs.cu', 257, 418), ('small_groups_direct', 'icikt_pairs.cu', 419, 470), ('small_groups_inplace', 'icikt_pairs.cu', 471, 510),
-           ('large_groups_sorted', 'icikt_pairs.cu', 511, 666),
-           ('kernel body: unit/masks', 'icikt_pairs.cu', 786, 911), ('gather', 'icikt_pairs.cu', 912, 944), ('tail/reduce', 'icikt_pairs.cu', 945, 1048)]
+           ('large_groups_sorted', 'icikt_pairs.cu', 511, 675), ('large_groups_sorted2', 'icikt_pairs.cu', 676, 868), ('staged_gather', 'icikt_pairs.cu', 869, 930),
+           ('kernel body: unit/masks', 'icikt_pairs.cu', 1040, 1170), ('gather', 'icikt_pairs.cu', 1171, 1208), ('tail/reduce', 'icikt_pairs.cu', 1209, 1320)]
 agg = {}
 ts = te = 0
 for k, r in enumerate(data):
