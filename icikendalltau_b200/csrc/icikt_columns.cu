@@ -124,6 +124,10 @@ __device__ __forceinline__ void block_sum_ll4(long long& a, long long& b, long l
 // Returns false without writing `out` when every key has the same digit (the order is unchanged):
 // count data and other low-entropy columns skip most of their passes.
 // cnt8: 16*T bytes, pre16: 16*T u16, misc: 64 words.  I <= 255.
+// WIDE (row ids in global memory): a thread's slice is a multiple of 4 ids and is read 8 bytes at a time --
+// lanes read at a stride of the slice length, so every 2-byte read would otherwise fetch its own 32-byte sector
+// (more ids per load would cost the registers that keep two CTAs on an SM).
+template <bool WIDE = false>
 __device__ __forceinline__ bool radix_pass(const unsigned char* src, const int stride_shift,
                                            const int shift, const uint16_t* in, uint16_t* out, const int n,
                                            unsigned char* cnt8, uint16_t* pre16, uint32_t* misc, const int T) {
@@ -132,9 +136,25 @@ __device__ __forceinline__ bool radix_pass(const unsigned char* src, const int s
   // each; the other threads only keep the barriers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
   const bool on = tid < T;
-  const int I = (n + T - 1) / T;
+  const int I = WIDE ? (((n + T - 1) / T + 3) & ~3) : (n + T - 1) / T;
   const int p0 = on ? min(tid * I, n) : n, p1 = min(p0 + I, n);
   const int boff = shift >> 3, bsh = shift & 4;
+  // four ids of the current order starting at position p (a multiple of 4); ids behind p1 are not used
+  auto ids4 = [&](const int p, uint32_t (&row)[4]) {
+    if (!in) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) row[u] = (uint32_t)(p + u);
+    } else if (p + 4 <= p1) {
+      const uint2 v = *reinterpret_cast<const uint2*>(in + p);
+      row[0] = v.x & 0xffffu;
+      row[1] = v.x >> 16;
+      row[2] = v.y & 0xffffu;
+      row[3] = v.y >> 16;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) row[u] = (p + u < p1) ? (uint32_t)in[p + u] : 0u;
+    }
+  };
   if (on) {  // zero this thread's 16 counters' worth of the array (128 bits per thread)
     uint4* z = reinterpret_cast<uint4*>(cnt8);
     z[tid] = make_uint4(0u, 0u, 0u, 0u);
@@ -144,6 +164,21 @@ __device__ __forceinline__ bool radix_pass(const unsigned char* src, const int s
   const uint32_t d0 = (src[((size_t)(in ? (uint32_t)in[0] : 0u) << stride_shift) + boff] >> bsh) & 15u;
   bool differs = false;
   unsigned char* mycnt = cnt8 + tid;
+  if (WIDE) {
+    for (int p = p0; p < p1; p += 4) {
+      uint32_t row[4], d[4];
+      ids4(p, row);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        d[u] = (p + u < p1) ? (src[((size_t)row[u] << stride_shift) + boff] >> bsh) & 15u : 16u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (d[u] < 16u) {
+          differs = differs || d[u] != d0;
+          mycnt[d[u] * T] += 1;
+        }
+    }
+  } else
   for (int p = p0; p < p1; p += 4) {
     uint32_t d[4];
 #pragma unroll
@@ -212,6 +247,22 @@ __device__ __forceinline__ bool radix_pass(const unsigned char* src, const int s
   }
   __syncthreads();
   uint16_t* mypre = pre16 + tid;
+  if (WIDE) {
+    for (int p = p0; p < p1; p += 4) {
+      uint32_t row[4], d[4];
+      ids4(p, row);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        d[u] = (p + u < p1) ? (src[((size_t)row[u] << stride_shift) + boff] >> bsh) & 15u : 16u;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (d[u] < 16u) {
+          const uint32_t slot = mypre[d[u] * T];
+          mypre[d[u] * T] = (uint16_t)(slot + 1u);
+          out[slot] = (uint16_t)row[u];
+        }
+    }
+  } else
   for (int p = p0; p < p1; p += 4) {
     uint32_t d[4], row[4];
 #pragma unroll
@@ -237,13 +288,14 @@ __device__ __forceinline__ bool radix_pass(const unsigned char* src, const int s
 
 // Sorts the rows of one column by the `nbits` key bits starting at bit0 (least significant digit
 // first); bufA / bufB ping-pong.  `cur` carries the order between calls (nullptr = identity).
+template <bool WIDE = false>
 __device__ __forceinline__ const uint16_t* radix_argsort(const unsigned char* src, int stride_shift, int bit0,
                                                          int nbits, const uint16_t* cur, uint16_t* bufA,
                                                          uint16_t* bufB, int n, unsigned char* cnt8,
                                                          uint16_t* pre16, uint32_t* misc, int T) {
   for (int b = bit0; b < bit0 + nbits; b += 4) {
     uint16_t* out = (cur == bufA) ? bufB : bufA;
-    if (radix_pass(src, stride_shift, b, cur, out, n, cnt8, pre16, misc, T)) cur = out;
+    if (radix_pass<WIDE>(src, stride_shift, b, cur, out, n, cnt8, pre16, misc, T)) cur = out;
   }
   return cur;
 }
@@ -287,6 +339,35 @@ __device__ __forceinline__ bool repair_equal_high_runs(const unsigned char* hi_s
             cur[p + 1] = (uint16_t)a;
             changed = true;
           }
+        }
+      }
+      if (changed) misc[9] = 1u;
+      __syncthreads();
+    }
+    const bool done = misc[9] == 0u;
+    __syncthreads();  // misc[9] is reset at the top of the next round
+    if (done) return true;
+  }
+  return false;
+}
+
+// The same for a column whose keys live in global memory (long columns): the pairs of a parity go to the
+// threads round-robin, so the ids are read coalesced, and a row's key is fetched once, all 64 bits.
+__device__ __forceinline__ bool repair_equal_high_runs_keys(const unsigned long long* __restrict__ keys, uint16_t* cur,
+                                                            const int n, uint32_t* misc, const int max_rounds) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int round = 0; round < max_rounds; ++round) {
+    if (tid == 0) misc[9] = 0u;
+    __syncthreads();
+    for (int parity = 0; parity < 2; ++parity) {
+      bool changed = false;
+      for (int p = parity + 2 * tid; p + 1 < n; p += 2 * T) {
+        const uint32_t a = cur[p], b = cur[p + 1];
+        const unsigned long long ka = keys[a], kb = keys[b];
+        if ((uint32_t)(ka >> 32) == (uint32_t)(kb >> 32) && (uint32_t)ka > (uint32_t)kb) {
+          cur[p] = (uint16_t)b;
+          cur[p + 1] = (uint16_t)a;
+          changed = true;
         }
       }
       if (changed) misc[9] = 1u;
@@ -621,9 +702,8 @@ int launch_column_fused(const double* d_data, int64_t ld, const double* d_global
 // Long columns (n > 8192): keys + sort in one kernel, one 1024-thread CTA per column.
 //   SM = true  (n <= kSortSmemRows): the keys' high words (the low words only if the repair of equal-high
 //              runs gives up) and both row-id buffers live in shared memory, 8 bytes per row;
-//   SM = false (longer): the same passes on global memory -- digits are read from the column's key
-//              array (480 KB at n = 60 000, L2 resident), the row ids ping-pong between `perm` and a
-//              scratch column.  Such shapes spend < 2 % of a job here.
+//   SM = false (longer): the row ids ping-pong between `perm` and a scratch column in global memory (L2), the
+//              byte of the keys a pair of passes sorts by is staged in shared memory (n bytes).
 // Writes the keys by row (keys_in), the sorted order (perm), the keys in sorted order (keys_out, what
 // column_rank_kernel walks) and the missing-row bit mask.
 constexpr int kSortThreads = 1024;
@@ -641,7 +721,8 @@ __global__ void __launch_bounds__(kSortThreads)
   uint32_t* part = reinterpret_cast<uint32_t*>(sort_smem);  // SM: [nstride] one half of every key, by row
   uint16_t* idA = SM ? reinterpret_cast<uint16_t*>(sort_smem + 4 * (size_t)nstride) : pm;
   uint16_t* idB = SM ? idA + nstride : vals + (size_t)col * nstride;
-  unsigned char* cnt8 = sort_smem + (SM ? 8 * (size_t)nstride : 0);
+  unsigned char* slice = sort_smem;  // !SM: [nstride] the byte of every key the current two passes sort by, by row
+  unsigned char* cnt8 = sort_smem + (SM ? 8 * (size_t)nstride : (size_t)nstride);
   uint16_t* pre16 = reinterpret_cast<uint16_t*>(cnt8 + 16 * kSortThreads);
   uint32_t* smisc = reinterpret_cast<uint32_t*>(cnt8 + 48 * kSortThreads);
   const int n32 = (n + 31) & ~31;
@@ -663,14 +744,26 @@ __global__ void __launch_bounds__(kSortThreads)
   // global memory: only neighbours with equal high words look there); all 64 bits only if the repair gives up
   const unsigned char* kb = reinterpret_cast<const unsigned char*>(kin);
   const unsigned char* pb = reinterpret_cast<const unsigned char*>(part);
-  const uint16_t* cur = SM ? radix_argsort(pb, 2, 0, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads)
-                           : radix_argsort(kb, 3, 32, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+  const uint16_t* cur = nullptr;
+  if (SM) {
+    cur = radix_argsort(pb, 2, 0, 32, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+  } else {
+    // long columns: a pass looks up the digit of 60 000 rows in sorted order -- one 32-byte L2 sector per byte
+    // if it reads the key array.  The byte the next two passes need is copied to shared memory first (one
+    // coalesced sweep over the keys), and the passes read it there.
+    for (int byte = 4; byte < 8; ++byte) {
+      for (int r = tid; r < n; r += kSortThreads) slice[r] = (unsigned char)(kin[r] >> (8 * byte));
+      __syncthreads();
+      cur = radix_argsort<true>(slice, 0, 0, 8, cur, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+      __syncthreads();  // the slice is rewritten
+    }
+  }
   if (!cur) {
     fill_identity(idA, n);
     cur = idA;
   }
   const bool repaired = SM ? repair_equal_high_runs(pb, 2, 0, kb, 3, 0, const_cast<uint16_t*>(cur), n, smisc, kSortThreads, kRepairRounds)
-                           : repair_equal_high_runs(kb, 3, 4, kb, 3, 0, const_cast<uint16_t*>(cur), n, smisc, kSortThreads, kRepairRounds);
+                           : repair_equal_high_runs_keys(kin, const_cast<uint16_t*>(cur), n, smisc, kRepairRounds);
   if (!repaired) {
     if (SM) {
       for (int r = tid; r < n; r += kSortThreads) part[r] = (uint32_t)kin[r];
@@ -681,7 +774,7 @@ __global__ void __launch_bounds__(kSortThreads)
       __syncthreads();
       cur = radix_argsort(pb, 2, 0, 32, cur, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
     } else {
-      cur = radix_argsort(kb, 3, 0, 64, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
+      cur = radix_argsort<true>(kb, 3, 0, 64, nullptr, idA, idB, n, cnt8, pre16, smisc, kSortThreads);
     }
   }
   __syncthreads();
@@ -953,7 +1046,7 @@ int launch_columns(const double* d_data, int64_t ld, const double* d_global_na, 
     return launches + l;  // the fused kernel computes the pass-A constants itself
   } else {
     const bool sm = n <= kSortSmemRows && !getenv("ICIKT_SORT_GLOBAL");
-    const size_t smem = (sm ? 8 * (size_t)nstride : 0) + sort_counter_bytes(kSortThreads);
+    const size_t smem = (sm ? 8 * (size_t)nstride : (size_t)nstride) + sort_counter_bytes(kSortThreads);
     if (sm) {
       if (cudaFuncSetAttribute(column_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
       column_sort_kernel<true><<<C, kSortThreads, smem, stream>>>(d_data, ld, n, nstride, wstride, d_global_na, n_global_na,
