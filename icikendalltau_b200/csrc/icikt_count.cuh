@@ -187,6 +187,11 @@ struct Mem<false> {
   static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(p), "r"(v) : "memory");
   }
+  static __device__ __forceinline__ uint32_t atom_or32(ptr p, uint32_t v) {  // returns the old word
+    uint32_t old;
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(p), "r"(v) : "memory");
+    return old;
+  }
   static __device__ __forceinline__ ptr from_shared(const void* q) { return smem_addr(q); }
   static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(p), "h"((unsigned short)v) : "memory");
@@ -232,6 +237,7 @@ struct Mem<true> {
     acc2 += qs >> 16;
   }
   static __device__ __forceinline__ void red_add32(ptr p, uint32_t v) { atomicAdd(reinterpret_cast<uint32_t*>(p), v); }
+  static __device__ __forceinline__ uint32_t atom_or32(ptr p, uint32_t v) { return atomicOr(reinterpret_cast<uint32_t*>(p), v); }
   // generic addressing reaches shared memory too
   static __device__ __forceinline__ ptr from_shared(const void* q) { return (ptr) const_cast<void*>(q); }
   static __device__ __forceinline__ void st16(ptr p, uint32_t v) {
