@@ -23,11 +23,11 @@ skip = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 rows = rows[starts[skip]:starts[skip + 1]]
 hdr, data = rows[1], [r for r in rows[2:] if len(r) > 10]
 iS, iE = hdr.index('# Samples'), hdr.index('Instructions Executed')
-regions = [('count.cuh step4 (scatter)', 'icikt_count.cuh', 130, 235), ('count.cuh count_pass rest', 'icikt_count.cuh', 236, 420), ('count.cuh accessors', 'icikt_count.cuh', 1, 129),
+regions = [('count.cuh step4 (scatter)', 'icikt_count.cuh', 130, 240), ('count.cuh count_pass rest', 'icikt_count.cuh', 241, 430), ('count.cuh accessors', 'icikt_count.cuh', 1, 129),
            ('count_pass_inplace', 'icikt_pairs.cu', 160, 256),
-           ('group_hist', 'icikt_pairs.cu', 257, 418), ('small_groups_direct', 'icikt_pairs.cu', 419, 470), ('small_groups_inplace', 'icikt_pairs.cu', 471, 510),
-           ('large_groups_sorted', 'icikt_pairs.cu', 511, 675), ('large_groups_sorted2', 'icikt_pairs.cu', 676, 868), ('staged_gather', 'icikt_pairs.cu', 869, 930),
-           ('kernel body: unit/masks', 'icikt_pairs.cu', 1040, 1170), ('gather', 'icikt_pairs.cu', 1171, 1208), ('tail/reduce', 'icikt_pairs.cu', 1209, 1320)]
+           ('group_hist', 'icikt_pairs.cu', 257, 482), ('small_groups_direct', 'icikt_pairs.cu', 483, 543), ('small_groups_inplace', 'icikt_pairs.cu', 544, 589),
+           ('large_groups_sorted', 'icikt_pairs.cu', 590, 750), ('large_groups_sorted2', 'icikt_pairs.cu', 751, 944), ('staged_gather', 'icikt_pairs.cu', 945, 998),
+           ('kernel body: unit/masks', 'icikt_pairs.cu', 1119, 1250), ('gather', 'icikt_pairs.cu', 1251, 1284), ('tail/reduce', 'icikt_pairs.cu', 1285, 1392)]
 agg = {}
 ts = te = 0
 for k, r in enumerate(data):

@@ -6,10 +6,10 @@ mkdir -p gpurun_out
 T=r02z
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.txt 2>&1; echo smoke_exit=$?; tail -1 gpurun_out/${T}_smoke.txt
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${T}_pytest_gpu.log 2>&1; echo pytest_exit=$? >> gpurun_out/${T}_pytest_gpu.log; tail -4 gpurun_out/${T}_pytest_gpu.log
-timeout 400 python tools/fuzz.py 120 777 > gpurun_out/${T}_fuzz.txt 2>&1; tail -3 gpurun_out/${T}_fuzz.txt
+timeout 400 python tools/fuzz.py 80 777 > gpurun_out/${T}_fuzz.txt 2>&1; tail -3 gpurun_out/${T}_fuzz.txt
 timeout 900 python bench.py > gpurun_out/${T}_bench_target.json 2> gpurun_out/${T}_bench_target.err; echo bench_exit=$?
 for wl in config1 config2 config3 config4 config5; do
-timeout 900 python bench.py --workload $wl > gpurun_out/${T}_bench_$wl.json 2> gpurun_out/${T}_bench_$wl.err; echo $wl exit=$?
+timeout 900 python bench.py --workload $wl --cpu-budget 8 > gpurun_out/${T}_bench_$wl.json 2> gpurun_out/${T}_bench_$wl.err; echo $wl exit=$?
 done
 for wl in target config1 config2 config3 config4 config5; do
 python - <<PY
