@@ -259,6 +259,11 @@ __device__ __forceinline__ void count_pass_inplace(const uint32_t a, const int n
 #define ICIKT_BITMAP_EMIT 1
 #endif
 constexpr bool kBitmapEmit = ICIKT_BITMAP_EMIT != 0;
+// ICIKT_BITMAP_BY_MASK: the fast path walks the group's membership mask instead of its row list
+#ifndef ICIKT_BITMAP_BY_MASK
+#define ICIKT_BITMAP_BY_MASK 1
+#endif
+constexpr bool kBitmapByMask = ICIKT_BITMAP_BY_MASK != 0;
 struct PwSide {
   unsigned long long S = 0;   // sum over the group's rows of (present rows of the other column below it)
   unsigned long long T = 0;   // ties of the group's present rows in the other column, sum C(count, 2)
@@ -295,7 +300,9 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
                                                uint32_t* __restrict__ mini, uint32_t* __restrict__ list,
                                                const int list_cap, uint32_t* descT, uint32_t* list_n,
                                                const int nwarps, const uint16_t* __restrict__ gstart,
-                                               const int a_tbl, PwSide& pw, const bool try_bits = false) {
+                                               const int a_tbl, PwSide& pw, const bool try_bits = false,
+                                               const uint32_t* __restrict__ grp_bits = nullptr,
+                                               const uint32_t* nab_other = nullptr, const int nwords = 0) {
   typedef Mem<G> M;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
   int hw = (cap - ((keep + 1) & ~1)) >> 1;         // counter words available above the kept slots
@@ -315,7 +322,32 @@ __device__ __forceinline__ uint32_t group_hist(typename Mem<G>::ptr buf, const i
     for (int w = tid; w < bw; w += T) M::st32(M::add(bits, w << 2), 0u);
     if (tid == 0) mini[17] = 0u;
     __syncthreads();
-    {
+    if (kBitmapByMask && grp_bits) {
+      // the group's rows from its membership mask instead of its list: the rows that are also missing in the
+      // other column (nab_other; most of x's missing rows at correlated missingness) have its lowest rank and
+      // are only counted -- one popcount per word -- and only the others look their rank up
+      uint32_t zeros = 0;
+      bool dup = false;
+      for (int i = tid; i < nwords; i += T) {
+        const uint32_t g = __ldg(grp_bits + i), nb = nab_other[i];
+        zeros += __popc(g & nb);
+        uint32_t m = g & ~nb;
+        while (m) {
+          const uint32_t row = (uint32_t)(i << 5) + (uint32_t)__ffs((int)m) - 1u;
+          m &= m - 1u;
+          const uint32_t r = GT ? (uint32_t)__ldg(rank_g + row) : M::ld16(M::add(rank_tbl, (int32_t)(row << 1)));
+          if (r == 0u) {
+            ++zeros;
+          } else {
+            const uint32_t bit = 1u << (r & 31u);
+            dup = dup || (M::atom_or32(M::add(bits, (int32_t)((r >> 5) << 2)), bit) & bit) != 0u;
+          }
+        }
+      }
+      zeros = __reduce_add_sync(FULL, zeros);
+      if (lane == 0 && zeros) atomicAdd(mini + 18, zeros);
+      if (dup) mini[17] = 1u;
+    } else {
       const uint4* px8 = reinterpret_cast<const uint4*>(rows);
       const int lim8 = (nrows + 7) >> 3;
       uint32_t zeros = 0;
@@ -1241,7 +1273,8 @@ __global__ void __launch_bounds__(MAXT, MINB) pairs_tiled_kernel(const TiledPara
           ties += group_hist<G, true, false, RG>(bufA, cap, f, f, YS.n_groups, permX, rank_tbl, rankY_g, sm.mini,
                                                    sm.fmask, fmask_words(nwarps, kkc) / 3, sm.descT, sm.mini + 16,
                                                    nwarps, nullptr, 0, pwy,
-                                                   8 * YS.n_tied <= n);  // y (nearly) tie-free: one bit per rank
+                                                   8 * YS.n_tied <= n,  // y (nearly) tie-free: one bit per rank
+                                                   fbXg, sm.nabY, nwords);
       }
       if (PW && YS.n_na > 0)  // the missing rows of y over the ranks of x (read from global memory)
         group_hist<G, false, true, true>(bufA, cap, f, YS.n_na, XS.n_groups, p.perm + (size_t)ycol * p.nstride,
