@@ -24,10 +24,10 @@ rows = rows[starts[skip]:starts[skip + 1]]
 hdr, data = rows[1], [r for r in rows[2:] if len(r) > 10]
 iS, iE = hdr.index('# Samples'), hdr.index('Instructions Executed')
 regions = [('count.cuh step4 (scatter)', 'icikt_count.cuh', 130, 240), ('count.cuh count_pass rest', 'icikt_count.cuh', 241, 430), ('count.cuh accessors', 'icikt_count.cuh', 1, 129),
-           ('count_pass_inplace', 'icikt_pairs.cu', 160, 256),
-           ('group_hist', 'icikt_pairs.cu', 257, 482), ('small_groups_direct', 'icikt_pairs.cu', 483, 543), ('small_groups_inplace', 'icikt_pairs.cu', 544, 589),
-           ('large_groups_sorted', 'icikt_pairs.cu', 590, 750), ('large_groups_sorted2', 'icikt_pairs.cu', 751, 944), ('staged_gather', 'icikt_pairs.cu', 945, 998),
-           ('kernel body: unit/masks', 'icikt_pairs.cu', 1119, 1250), ('gather', 'icikt_pairs.cu', 1251, 1284), ('tail/reduce', 'icikt_pairs.cu', 1285, 1392)]
+           ('count_pass_inplace', 'icikt_pairs.cu', 160, 255),
+           ('group_hist', 'icikt_pairs.cu', 256, 514), ('small_groups_direct', 'icikt_pairs.cu', 515, 575), ('small_groups_inplace', 'icikt_pairs.cu', 576, 621),
+           ('large_groups_sorted', 'icikt_pairs.cu', 622, 782), ('large_groups_sorted2', 'icikt_pairs.cu', 783, 976), ('staged_gather', 'icikt_pairs.cu', 977, 1030),
+           ('kernel body: unit/masks', 'icikt_pairs.cu', 1151, 1283), ('gather', 'icikt_pairs.cu', 1284, 1317), ('tail/reduce', 'icikt_pairs.cu', 1318, 1425)]
 agg = {}
 ts = te = 0
 for k, r in enumerate(data):
