@@ -1010,3 +1010,31 @@ def test_pipelined_matrices_match_plain_call(monkeypatch):
         np.testing.assert_array_equal(piped[k], plain[k], err_msg=k)
     np.testing.assert_array_equal(piped["status_counts"], plain["status_counts"])
     assert piped["max_taumax"] == plain["max_taumax"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [700, 9000, 30000])
+def test_first_group_bitmap_fallback_on_shared_ranks(n):
+    """The first-group emission keeps one BIT per rank of the other column when that column is nearly tie-free
+    (fewer than n/8 tied rows); two rows of the group that do share a rank must send the pair through the
+    counter path instead.  Columns: x left-censored, y continuous except for a few duplicated values planted on
+    rows that are missing in x (the collision), z with its duplicates on rows present in x (no collision), w with
+    its minimum tied and no missing rows (rank 0 is a real value there)."""
+    rng = np.random.default_rng(n)
+    base = rng.normal(size=n)
+    x = base + 0.3 * rng.normal(size=n)
+    x[x < np.quantile(x, 0.3)] = np.nan
+    miss = np.flatnonzero(np.isnan(x))
+    pres = np.flatnonzero(~np.isnan(x))
+    y = base + 0.5 * rng.normal(size=n)
+    y[miss[1:40:2]] = y[miss[0:39:2][: len(miss[1:40:2])]]       # pairs of equal values inside x's missing rows
+    y[miss[50:53]] = y[miss[49]]                                  # and one run of four
+    y[rng.choice(n, n // 10, replace=False)] = np.nan             # y has missing rows of its own (rank 0 = missing)
+    z = base + 0.5 * rng.normal(size=n)
+    z[pres[1:40:2]] = z[pres[0:39:2][: len(pres[1:40:2])]]
+    w = rng.normal(size=n)
+    w[miss[:5]] = w.min() - 1.0                                   # five rows of x's first group share w's lowest rank
+    data = np.asfortranarray(np.stack([x, y, z, w, base], axis=1))
+    for persp in ("global", "local"):
+        got = ik.run_pairs(data, (), perspective=persp, want_counts=True)
+        assert_parity(got, oracle_pairs(data, perspective=persp), f"bitmap fallback n={n} {persp}")
