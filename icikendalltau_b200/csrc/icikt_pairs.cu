@@ -791,7 +791,13 @@ __device__ __forceinline__ uint32_t large_groups_sorted(typename Mem<G>::ptr buf
 //   * runs of kListRun (16) keys and more are parked in the list, longer ones in pieces of kRunPiece, and every
 //     list entry is written by one warp (the CTA-wide loop spent 28 loop headers per entry).
 // `pre` = 256 words of shared memory: [0,128) the packed group table, [128,256) the output slots.
-constexpr int kWideGroup = 512, kListRun = 16, kRunPiece = 512;
+#ifndef ICIKT_WIDE_GROUP
+#define ICIKT_WIDE_GROUP 512
+#endif
+#ifndef ICIKT_LIST_RUN
+#define ICIKT_LIST_RUN 16
+#endif
+constexpr int kWideGroup = ICIKT_WIDE_GROUP, kListRun = ICIKT_LIST_RUN, kRunPiece = 512;
 template <bool G, bool RG>
 __device__ __forceinline__ uint32_t large_groups_sorted2(typename Mem<G>::ptr buf, typename Mem<G>::ptr hist,
                                                          const int hist_words, const uint16_t* __restrict__ permX,
