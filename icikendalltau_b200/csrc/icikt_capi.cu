@@ -1,6 +1,9 @@
 // icikt_capi.cu -- host side of libicikt_b200.so: the C ABI declared in include/icikt_b200.h.
-// Owns device memory, the stream, the pair-unit table and the CUDA-event timings; all
+// Owns device memory, the streams, the pair-unit table and the CUDA-event timings; all
 // arithmetic lives in icikt_columns.cu / icikt_pairs.cu.  There is no CPU fallback.
+// Large all-pairs jobs of the one-shot entry points are pipelined (build_stage_table, run_staged):
+// column chunks upload behind the pair launches of earlier chunks, finished row blocks of the
+// results leave behind later ones.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

@@ -32,6 +32,14 @@
 //   in ascending y order by the same histogram technique (large_groups_sorted).  Pass B
 //   (bucket_pass: one-bit levels on the composite key with explicit bucket boundaries, ballot +
 //   clz) survives only as tier 2, for columns with very many large groups x distinct values.
+//   When y is (nearly) tie-free the first group's histogram shrinks to ONE BIT per rank, set from the
+//   membership masks (popc(first_x & missing_y) rows are only counted), see group_hist.
+//   Long vectors (the in-place variant, IP != 0) order the work differently: staged_gather fills
+//   every position through a rank table that passes through the idle counter area in TMA parts,
+//   small_groups_inplace compares on the sequence itself, large_groups_sorted2 sorts the first
+//   group together with the large ones.  Those routines exist only in the long-vector
+//   instantiations: the same edits in the short-vector kernel cost it 2-3 % through register
+//   allocation (profiles/r02_build_variants_ab.txt).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

@@ -50,6 +50,15 @@ def test_no_cpu_fallback():
         ik.ici_kt(x[:, 0], x[:, 1])
     with pytest.raises(ik.IciktError):
         ik.Plan(20, 3)
+    # a job large enough for the pipelined one-shot call (>= 32 MB, >= 128 columns) fails the same way, before
+    # any stream or staging buffer exists
+    big = np.zeros((16500, 256), order="F")
+    with pytest.raises(ik.IciktError) as e:
+        ik.run_pairs(big)
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(ik.IciktError) as e:
+        _lib.run_matrices(big, want=("raw",))
+    assert e.value.code == _lib.ERR_NO_DEVICE
 
 
 def test_argument_errors_before_any_device_work():
