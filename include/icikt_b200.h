@@ -99,7 +99,10 @@ typedef struct icikt_opts {
   int64_t pair_hi;      /* output arrays are still indexed from 0 = pair_lo.  0,0 = all.  */
 } icikt_opts;
 
-typedef struct icikt_timings { /* milliseconds, CUDA events on the library's stream */
+/* A pipelined one-shot call (see icikt_stage_table) overlaps the copies with the kernels: columns_ms,
+ * pairs_ms and epilogue_ms are then sums over its launches, h2d_ms runs from the start of the call until
+ * the last column has landed, d2h_ms from the first result copy to the last, and the parts exceed total_ms. */
+typedef struct icikt_timings { /* milliseconds, CUDA events on the library's streams */
   float h2d_ms;      /* host -> device copy of the data matrix                        */
   float columns_ms;  /* per-column preprocessing kernels (K1)                         */
   float pairs_ms;    /* pair kernel (K2) alone                                        */
