@@ -1899,7 +1899,7 @@ TiledShape tiled_shape(int64_t n, int tier, int64_t wstride, int n_sm, int64_t n
       sh.warps = W = w;
       sh.kk = KK;
       sh.region_bytes = region;
-      if (!getenv("ICIKT_INPLACE_SMALL_HIST")) {
+      {
         // one CTA per SM either way: the rank counters of the tie groups take all that is left (more groups
         // per round); before that the area stages y's rank table for the gather (tier 0 as well: the first
         // group is sorted there)

@@ -12,4 +12,3 @@ run $PWD/icikendalltau_b200/variant_base.so config4 base
 run $PWD/icikendalltau_b200/libicikt_b200.so config4 new
 done
 run $PWD/icikendalltau_b200/libicikt_b200.so target new
-ICIKT_INPLACE_SMALL_HIST=1 run $PWD/icikendalltau_b200/libicikt_b200.so config4 new_smallhist
