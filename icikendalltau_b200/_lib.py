@@ -32,7 +32,7 @@ EXPORTS = [
     "icikt_pair_from_index", "icikt_all_pairs_multi", "icikt_matrices", "icikt_plan_download_matrices",
     "icikt_pairwise_completeness", "icikt_plan_upload_columns", "icikt_plan_columns_range",
     "icikt_plan_tables", "icikt_plan_columns_finish", "icikt_measure_issue_rate",
-    "icikt_matrices_multi", "icikt_stage_table",
+    "icikt_matrices_multi", "icikt_stage_table", "icikt_launch_shape",
 ]
 NSTATUS = 10
 
@@ -163,6 +163,8 @@ def load():
     L.icikt_stage_table.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                     _lp, ctypes.c_int64, _lp, _lp]
     L.icikt_stage_table.restype = ctypes.c_int64
+    L.icikt_launch_shape.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _ip]
+    L.icikt_launch_shape.restype = ctypes.c_int
     _lib = L
     return L
 
@@ -452,6 +454,15 @@ def stage_table(C, include_diag=False, cta_slots=296, n_blocks=8):
     L.icikt_stage_table(C, int(bool(include_diag)), cta_slots, n_blocks, nu, units.ctypes.data, nl.value,
                         launches.ctypes.data, ctypes.byref(nl))
     return units[:nu], launches[:nl.value]
+
+
+def launch_shape(n, tier=0, n_sm=148, complete_obs=False):
+    """The pair kernel's launch shape for n rows (host only): dict(warps, runs, region_bytes, variant, cap, stage_rows);
+    variant: 'smem' two sequence buffers in shared memory, 'inplace', 'gmem' global scratch."""
+    out = np.zeros(8, dtype=np.int32)
+    check(load().icikt_launch_shape(int(n), int(tier), int(n_sm), int(bool(complete_obs)), out.ctypes.data))
+    return dict(warps=int(out[0]), runs=int(out[1]), region_bytes=int(out[2]),
+                variant=("smem", "inplace", "gmem")[int(out[3])], cap=int(out[4]), stage_rows=int(out[5]))
 
 
 def pair_from_index(C, index, include_diag=False):

@@ -1339,6 +1339,22 @@ int64_t icikt_stage_table(int64_t C, int32_t include_diag, int32_t cta_slots, in
   return (int64_t)U.size();
 }
 
+int icikt_launch_shape(int64_t n, int32_t tier, int32_t n_sm, int32_t complete_obs, int32_t* out) {
+  if (n < 1 || n > tiled_max_n() || tier < 0 || tier > 2 || n_sm < 1 || !out)
+    return fail(ICIKT_ERR_BAD_ARG, "bad launch shape arguments");
+  const int64_t nwords = ((n + 31) & ~31LL) / 32, wstride = (nwords + 3) & ~3LL;
+  const TiledShape sh = tiled_shape(n, tier, wstride, n_sm, 0, complete_obs == 0);
+  const int cap = sh.warps * sh.kk * 256;
+  out[0] = sh.warps;
+  out[1] = sh.kk;
+  out[2] = sh.region_bytes;
+  out[3] = sh.inplace_kk != 0 ? 1 : (sh.gmem ? 2 : 0);
+  out[4] = cap;
+  // in place: rows of the other column's rank table one staging part holds (the counter area behind the sequence)
+  out[5] = sh.inplace_kk != 0 ? (int)std::min<int64_t>((n + 63) & ~63LL, ((sh.region_bytes - 2 * cap) >> 1) & ~63) : 0;
+  return ICIKT_OK;
+}
+
 int icikt_measure_smem_bandwidth(int32_t device, double* g32, double* g128) {
   int rc = select_device(device);
   if (rc != ICIKT_OK) return rc;
